@@ -1,0 +1,187 @@
+/*
+ * sosat_b200.h -- C-ABI of libsosat_b200.so: the B200 (sm_100a) implementation of the
+ * sosat_optics beam-simulation hot path (ray trace feed -> source plane, near-field
+ * binning, far-field transform).
+ *
+ * The reference (McMahonCosmologyGroup/sosat_optics) is pure Python and has no FFI; the
+ * boundary it exposes is the Python function surface its notebooks call.  Each entry point
+ * below names the reference function (file:line, relative to the reference checkout) whose
+ * arithmetic it replaces.  sosat_optics_b200/{ray_trace,opt_analyze}.py bind these with
+ * ctypes under the reference's own function names; INTEGRATION.md shows the stub a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - plain C types only; pointers named d_* are DEVICE pointers, h_* are HOST pointers.
+ *   - every function returns 0 on success or a negative sosat_status_t; the message is
+ *     available from sosat_last_error() (thread-local).
+ *   - functions taking a stream are asynchronous on it (stream = cudaStream_t as void*;
+ *     NULL = legacy default stream).  The *_host convenience calls are synchronous.
+ *   - the caller owns every buffer.  The library keeps only the per-device geometry in
+ *     __constant__ memory (sosat_set_geometry) and allocates nothing persistent; the
+ *     *_host calls allocate and free their own temporaries.
+ *   - numerical invalidity is not an error: an invalid ray gets amplitude = OPL = 0 exactly
+ *     like ray_trace.py:1578-1580.
+ *   - there is no CPU fallback anywhere in this library.
+ */
+#ifndef SOSAT_B200_H
+#define SOSAT_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define SOSAT_ABI_VERSION 1
+#define SOSAT_NUM_SURFACES 6
+#define SOSAT_OUT_ROWS 17 /* ray_trace.py:1095  out = np.zeros((17, n_pts)) */
+#define SOSAT_MAX_FREQS 64
+
+typedef enum {
+    SOSAT_OK = 0,
+    SOSAT_ERR_INVALID_ARG = -1,
+    SOSAT_ERR_CUDA = -2,
+    SOSAT_ERR_NO_GEOMETRY = -3,
+    SOSAT_ERR_UNSUPPORTED = -4,
+    SOSAT_ERR_NO_DEVICE = -5
+} sosat_status_t;
+
+/* One refracting surface, in trace order 3b,3a,2b,2a,1b,1a.
+ * sag_mm(x,y) = 10*[c r^2/(1+sqrt(1-(1+k)c^2 r^2)) + a1 r^2 + a2 r^4 + a3 r^6], r in cm
+ * (ot_geo.py:49-91,182-227,313-354; slopes :94-143,230-276,364-414).  The surface frame is
+ * the tele frame translated to y0 and rotated by pi/2 about x (ot_geo.py:162-179 etc.). */
+typedef struct {
+    double c, k, a1, a2, a3;
+    double y0;          /* vertex position on the tele y axis [mm] (ot_geo.py:43-46)        */
+    double n_in, n_out; /* refractive index before / after the surface (ot_geo.py:13-14)    */
+    double t_lo, t_hi;  /* the reference's brentq bracket [mm] (ray_trace.py:1130,1198,...) */
+} sosat_surface_t;
+
+/* Frequency-independent optics (SatGeo + ot_geo module constants). */
+typedef struct {
+    sosat_surface_t surf[SOSAT_NUM_SURFACES];
+    double y_lyot;    /* ot_geo.py:46                                              */
+    double y_source;  /* SatGeo.y_source (ot_geo.py:29)                            */
+    double clip_l3;   /* 392/2 mm: lens-3 clip, strict >= (ray_trace.py:1138)      */
+    double clip_stop; /* 210 mm: Lyot-stop and lens-2a clip, <= (ray_trace.py:1569) */
+    double cone;      /* 0.4 rad launch half-cone (ray_trace.py:1086-1087)         */
+} sosat_geom_t;
+
+/* Per-frequency feed/phase parameters (SatGeo.th_fwhp_x, th_fwhp_y, k). */
+typedef struct {
+    double fwhp_x;    /* rad; divides de_ho (ray_trace.py:1575) */
+    double fwhp_y;    /* rad; divides de_ve                      */
+    double k_over_2e3;/* SatGeo.k / 1e3 / 2: phase per mm of OPL (ray_trace.py:1601) */
+} sosat_freq_t;
+
+/* Diagnostics accumulated by the tracer (device array of SOSAT_NUM_STATS doubles). */
+enum {
+    SOSAT_STAT_N_VALID = 0,  /* rays with amplitude != 0                          */
+    SOSAT_STAT_SUM_OPL = 1,  /* sum of OPL over valid rays [mm]                    */
+    SOSAT_STAT_SUM_DX = 2,   /* sum of exit direction x,y,z over valid rays        */
+    SOSAT_STAT_SUM_DY = 3,
+    SOSAT_STAT_SUM_DZ = 4,
+    SOSAT_STAT_N_SLOW = 5,   /* rays re-solved with the bracketed (Brent) slow path */
+    SOSAT_STAT_N_BRACKET_FAIL = 6, /* solves where the reference's brentq would raise */
+    SOSAT_STAT_N_BINNED = 7, /* valid rays that landed inside the bin grid          */
+    SOSAT_NUM_STATS = 8
+};
+
+/* ---- library / device ------------------------------------------------------------- */
+int sosat_abi_version(void);
+const char *sosat_last_error(void);
+int sosat_device_count(void);
+int sosat_set_device(int device);
+/* name: >= 256 bytes; sm: compute capability major*10+minor; n_sm: multiprocessors */
+int sosat_device_info(char *name, int *sm, int *n_sm, size_t *mem_bytes);
+
+/* ---- geometry (ot_geo.py:8-46) ------------------------------------------------------ */
+/* Copies *h_geom into the current device's __constant__ memory (async on stream). */
+int sosat_set_geometry(const sosat_geom_t *h_geom, void *stream);
+
+/* ---- stage 1: ray trace (ray_trace.py:1070-1591 rx_to_lyot) ------------------------- */
+/* Rays ii in [ray_begin, ray_end) of the n_scan x n_scan launch grid, ii = iphi*n_scan +
+ * itheta (ray_trace.py:1086-1091), from feed position h_rx[3] (tele frame, mm).
+ * d_out: [17][ray_end-ray_begin] row-major float64, rows as ray_trace.py:1558-1588
+ * (0-2 pos_ap, 3 OPL, 4 amplitude, 5-7 last normal, 8-10 exit direction, 11-16 zero).
+ * d_stats: SOSAT_NUM_STATS doubles, accumulated into (caller zeroes), may be NULL. */
+int sosat_trace_rays(const double *h_rx, const sosat_freq_t *h_freq, int n_scan,
+                     int64_t ray_begin, int64_t ray_end, double *d_out, double *d_stats,
+                     void *stream);
+
+/* Host-buffer form of the same call: h_out is [17][n] float64 host memory.  Synchronous. */
+int sosat_rx_to_lyot_host(const sosat_geom_t *h_geom, const double *h_rx,
+                          const sosat_freq_t *h_freq, int n_scan, int64_t ray_begin,
+                          int64_t ray_end, double *h_out, double *h_stats);
+
+/* ---- stage 1b: getNearField post-processing (ray_trace.py:1594-1614) ---------------- */
+/* From d_out (layout above, n rays) computes, for every ray, x_sim = out[0]/10,
+ * y_sim = out[2]/10, a_sim = out[4], p_sim = mod(k (OPL - <OPL>)/1e3/2, 2 pi) - <p>, where
+ * the means run over rays with out[4] != 0, and d_mask[i] = (out[4][i] != 0).
+ * d_xyap: [4][n] float64 (x, y, a, p); d_tan_og: 3 doubles (mean exit direction);
+ * d_work: SOSAT_NUM_STATS doubles of scratch.  Compaction by d_mask is the caller's. */
+int sosat_near_field_arrays(const double *d_out, int64_t n, double k, double *d_xyap,
+                            uint8_t *d_mask, double *d_tan_og, double *d_work,
+                            void *stream);
+
+/* ---- stage 1c: fused trace + near-field binning (north_star) -- */
+/* Traces launch rows iphi in [row_begin, row_end) (all itheta) for n_rx feed positions
+ * (d_rx: [n_rx][3] device doubles) and n_freq <= SOSAT_MAX_FREQS frequencies, and
+ * accumulates, per (rx, freq), sum a*cos(p), sum a*sin(p) and the ray count into
+ * grid_n x grid_n float32 planes covering [-extent_mm/2, extent_mm/2)^2 of the source
+ * plane: row index = tele z (reference y_sim), column index = tele x (x_sim).
+ * p = k_over_2e3 * (OPL - opl_ref).  Planes are accumulated into (caller zeroes):
+ *   d_re, d_im: [n_rx][n_freq][grid_n][grid_n];  d_cnt: [n_rx][grid_n][grid_n];
+ *   d_stats:    [n_rx][SOSAT_NUM_STATS] doubles.
+ * d_re/d_im/d_cnt may all be NULL to accumulate the statistics only. */
+int sosat_trace_bin(const double *d_rx, int n_rx, const sosat_freq_t *h_freq, int n_freq,
+                    int n_scan, int64_t row_begin, int64_t row_end, int grid_n,
+                    double extent_mm, double opl_ref, float *d_re, float *d_im, float *d_cnt,
+                    double *d_stats, void *stream);
+
+/* b = (re + i im)/cnt * exp(-i k_over_2e3 (mean_opl - opl_ref)) per cell (0 where cnt = 0);
+ * d_b: [n][2] float32 interleaved complex.  In place over (re, im) is not supported. */
+int sosat_bins_to_field(const float *d_re, const float *d_im, const float *d_cnt, int64_t n,
+                        double phase_offset_rad, float *d_b, void *stream);
+
+/* ---- stage 2: far-field transform (opt_analyze.py:220-230 a2b) ----------------------- */
+/* B = W_r b W_c^T, W[k,n] = exp(-2 pi i (k - floor(N/2)) (n - ceil(N/2)) / N): identical to
+ * fftshift(fft2(fftshift(b))).  Dense separable complex contraction executed as two
+ * split-bf16 GEMM passes on tcgen05 tensor cores with TMA-staged tiles.
+ * d_b, d_B: [n][n][2] float32 interleaved complex (may alias).  Workspace from
+ * sosat_dft2_workspace_bytes(n), 256-byte aligned; twiddle operands are cached in it. */
+size_t sosat_dft2_workspace_bytes(int n);
+/* The twiddle operands written into a workspace are remembered per (device, address, n);
+ * call this before freeing a workspace so a later allocation at the same address is
+ * re-planned. */
+int sosat_dft2_forget(const void *d_workspace);
+int sosat_dft2_gemm(const float *d_b, int n, float *d_B, void *d_workspace,
+                    size_t workspace_bytes, void *stream);
+
+/* a2b with the reference's argument meaning: d_apert (amplitude, abs() is taken) and
+ * d_phi_deg (phase in degrees) are [n][n] float64; outputs d_beam [n][n][2] float64
+ * (complex128) and d_phase [n][n] float64 = arctan2(imag, real). */
+int sosat_a2b(const double *d_apert, const double *d_phi_deg, int n, double *d_beam,
+              double *d_phase, void *d_workspace, size_t workspace_bytes, void *stream);
+/* Host-buffer form (synchronous): allocates and frees device temporaries. */
+int sosat_a2b_host(const double *h_apert, const double *h_phi_deg, int n, double *h_beam,
+                   double *h_phase);
+
+/* Direct-sum far field on irregular samples (north_star): for j < n_ang
+ *   B_j = sum_p b_p exp(-2 pi i (x_p thx_j + y_p thy_j) * inv_lambda),
+ * phase factor generated in registers.  d_xyb: [n_pts] float4 {x, y, Re b, Im b} (x, y in
+ * the unit of 1/inv_lambda); d_th: [n_ang] float2 {thx, thy} [rad]; d_B: [n_ang] float2. */
+int sosat_nudft_direct(const float *d_xyb, int64_t n_pts, const float *d_th, int64_t n_ang,
+                       double inv_lambda, float *d_B, void *stream);
+
+/* ---- measurement helpers --------------------------------------------------------------- */
+/* Dependent-free FP64 FMA throughput microkernel: returns achieved FLOP/s (2 per FMA) in
+ * *flops_per_s; used by bench.py as the roofline denominator of the ray tracer because
+ * MEASURED_PEAKS.json carries no FP64 peak. */
+int sosat_measure_fp64_peak(double *flops_per_s, double *ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* SOSAT_B200_H */

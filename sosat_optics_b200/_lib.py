@@ -1,0 +1,107 @@
+"""ctypes binding of libsosat_b200.so (the C-ABI declared in include/sosat_b200.h).
+
+There is no CPU fallback: if the shared library is missing, or no CUDA device is visible
+when a compute entry point is called, the call raises.
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+from ctypes import (POINTER, Structure, c_char_p, c_double, c_float, c_int, c_int64, c_size_t,
+                    c_uint8, c_void_p)
+
+NUM_SURFACES = 6
+OUT_ROWS = 17
+MAX_FREQS = 64
+NUM_STATS = 8
+(STAT_N_VALID, STAT_SUM_OPL, STAT_SUM_DX, STAT_SUM_DY, STAT_SUM_DZ, STAT_N_SLOW,
+ STAT_N_BRACKET_FAIL, STAT_N_BINNED) = range(8)
+
+LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsosat_b200.so")
+
+
+class Surface(Structure):
+    _fields_ = [(n, c_double) for n in
+                ("c", "k", "a1", "a2", "a3", "y0", "n_in", "n_out", "t_lo", "t_hi")]
+
+
+class Geom(Structure):
+    _fields_ = [("surf", Surface * NUM_SURFACES)] + [
+        (n, c_double) for n in ("y_lyot", "y_source", "clip_l3", "clip_stop", "cone")]
+
+
+class Freq(Structure):
+    _fields_ = [("fwhp_x", c_double), ("fwhp_y", c_double), ("k_over_2e3", c_double)]
+
+
+# name -> (restype, argtypes); mirrors include/sosat_b200.h one to one
+SIGNATURES = {
+    "sosat_abi_version": (c_int, []),
+    "sosat_last_error": (c_char_p, []),
+    "sosat_device_count": (c_int, []),
+    "sosat_set_device": (c_int, [c_int]),
+    "sosat_device_info": (c_int, [c_char_p, POINTER(c_int), POINTER(c_int), POINTER(c_size_t)]),
+    "sosat_set_geometry": (c_int, [POINTER(Geom), c_void_p]),
+    "sosat_trace_rays": (c_int, [POINTER(c_double), POINTER(Freq), c_int, c_int64, c_int64,
+                                 c_void_p, c_void_p, c_void_p]),
+    "sosat_rx_to_lyot_host": (c_int, [POINTER(Geom), POINTER(c_double), POINTER(Freq), c_int,
+                                      c_int64, c_int64, POINTER(c_double), POINTER(c_double)]),
+    "sosat_near_field_arrays": (c_int, [c_void_p, c_int64, c_double, c_void_p, c_void_p,
+                                        c_void_p, c_void_p, c_void_p]),
+    "sosat_trace_bin": (c_int, [c_void_p, c_int, POINTER(Freq), c_int, c_int, c_int64, c_int64,
+                                c_int, c_double, c_double, c_void_p, c_void_p, c_void_p,
+                                c_void_p, c_void_p]),
+    "sosat_bins_to_field": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p,
+                                    c_void_p]),
+    "sosat_dft2_workspace_bytes": (c_size_t, [c_int]),
+    "sosat_dft2_forget": (c_int, [c_void_p]),
+    "sosat_dft2_gemm": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "sosat_a2b": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                          c_void_p]),
+    "sosat_a2b_host": (c_int, [POINTER(c_double), POINTER(c_double), c_int, POINTER(c_double),
+                               POINTER(c_double)]),
+    "sosat_nudft_direct": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_double, c_void_p,
+                                   c_void_p]),
+    "sosat_measure_fp64_peak": (c_int, [POINTER(c_double), POINTER(c_double)]),
+}
+
+_lib = None
+
+
+class SosatError(RuntimeError):
+    pass
+
+
+def load():
+    """Load the shared library (once).  Raises ImportError if it has not been built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError(
+            f"{LIB_PATH} is missing: build it with `python -m sosat_optics_b200.build` "
+            "(needs nvcc).  sosat_optics_b200 has no CPU fallback.")
+    lib = ctypes.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)  # AttributeError if the library does not export it
+        fn.restype = res
+        fn.argtypes = args
+    if lib.sosat_abi_version() != 1:
+        raise ImportError(f"{LIB_PATH}: ABI version {lib.sosat_abi_version()} != 1")
+    _lib = lib
+    return lib
+
+
+def check(rc: int) -> None:
+    if rc != 0:
+        msg = load().sosat_last_error()
+        raise SosatError(f"libsosat_b200 error {rc}: {msg.decode() if msg else ''}")
+
+
+def require_gpu():
+    """The product path needs a B200; say so loudly instead of computing on the CPU."""
+    lib = load()
+    if lib.sosat_device_count() <= 0:
+        raise SosatError("no CUDA device visible: sosat_optics_b200 runs only on the GPU "
+                         "(there is deliberately no CPU fallback)")
+    return lib

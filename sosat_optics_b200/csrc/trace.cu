@@ -1,0 +1,650 @@
+// Stage 1 of the hot path on sm_100a: ray trace feed -> source plane (K1), in three forms:
+//   trace_rows_kernel   the reference's out[17, n] table            (ray_trace.py:1070-1591)
+//   trace_bin_kernel    fused trace + near-field binning b(x,y)      (north_star / SURVEY 8 a7)
+//   near-field arrays   getNearField's means, phase wrap, scaling    (ray_trace.py:1594-1614)
+// One ray per thread, fp64 state, geometry in __constant__ memory, no per-ray global reads.
+#include <cmath>
+#include <cstdlib>
+#include <cstring>
+
+#include "common.cuh"
+#include "trace_device.cuh"
+
+namespace sosat {
+
+__constant__ GeomC g_geom;
+static bool g_geom_set[64] = {false};
+
+static constexpr double kHalfPi = 1.5707963267948966;
+static constexpr double kFourLn2 = 2.772588722239781;  // (1/2) / (1/sqrt(8 ln 2))^2
+
+// numpy.linspace(start, stop, n)[i] = i*step + start, last element forced to stop
+// (two roundings, no fused multiply-add), ray_trace.py:1086-1087.
+__device__ __forceinline__ double linspace_at(double start, double stop, double step, int n,
+                                              int i) {
+    if (i == n - 1 && n > 1) return stop;
+    return __dadd_rn(__dmul_rn((double)i, step), start);
+}
+
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+
+// Block-wide sum of NV per-thread doubles; one atomicAdd per value per block.
+template <int NV>
+__device__ __forceinline__ void block_accumulate(const double (&v)[NV], double *dst) {
+    __shared__ double red[NV][32];
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+    __syncthreads();
+#pragma unroll
+    for (int i = 0; i < NV; ++i) {
+        const double s = warp_sum(v[i]);
+        if (lane == 0) red[i][wid] = s;
+    }
+    __syncthreads();
+    if (wid == 0) {
+#pragma unroll
+        for (int i = 0; i < NV; ++i) {
+            double s = lane < nw ? red[i][lane] : 0.0;
+            s = warp_sum(s);
+            if (lane == 0 && s != 0.0) atomicAdd(dst + i, s);
+        }
+    }
+}
+
+struct RowsParams {
+    double rx[3];
+    double fwhp_x, fwhp_y;
+    double lin_start, lin_stop, lin_step;
+    int n_scan;
+    long long ray_begin, n;
+};
+
+// ---- K1a: reference table out[17][n] ----------------------------------------------------
+template <int N32, int N64>
+__global__ void __launch_bounds__(256)
+trace_rows_kernel(RowsParams p, double *__restrict__ out, double *__restrict__ stats) {
+    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    double acc[SOSAT_NUM_STATS] = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (j < p.n) {
+        const long long ii = p.ray_begin + j;
+        const int ith = (int)(ii % p.n_scan), iph = (int)(ii / p.n_scan);
+        const double th = linspace_at(p.lin_start, p.lin_stop, p.lin_step, p.n_scan, ith);
+        const double ph = linspace_at(p.lin_start, p.lin_stop, p.lin_step, p.n_scan, iph);
+        double sth, cth, sph, cph;
+        sincos(th, &sth, &cth);
+        sincos(ph, &sph, &cph);
+        // r_hat, ray_trace.py:1103
+        const double d0x = sth * cph, d0y = sth * sph, d0z = cth;
+        RayResult r;
+        unsigned n_slow = 0;
+        trace_ray<N32, N64>(g_geom, p.rx[0], p.rx[1], p.rx[2], d0x, d0y, d0z, r, n_slow);
+        double row[11];
+        if (r.flags & RAY_CLIPPED_L3) {
+#pragma unroll
+            for (int q = 0; q < 11; ++q) row[q] = 0.0;
+        } else {
+            row[0] = r.ax; row[1] = r.ay; row[2] = r.az;
+            row[3] = 0.0; row[4] = 0.0;
+            if (r.valid) {
+                // launch angles and Gaussian feed taper, ray_trace.py:1529-1532, 1573-1577
+                const double de_ve = atan(d0x / (-d0y));
+                const double de_ho = atan(d0z / sqrt(d0x * d0x + d0y * d0y));
+                const double hx = de_ho / p.fwhp_x, hy = de_ve / p.fwhp_y;
+                row[3] = r.opl;
+                row[4] = exp(-kFourLn2 * (hx * hx + hy * hy));
+                acc[SOSAT_STAT_N_VALID] = row[4] != 0.0 ? 1.0 : 0.0;
+                acc[SOSAT_STAT_SUM_OPL] = row[4] != 0.0 ? r.opl : 0.0;
+                acc[SOSAT_STAT_SUM_DX] = row[4] != 0.0 ? r.dx : 0.0;
+                acc[SOSAT_STAT_SUM_DY] = row[4] != 0.0 ? r.dy : 0.0;
+                acc[SOSAT_STAT_SUM_DZ] = row[4] != 0.0 ? r.dz : 0.0;
+            }
+            row[5] = r.nx; row[6] = r.ny; row[7] = r.nz;
+            row[8] = r.dx; row[9] = r.dy; row[10] = r.dz;
+        }
+        acc[SOSAT_STAT_N_SLOW] = (double)n_slow;
+        acc[SOSAT_STAT_N_BRACKET_FAIL] = (r.flags & RAY_BRACKET_FAIL) ? 1.0 : 0.0;
+#pragma unroll
+        for (int q = 0; q < 11; ++q) out[(long long)q * p.n + j] = row[q];
+#pragma unroll
+        for (int q = 11; q < SOSAT_OUT_ROWS; ++q) out[(long long)q * p.n + j] = 0.0;
+    }
+    if (stats) block_accumulate<SOSAT_NUM_STATS>(acc, stats);
+}
+
+// ---- K1b: fused trace + binning ------------------------------------------------------------
+constexpr int kTile = 16;      // rays per tile edge: a CTA traces a 16 x 16 patch of the launch grid
+constexpr int kMaxGroups = 4;  // distinct bins per warp aggregated by shuffle before atomics
+
+struct BinFreq {
+    float neg_c_fx[SOSAT_MAX_FREQS];  // -4 ln2 / fwhp_x^2
+    float neg_c_fy[SOSAT_MAX_FREQS];
+    double kk[SOSAT_MAX_FREQS];       // k / 2e3 / (2 pi): OPL [mm] -> phase in cycles
+};
+__constant__ BinFreq g_freq;
+
+struct BinParams {
+    double lin_start, lin_stop, lin_step;
+    double opl_ref, half_extent, inv_cell;
+    long long row_begin;
+    int n_scan, n_rows, n_rx, n_freq, grid_n;
+    int tiles_x, tiles_y;
+    long long n_tiles;
+};
+
+template <int N32, int N64>
+__global__ void __launch_bounds__(256)
+trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict__ re,
+                 float *__restrict__ im, float *__restrict__ cnt, double *__restrict__ stats) {
+    __shared__ double s_sin[2][kTile], s_cos[2][kTile], s_ang[2][kTile];
+    __shared__ float s_amp[2][SOSAT_MAX_FREQS][kTile];  // [theta|phi][freq][index in tile]
+
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    // a warp covers 8 (theta) x 4 (phi) neighbouring rays so that they land in 1-2 bins
+    const int lth = (lane & 7) + 8 * (warp & 1);
+    const int lph = (lane >> 3) + 4 * (warp >> 1);
+
+    double acc[SOSAT_NUM_STATS] = {0, 0, 0, 0, 0, 0, 0, 0};
+    int acc_rx = -1;
+    const long long tiles_per_rx = (long long)p.tiles_x * p.tiles_y;
+    const long long plane = (long long)p.grid_n * p.grid_n;
+
+    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+        const int irx = (int)(tile / tiles_per_rx);
+        const long long trem = tile - (long long)irx * tiles_per_rx;
+        const int ty = (int)(trem / p.tiles_x), tx = (int)(trem - (long long)ty * p.tiles_x);
+        if (irx != acc_rx) {
+            if (acc_rx >= 0 && stats)
+                block_accumulate<SOSAT_NUM_STATS>(acc, stats + (long long)acc_rx * SOSAT_NUM_STATS);
+#pragma unroll
+            for (int q = 0; q < SOSAT_NUM_STATS; ++q) acc[q] = 0.0;
+            acc_rx = irx;
+        }
+        __syncthreads();  // previous tile done with the tables
+        if (tid < 2 * kTile) {
+            const int which = tid / kTile, l = tid % kTile;  // 0: theta, 1: phi
+            const long long idx = which == 0 ? (long long)tx * kTile + l
+                                             : p.row_begin + (long long)ty * kTile + l;
+            const int ic = (int)(idx < p.n_scan ? idx : p.n_scan - 1);
+            const double a = linspace_at(p.lin_start, p.lin_stop, p.lin_step, p.n_scan, ic);
+            double s, c;
+            sincos(a, &s, &c);
+            s_sin[which][l] = s;
+            s_cos[which][l] = c;
+            s_ang[which][l] = a - kHalfPi;  // -de_ho (theta) / de_ve (phi), ray_trace.py:1529-1532
+        }
+        __syncthreads();
+        for (int e = tid; e < 2 * kTile * p.n_freq; e += blockDim.x) {
+            const int which = e / (kTile * p.n_freq), rem = e % (kTile * p.n_freq);
+            const int f = rem / kTile, l = rem % kTile;
+            const float ang = (float)s_ang[which][l];
+            const float cf = which == 0 ? g_freq.neg_c_fx[f] : g_freq.neg_c_fy[f];
+            s_amp[which][f][l] = expf(cf * ang * ang);
+        }
+        __syncthreads();
+
+        const long long ith = (long long)tx * kTile + lth;
+        const long long iph = (long long)ty * kTile + lph;  // relative to row_begin
+        const bool live = ith < p.n_scan && iph < p.n_rows;
+        RayResult r;
+        r.valid = false;
+        r.flags = 0;
+        unsigned n_slow = 0;
+        if (live) {
+            const double sth = s_sin[0][lth], cth = s_cos[0][lth];
+            const double sph = s_sin[1][lph], cph = s_cos[1][lph];
+            const double *rx = d_rx + 3 * irx;
+            trace_ray<N32, N64>(g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph, cth, r, n_slow);
+        }
+        const bool valid = live && r.valid;
+        int bin = -1;
+        if (valid) {
+            const int ix = __double2int_rd((r.ax + p.half_extent) * p.inv_cell);
+            const int iz = __double2int_rd((r.az + p.half_extent) * p.inv_cell);
+            if (ix >= 0 && ix < p.grid_n && iz >= 0 && iz < p.grid_n) bin = iz * p.grid_n + ix;
+            acc[SOSAT_STAT_N_VALID] += 1.0;
+            acc[SOSAT_STAT_SUM_OPL] += r.opl;
+            acc[SOSAT_STAT_SUM_DX] += r.dx;
+            acc[SOSAT_STAT_SUM_DY] += r.dy;
+            acc[SOSAT_STAT_SUM_DZ] += r.dz;
+            if (bin >= 0) acc[SOSAT_STAT_N_BINNED] += 1.0;
+        }
+        acc[SOSAT_STAT_N_SLOW] += (double)n_slow;
+        if (live && (r.flags & RAY_BRACKET_FAIL)) acc[SOSAT_STAT_N_BRACKET_FAIL] += 1.0;
+        if (re == nullptr) continue;
+
+        // ---- warp-level aggregation: lanes that share a bin are summed by shuffle, one
+        // atomic per (bin, plane) and warp; lanes beyond kMaxGroups distinct bins go direct.
+        unsigned todo = __ballot_sync(0xffffffffu, bin >= 0);
+        if (todo == 0u) continue;
+        unsigned gmask[kMaxGroups];
+        int gbin[kMaxGroups];
+#pragma unroll
+        for (int gi = 0; gi < kMaxGroups; ++gi) {
+            gmask[gi] = 0u;
+            gbin[gi] = -1;
+            if (todo) {
+                const int leader = __ffs(todo) - 1;
+                const int b = __shfl_sync(0xffffffffu, bin, leader);
+                const unsigned m = __ballot_sync(0xffffffffu, bin == b);
+                gmask[gi] = m;
+                gbin[gi] = b;
+                todo &= ~m;
+            }
+        }
+        const bool direct = (todo >> lane) & 1u;
+        const long long base_cnt = (long long)irx * plane;
+#pragma unroll
+        for (int gi = 0; gi < kMaxGroups; ++gi)
+            if (gmask[gi] && lane == __ffs(gmask[gi]) - 1)
+                atomicAdd(cnt + base_cnt + gbin[gi], (float)__popc(gmask[gi]));
+        if (direct) atomicAdd(cnt + base_cnt + bin, 1.0f);
+
+        const double dopl = r.opl - p.opl_ref;
+        for (int f = 0; f < p.n_freq; ++f) {
+            float vre = 0.f, vim = 0.f;
+            if (bin >= 0) {
+                const float a = s_amp[0][f][lth] * s_amp[1][f][lph];
+                double cyc = dopl * g_freq.kk[f];
+                cyc -= rint(cyc);
+                float sn, cs;
+                sincospif(2.0f * (float)cyc, &sn, &cs);
+                vre = a * cs;
+                vim = a * sn;
+            }
+            const long long base = ((long long)irx * p.n_freq + f) * plane;
+#pragma unroll
+            for (int gi = 0; gi < kMaxGroups; ++gi) {
+                if (gmask[gi] == 0u) break;  // warp-uniform
+                const bool in = (gmask[gi] >> lane) & 1u;
+                float sre = in ? vre : 0.f, sim = in ? vim : 0.f;
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    sre += __shfl_xor_sync(0xffffffffu, sre, o);
+                    sim += __shfl_xor_sync(0xffffffffu, sim, o);
+                }
+                if (lane == __ffs(gmask[gi]) - 1) {
+                    atomicAdd(re + base + gbin[gi], sre);
+                    atomicAdd(im + base + gbin[gi], sim);
+                }
+            }
+            if (direct) {
+                atomicAdd(re + base + bin, vre);
+                atomicAdd(im + base + bin, vim);
+            }
+        }
+    }
+    if (acc_rx >= 0 && stats)
+        block_accumulate<SOSAT_NUM_STATS>(acc, stats + (long long)acc_rx * SOSAT_NUM_STATS);
+}
+
+// ---- getNearField post-processing (ray_trace.py:1599-1614) ---------------------------------
+__global__ void nf_sums_kernel(const double *__restrict__ out, long long n,
+                               double *__restrict__ work) {
+    double acc[5] = {0, 0, 0, 0, 0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        if (out[4 * n + i] != 0.0) {  // xx = np.where(out[4] != 0)
+            acc[0] += 1.0;
+            acc[1] += out[3 * n + i];
+            acc[2] += out[8 * n + i];
+            acc[3] += out[9 * n + i];
+            acc[4] += out[10 * n + i];
+        }
+    }
+    block_accumulate<5>(acc, work);
+}
+
+// numpy.mod for floats: result takes the sign of the divisor
+__device__ __forceinline__ double np_mod(double x, double y) {
+    double r = fmod(x, y);
+    if (r != 0.0 && ((r < 0.0) != (y < 0.0))) r += y;
+    return r;
+}
+
+__global__ void nf_phase_kernel(const double *__restrict__ out, long long n, double k,
+                                double *__restrict__ xyap, uint8_t *__restrict__ mask,
+                                double *__restrict__ work) {
+    const double mean_opl = work[1] / work[0];
+    double acc[1] = {0};
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const double a = out[4 * n + i];
+        const bool m = a != 0.0;
+        double p = 0.0;
+        if (m) {
+            // np.mod(k * (OPL - mean) / 1e3 / 2, 2 pi), ray_trace.py:1601
+            p = np_mod(__ddiv_rn(__ddiv_rn(__dmul_rn(k, out[3 * n + i] - mean_opl), 1e3), 2.0),
+                       6.283185307179586);
+            acc[0] += p;
+        }
+        xyap[0 * n + i] = out[0 * n + i] / 1e1;  // x_sim [cm]
+        xyap[1 * n + i] = out[2 * n + i] / 1e1;  // y_sim [cm]
+        xyap[2 * n + i] = a;
+        xyap[3 * n + i] = p;
+        mask[i] = m ? 1 : 0;
+    }
+    block_accumulate<1>(acc, work + 5);
+}
+
+__global__ void nf_finish_kernel(long long n, double *__restrict__ xyap,
+                                 const uint8_t *__restrict__ mask, double *__restrict__ tan_og,
+                                 const double *__restrict__ work) {
+    const double mean_p = work[5] / work[0];
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x)
+        if (mask[i]) xyap[3 * n + i] -= mean_p;  // p_sim - np.mean(p_sim), ray_trace.py:1614
+    if (blockIdx.x == 0 && threadIdx.x < 3) tan_og[threadIdx.x] = work[2 + threadIdx.x] / work[0];
+}
+
+__global__ void bins_to_field_kernel(const float *__restrict__ re, const float *__restrict__ im,
+                                     const float *__restrict__ cnt, long long n, float cs,
+                                     float sn, float2 *__restrict__ b) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float c = cnt[i];
+        float2 v = make_float2(0.f, 0.f);
+        if (c > 0.f) {
+            const float inv = 1.0f / c, x = re[i] * inv, y = im[i] * inv;
+            v.x = x * cs + y * sn;  // (x + i y) * exp(-i phi0)
+            v.y = y * cs - x * sn;
+        }
+        b[i] = v;
+    }
+}
+
+// ---- FP64 FMA throughput microkernel (roofline denominator of K1) ---------------------------
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b) {
+    double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
+           x6 = x0 + 6, x7 = x0 + 7;
+    for (int i = 0; i < iters; ++i) {
+        x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+        x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+    const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+    if (s == 123.456) out[0] = s;
+}
+
+// ---- host side ---------------------------------------------------------------------------------
+// Newton schedule (fp32 steps, fp64 steps) of the fast path; SOSAT_TRACE_VARIANT selects
+// another compiled schedule for experiments.
+static int trace_variant() {
+    const char *e = getenv("SOSAT_TRACE_VARIANT");
+    return e ? atoi(e) : 0;
+}
+
+static void fill_linspace(double cone, int n_scan, double &start, double &stop, double &step) {
+    start = kHalfPi - cone;
+    stop = kHalfPi + cone;
+    step = n_scan > 1 ? (stop - start) / (double)(n_scan - 1) : 0.0;
+}
+
+static sosat_geom_t g_host_geom[64];
+
+static int current_device(int *dev) {
+    SOSAT_CUDA_OK(cudaGetDevice(dev));
+    if (*dev < 0 || *dev >= 64) return set_error(SOSAT_ERR_UNSUPPORTED, "device index %d", *dev);
+    return 0;
+}
+
+}  // namespace sosat
+
+using namespace sosat;
+
+extern "C" int sosat_set_geometry(const sosat_geom_t *h, void *stream) {
+    SOSAT_REQUIRE(h != nullptr, "sosat_set_geometry: null geometry");
+    int dev;
+    if (int rc = current_device(&dev)) return rc;
+    GeomC g;
+    memset(&g, 0, sizeof g);
+    for (int i = 0; i < SOSAT_NUM_SURFACES; ++i) {
+        const sosat_surface_t &s = h->surf[i];
+        SOSAT_REQUIRE(s.n_in > 0 && s.n_out > 0, "surface %d: refractive index <= 0", i);
+        SurfC &c = g.s[i];
+        c.Kp = 0.01 * (1.0 + s.k) * s.c * s.c;
+        c.cp = 0.1 * s.c;
+        c.a1p = 0.1 * s.a1;
+        c.a2p = 1e-3 * s.a2;
+        c.a3p = 1e-5 * s.a3;
+        c.a1p2 = 2.0 * c.a1p;
+        c.a2p4 = 4.0 * c.a2p;
+        c.a3p6 = 6.0 * c.a3p;
+        c.y0 = s.y0;
+        c.mu = s.n_in / s.n_out;
+        c.mu2 = c.mu * c.mu;
+        c.n_in = s.n_in;
+        c.t_lo = s.t_lo;
+        c.t_hi = s.t_hi;
+        SurfF &f = g.f[i];
+        f.Kp = (float)c.Kp; f.cp = (float)c.cp; f.a1p = (float)c.a1p; f.a2p = (float)c.a2p;
+        f.a3p = (float)c.a3p; f.a1p2 = (float)c.a1p2; f.a2p4 = (float)c.a2p4;
+        f.a3p6 = (float)c.a3p6;
+    }
+    g.y_lyot = h->y_lyot;
+    g.y_source = h->y_source;
+    g.clip_l3_sq = h->clip_l3 * h->clip_l3;
+    g.clip_stop_sq = h->clip_stop * h->clip_stop;
+    g.cone = h->cone;
+    SOSAT_CUDA_OK(cudaMemcpyToSymbolAsync(g_geom, &g, sizeof g, 0, cudaMemcpyHostToDevice,
+                                          (cudaStream_t)stream));
+    // the staging copy above reads &g before returning only for pageable memory semantics
+    SOSAT_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
+    g_host_geom[dev] = *h;
+    g_geom_set[dev] = true;
+    return SOSAT_OK;
+}
+
+template <int N32, int N64>
+static void launch_rows(const RowsParams &p, double *out, double *stats, cudaStream_t st) {
+    const int threads = 256;
+    const long long blocks = (p.n + threads - 1) / threads;
+    trace_rows_kernel<N32, N64><<<(unsigned)blocks, threads, 0, st>>>(p, out, stats);
+}
+
+extern "C" int sosat_trace_rays(const double *h_rx, const sosat_freq_t *h_freq, int n_scan,
+                                int64_t ray_begin, int64_t ray_end, double *d_out,
+                                double *d_stats, void *stream) {
+    int dev;
+    if (int rc = current_device(&dev)) return rc;
+    if (!g_geom_set[dev]) return set_error(SOSAT_ERR_NO_GEOMETRY, "call sosat_set_geometry first");
+    SOSAT_REQUIRE(h_rx && h_freq && d_out, "sosat_trace_rays: null pointer");
+    SOSAT_REQUIRE(n_scan >= 1, "n_scan must be >= 1 (got %d)", n_scan);
+    const int64_t total = (int64_t)n_scan * n_scan;
+    SOSAT_REQUIRE(ray_begin >= 0 && ray_end >= ray_begin && ray_end <= total,
+                  "ray range [%lld, %lld) outside [0, %lld]", (long long)ray_begin,
+                  (long long)ray_end, (long long)total);
+    SOSAT_REQUIRE(h_freq->fwhp_x != 0 && h_freq->fwhp_y != 0, "feed FWHP must be non-zero");
+    RowsParams p;
+    p.rx[0] = h_rx[0]; p.rx[1] = h_rx[1]; p.rx[2] = h_rx[2];
+    p.fwhp_x = h_freq->fwhp_x;
+    p.fwhp_y = h_freq->fwhp_y;
+    fill_linspace(g_host_geom[dev].cone, n_scan, p.lin_start, p.lin_stop, p.lin_step);
+    p.n_scan = n_scan;
+    p.ray_begin = ray_begin;
+    p.n = ray_end - ray_begin;
+    if (p.n == 0) return SOSAT_OK;
+    SOSAT_REQUIRE((p.n + 255) / 256 < 2147483647LL, "too many rays for one launch");
+    cudaStream_t st = (cudaStream_t)stream;
+    switch (trace_variant()) {
+        case 1: launch_rows<0, 6>(p, d_out, d_stats, st); break;
+        case 2: launch_rows<3, 2>(p, d_out, d_stats, st); break;
+        case 3: launch_rows<3, 3>(p, d_out, d_stats, st); break;
+        case 4: launch_rows<2, 3>(p, d_out, d_stats, st); break;
+        case 5: launch_rows<0, 4>(p, d_out, d_stats, st); break;
+        default: launch_rows<0, 5>(p, d_out, d_stats, st); break;
+    }
+    SOSAT_CUDA_OK(cudaGetLastError());
+    return SOSAT_OK;
+}
+
+extern "C" int sosat_rx_to_lyot_host(const sosat_geom_t *h_geom, const double *h_rx,
+                                     const sosat_freq_t *h_freq, int n_scan, int64_t ray_begin,
+                                     int64_t ray_end, double *h_out, double *h_stats) {
+    SOSAT_REQUIRE(h_geom && h_out, "sosat_rx_to_lyot_host: null pointer");
+    if (int rc = sosat_set_geometry(h_geom, nullptr)) return rc;
+    const int64_t n = ray_end - ray_begin;
+    SOSAT_REQUIRE(n >= 0, "empty or negative ray range");
+    if (n == 0) return SOSAT_OK;
+    double *d_out = nullptr, *d_stats = nullptr;
+    SOSAT_CUDA_OK(cudaMalloc(&d_out, sizeof(double) * SOSAT_OUT_ROWS * n));
+    cudaError_t e = cudaMalloc(&d_stats, sizeof(double) * SOSAT_NUM_STATS);
+    if (e != cudaSuccess) {
+        cudaFree(d_out);
+        return set_error(SOSAT_ERR_CUDA, "cudaMalloc: %s", cudaGetErrorString(e));
+    }
+    cudaMemset(d_stats, 0, sizeof(double) * SOSAT_NUM_STATS);
+    int rc = sosat_trace_rays(h_rx, h_freq, n_scan, ray_begin, ray_end, d_out, d_stats, nullptr);
+    if (rc == 0) {
+        e = cudaMemcpy(h_out, d_out, sizeof(double) * SOSAT_OUT_ROWS * n, cudaMemcpyDeviceToHost);
+        if (e == cudaSuccess && h_stats)
+            e = cudaMemcpy(h_stats, d_stats, sizeof(double) * SOSAT_NUM_STATS,
+                           cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) rc = set_error(SOSAT_ERR_CUDA, "cudaMemcpy: %s", cudaGetErrorString(e));
+    }
+    cudaFree(d_out);
+    cudaFree(d_stats);
+    return rc;
+}
+
+template <int N32, int N64>
+static void launch_bin(const BinParams &p, int blocks, const double *rx, float *re, float *im,
+                       float *cnt, double *stats, cudaStream_t st) {
+    trace_bin_kernel<N32, N64><<<blocks, 256, 0, st>>>(p, rx, re, im, cnt, stats);
+}
+
+extern "C" int sosat_trace_bin(const double *d_rx, int n_rx, const sosat_freq_t *h_freq,
+                               int n_freq, int n_scan, int64_t row_begin, int64_t row_end,
+                               int grid_n, double extent_mm, double opl_ref, float *d_re,
+                               float *d_im, float *d_cnt, double *d_stats, void *stream) {
+    int dev;
+    if (int rc = current_device(&dev)) return rc;
+    if (!g_geom_set[dev]) return set_error(SOSAT_ERR_NO_GEOMETRY, "call sosat_set_geometry first");
+    SOSAT_REQUIRE(d_rx && h_freq, "sosat_trace_bin: null pointer");
+    SOSAT_REQUIRE(n_rx >= 1, "n_rx must be >= 1");
+    SOSAT_REQUIRE(n_freq >= 1 && n_freq <= SOSAT_MAX_FREQS, "n_freq must be in [1, %d]",
+                  SOSAT_MAX_FREQS);
+    SOSAT_REQUIRE(n_scan >= 1, "n_scan must be >= 1");
+    SOSAT_REQUIRE(row_begin >= 0 && row_end >= row_begin && row_end <= n_scan,
+                  "row range [%lld, %lld) outside [0, %d]", (long long)row_begin,
+                  (long long)row_end, n_scan);
+    const bool binning = d_re || d_im || d_cnt;
+    if (binning) {
+        SOSAT_REQUIRE(d_re && d_im && d_cnt, "d_re, d_im, d_cnt must be all set or all NULL");
+        SOSAT_REQUIRE(grid_n >= 1 && grid_n <= 32768, "grid_n out of range");
+        SOSAT_REQUIRE(extent_mm > 0, "extent_mm must be positive");
+    }
+    if (row_end == row_begin) return SOSAT_OK;
+    BinFreq bf;
+    memset(&bf, 0, sizeof bf);
+    for (int f = 0; f < n_freq; ++f) {
+        SOSAT_REQUIRE(h_freq[f].fwhp_x != 0 && h_freq[f].fwhp_y != 0, "feed FWHP must be non-zero");
+        bf.neg_c_fx[f] = (float)(-kFourLn2 / (h_freq[f].fwhp_x * h_freq[f].fwhp_x));
+        bf.neg_c_fy[f] = (float)(-kFourLn2 / (h_freq[f].fwhp_y * h_freq[f].fwhp_y));
+        bf.kk[f] = h_freq[f].k_over_2e3 / 6.283185307179586;
+    }
+    cudaStream_t st = (cudaStream_t)stream;
+    SOSAT_CUDA_OK(cudaMemcpyToSymbolAsync(g_freq, &bf, sizeof bf, 0, cudaMemcpyHostToDevice, st));
+    BinParams p;
+    fill_linspace(g_host_geom[dev].cone, n_scan, p.lin_start, p.lin_stop, p.lin_step);
+    p.opl_ref = opl_ref;
+    p.half_extent = binning ? 0.5 * extent_mm : 0.0;
+    p.inv_cell = binning ? (double)grid_n / extent_mm : 0.0;
+    p.row_begin = row_begin;
+    p.n_scan = n_scan;
+    p.n_rows = (int)(row_end - row_begin);
+    p.n_rx = n_rx;
+    p.n_freq = n_freq;
+    p.grid_n = binning ? grid_n : 0;
+    p.tiles_x = (n_scan + kTile - 1) / kTile;
+    p.tiles_y = (p.n_rows + kTile - 1) / kTile;
+    p.n_tiles = (long long)p.tiles_x * p.tiles_y * n_rx;
+    int occ = 0;
+    const int sms = num_sms();
+    long long want;
+    switch (trace_variant()) {
+#define SOSAT_BIN_CASE(ID, A, B)                                                              \
+    case ID:                                                                                  \
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_bin_kernel<A, B>, 256, 0);  \
+        want = (long long)sms * (occ > 0 ? occ : 1);                                          \
+        launch_bin<A, B>(p, (int)(p.n_tiles < want ? p.n_tiles : want), d_rx, d_re, d_im,     \
+                         d_cnt, d_stats, st);                                                 \
+        break;
+        SOSAT_BIN_CASE(1, 0, 6)
+        SOSAT_BIN_CASE(2, 3, 2)
+        SOSAT_BIN_CASE(3, 3, 3)
+        SOSAT_BIN_CASE(4, 2, 3)
+        SOSAT_BIN_CASE(5, 0, 4)
+        default:
+            SOSAT_BIN_CASE(0, 0, 5)
+#undef SOSAT_BIN_CASE
+    }
+    SOSAT_CUDA_OK(cudaGetLastError());
+    // bf lives on this stack frame: the async symbol copy from pageable memory is staged
+    // before the call returns, so no synchronisation is needed here.
+    return SOSAT_OK;
+}
+
+extern "C" int sosat_near_field_arrays(const double *d_out, int64_t n, double k, double *d_xyap,
+                                       uint8_t *d_mask, double *d_tan_og, double *d_work,
+                                       void *stream) {
+    SOSAT_REQUIRE(d_out && d_xyap && d_mask && d_tan_og && d_work,
+                  "sosat_near_field_arrays: null pointer");
+    SOSAT_REQUIRE(n >= 0, "negative ray count");
+    cudaStream_t st = (cudaStream_t)stream;
+    SOSAT_CUDA_OK(cudaMemsetAsync(d_work, 0, sizeof(double) * SOSAT_NUM_STATS, st));
+    if (n == 0) return SOSAT_OK;
+    const int threads = 256;
+    long long blocks = (n + threads - 1) / threads;
+    const long long cap = (long long)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    nf_sums_kernel<<<(unsigned)blocks, threads, 0, st>>>(d_out, n, d_work);
+    nf_phase_kernel<<<(unsigned)blocks, threads, 0, st>>>(d_out, n, k, d_xyap, d_mask, d_work);
+    nf_finish_kernel<<<(unsigned)blocks, threads, 0, st>>>(n, d_xyap, d_mask, d_tan_og, d_work);
+    SOSAT_CUDA_OK(cudaGetLastError());
+    return SOSAT_OK;
+}
+
+extern "C" int sosat_bins_to_field(const float *d_re, const float *d_im, const float *d_cnt,
+                                   int64_t n, double phase_offset_rad, float *d_b, void *stream) {
+    SOSAT_REQUIRE(d_re && d_im && d_cnt && d_b, "sosat_bins_to_field: null pointer");
+    SOSAT_REQUIRE(n >= 0, "negative cell count");
+    if (n == 0) return SOSAT_OK;
+    long long blocks = (n + 255) / 256;
+    const long long cap = (long long)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    bins_to_field_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        d_re, d_im, d_cnt, n, (float)cos(phase_offset_rad), (float)sin(phase_offset_rad),
+        (float2 *)d_b);
+    SOSAT_CUDA_OK(cudaGetLastError());
+    return SOSAT_OK;
+}
+
+extern "C" int sosat_measure_fp64_peak(double *flops_per_s, double *ms_out) {
+    SOSAT_REQUIRE(flops_per_s, "sosat_measure_fp64_peak: null pointer");
+    double *d = nullptr;
+    SOSAT_CUDA_OK(cudaMalloc(&d, 64));
+    const int iters = 1 << 15, threads = 256, blocks = num_sms() * 16;
+    cudaEvent_t e0, e1;
+    SOSAT_CUDA_OK(cudaEventCreate(&e0));
+    SOSAT_CUDA_OK(cudaEventCreate(&e1));
+    float best = 1e30f;
+    for (int rep = 0; rep < 5; ++rep) {
+        cudaEventRecord(e0);
+        fp64_peak_kernel<<<blocks, threads>>>(d, iters, 0.999999, 1e-9);
+        cudaEventRecord(e1);
+        SOSAT_CUDA_OK(cudaEventSynchronize(e1));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        if (rep > 0 && ms < best) best = ms;
+    }
+    cudaEventDestroy(e0);
+    cudaEventDestroy(e1);
+    cudaFree(d);
+    SOSAT_CUDA_OK(cudaGetLastError());
+    const double fl = 2.0 * 8.0 * (double)iters * threads * (double)blocks;
+    *flops_per_s = fl / (best * 1e-3);
+    if (ms_out) *ms_out = best;
+    return SOSAT_OK;
+}

@@ -1,0 +1,378 @@
+// Device-side ray tracer: one ray per thread, fp64 state, geometry in __constant__ memory.
+//
+// Replaces the per-ray body of ray_trace.py:1098-1588 (rx_to_lyot).  The six surface
+// intersections the reference finds with scipy.optimize.brentq (ray_trace.py:1130, 1198,
+// 1261, 1326, 1393, 1460) are found by Newton iteration on the same function
+//     f(t) = z_l(o + d t) - sag(x_l, y_l)              (root_z?? closures, e.g. :1114-1128)
+// written directly in the tele frame: with every tilt angle = pi/2 (ot_geo.py:32-37) the
+// surface frame is x_l = x, y_l = z, z_l = -(y - y0) (ot_geo.py:449-458), so
+//     f(t) = (y0 - o_y) - d_y t - S(u),   u = X^2 + Z^2 [mm^2],  X = o_x + d_x t, Z = o_z + d_z t
+//     S(u) = u [ c'/(1+s) + a1' + a2' u + a3' u^2 ],  s = sqrt(1 - K' u)
+// with the cm->mm factors of ot_geo.py:54-55,69 folded into the primed constants.
+// A ray whose Newton solve is not clearly converged, or that grazes the conic-domain edge
+// of lens 1b, is re-traced with a bracketed Brent solve that restates the reference's
+// brentq call (same brackets, same tolerances), so such rays get the reference's answer.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdint>
+
+#include "sosat_b200.h"
+
+namespace sosat {
+
+struct SurfC {
+    double Kp;    // 0.01 (1+k) c^2
+    double cp;    // 0.1 c
+    double a1p;   // 0.1 a1
+    double a2p;   // 1e-3 a2
+    double a3p;   // 1e-5 a3
+    double a1p2;  // 2 a1'
+    double a2p4;  // 4 a2'
+    double a3p6;  // 6 a3'
+    double y0;    // vertex y [mm]
+    double mu;    // n_in / n_out
+    double mu2;   // mu^2
+    double n_in;  // OPL weight of the segment arriving at this surface
+    double t_lo, t_hi;
+};
+
+struct SurfF {
+    float Kp, cp, a1p, a2p, a3p, a1p2, a2p4, a3p6;
+};
+
+struct GeomC {
+    SurfC s[SOSAT_NUM_SURFACES];
+    SurfF f[SOSAT_NUM_SURFACES];
+    double y_lyot, y_source, clip_l3_sq, clip_stop_sq, cone;
+};
+
+// Newton acceptance: a surface whose last Newton step exceeds this [mm] (or is NaN) marks
+// the ray for the bracketed slow path.  The normal is taken at the iterate before the last
+// step, so this also bounds the normal error (curvature ~1e-2/mm  ->  <= 1e-8).
+#define SOSAT_NEWTON_TOL 1.0e-6
+// lens 1b is the only surface with a bounded conic domain (k > -1): hits
+// with w = 1 - K'u below this are within ~8 mm of the domain edge r = 300.4 mm, where the
+// reference's brentq converges onto the sag discontinuity instead of a root.
+#define SOSAT_EDGE_W 0.05
+
+enum : unsigned {
+    RAY_CLIPPED_L3 = 1u,  // ray_trace.py:1138-1140: whole output column stays zero
+    RAY_FLAGGED = 2u,     // Newton not clearly converged / conic edge: needs the slow path
+    RAY_BRACKET_FAIL = 4u // slow path: f(lo), f(hi) same sign (reference raises ValueError)
+};
+
+struct RayResult {
+    double ax, ay, az;  // pos_ap (source plane), mm
+    double opl;         // total optical path length, mm
+    double nx, ny, nz;  // last surface normal, tele frame (out rows 5-7)
+    double dx, dy, dz;  // exit direction (out rows 8-10)
+    unsigned flags;
+    bool valid;         // passes the stop / lens-2a clips, nothing NaN
+};
+
+// ---- fast fp64 reciprocal / reciprocal square root: MUFU seed + Newton-Raphson ---------
+__device__ __forceinline__ double rcp_seed(double x) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+}
+__device__ __forceinline__ double rsqrt_seed(double x) {
+    double r;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+    return r;
+}
+// full precision (~1 ulp): seed is good to ~2^-22, two NR steps square that twice
+__device__ __forceinline__ double rcp_fast(double x) {
+    double r = rcp_seed(x);
+    double e = fma(-x, r, 1.0);
+    r = fma(r, e, r);
+    e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+// ~2^-44: enough for a Newton step quotient
+__device__ __forceinline__ double rcp_half(double x) {
+    double r = rcp_seed(x);
+    double e = fma(-x, r, 1.0);
+    return fma(r, e, r);
+}
+__device__ __forceinline__ double rsqrt_fast(double x) {
+    double y = rsqrt_seed(x);
+    double a = x * y;
+    double e = fma(-a, y, 1.0);
+    y = fma(0.5 * y, e, y);
+    a = x * y;
+    e = fma(-a, y, 1.0);
+    return fma(0.5 * y, e, y);
+}
+__device__ __forceinline__ float rcp_f32(float x) {
+    float r;
+    asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+__device__ __forceinline__ float rsqrt_f32(float x) {
+    float r;
+    asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+    return r;
+}
+
+// ---- surface function in the tele frame -------------------------------------------------
+// Returns f and df/dt at parameter t, plus X, Z of the point and G = (dS/dX)/X = (dS/dZ)/Z,
+// the slope factor of d_z?? (ot_geo.py:108-115): the surface gradient is (G X, G Z).
+__device__ __forceinline__ void surf_eval(const SurfC &S, double Px, double Pz, double dx,
+                                          double dy, double dz, double y0Py, double t,
+                                          double &f, double &fp, double &X, double &Z,
+                                          double &G, double &w) {
+    X = fma(dx, t, Px);
+    Z = fma(dz, t, Pz);
+    const double u = fma(X, X, Z * Z);
+    w = fma(-S.Kp, u, 1.0);
+    const double rs = rsqrt_fast(w);
+    const double s = w * rs;
+    const double inv = rcp_fast(1.0 + s);
+    const double poly = fma(fma(S.a3p, u, S.a2p), u, S.a1p);
+    const double q = S.cp * inv;
+    f = fma(-dy, t, y0Py) - u * (q + poly);
+    const double h = (1.0 - w) * inv * rs;  // K'u / (s (1+s))
+    G = fma(u, fma(S.a3p6, u, S.a2p4), S.a1p2) + q * (2.0 + h);
+    fp = -dy - G * fma(X, dx, Z * dz);
+}
+
+__device__ __forceinline__ void surf_eval_f32(const SurfF &S, float Px, float Pz, float dx,
+                                              float dy, float dz, float y0Py, float t,
+                                              float &f, float &fp) {
+    const float X = fmaf(dx, t, Px);
+    const float Z = fmaf(dz, t, Pz);
+    const float u = fmaf(X, X, Z * Z);
+    const float w = fmaf(-S.Kp, u, 1.0f);
+    const float rs = rsqrt_f32(w);
+    const float s = w * rs;
+    const float inv = rcp_f32(1.0f + s);
+    const float poly = fmaf(fmaf(S.a3p, u, S.a2p), u, S.a1p);
+    const float q = S.cp * inv;
+    f = fmaf(-dy, t, y0Py) - u * (q + poly);
+    const float h = (1.0f - w) * inv * rs;
+    const float G = fmaf(u, fmaf(S.a3p6, u, S.a2p4), S.a1p2) + q * (2.0f + h);
+    fp = -dy - G * fmaf(X, dx, Z * dz);
+}
+
+// Vector Snell refraction, ray_trace.py:27-35 with N x (-N x s) = s - N (N.s) and
+// |N x s|^2 = 1 - (N.s)^2:  s2 = mu s + (mu cos_i - sqrt(1 - mu^2 (1 - cos_i^2))) N.
+// A negative radicand (total internal reflection) gives NaN, as in the reference.
+__device__ __forceinline__ void refract(const SurfC &S, double X, double Z, double G,
+                                        double &dx, double &dy, double &dz, double &nx,
+                                        double &ny, double &nz) {
+    const double gx = G * X, gz = G * Z;
+    const double rn = rsqrt_fast(fma(gx, gx, fma(gz, gz, 1.0)));
+    // local normal (-gx, -gy, 1)/|.| maps to tele (-gx, -1, -gz)/|.| (ray_trace.py:1162-1166)
+    nx = -gx * rn;
+    ny = -rn;
+    nz = -gz * rn;
+    const double ci = -fma(nx, dx, fma(ny, dy, nz * dz));
+    const double rad2 = fma(S.mu2, fma(ci, ci, -1.0), 1.0);
+    const double rad = rad2 * rsqrt_fast(rad2);
+    const double kf = fma(S.mu, ci, -rad);
+    dx = fma(S.mu, dx, kf * nx);
+    dy = fma(S.mu, dy, kf * ny);
+    dz = fma(S.mu, dz, kf * nz);
+}
+
+// Stop / source planes, OPL total and validity: ray_trace.py:1510-1526, 1565-1580.
+__device__ __forceinline__ void finish_ray(const GeomC &g, double Px, double Py, double Pz,
+                                           double dx, double dy, double dz, double opl,
+                                           double r2a_sq, RayResult &r) {
+    const double idy = 1.0 / dy;
+    const double t1 = fabs((g.y_lyot - Py) * idy);
+    const double Lx = fma(dx, t1, Px), Ly = fma(dy, t1, Py), Lz = fma(dz, t1, Pz);
+    const double t2 = fabs((g.y_source - Ly) * idy);
+    r.ax = fma(dx, t2, Lx);
+    r.ay = fma(dy, t2, Ly);
+    r.az = fma(dz, t2, Lz);
+    r.opl = opl + t1 + t2;
+    r.dx = dx;
+    r.dy = dy;
+    r.dz = dz;
+    // NaN anywhere makes both comparisons false, as in the reference
+    r.valid = (fma(Lx, Lx, Lz * Lz) <= g.clip_stop_sq) && (r2a_sq <= g.clip_stop_sq) &&
+              (r.opl == r.opl);
+}
+
+// Fast path.  N32 Newton steps in fp32 from the vertex-plane guess, then N64 in fp64.
+template <int N32, int N64>
+__device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, double Py,
+                                                 double Pz, double dx, double dy, double dz,
+                                                 RayResult &r) {
+    double opl = 0.0, r2a_sq = 0.0;
+    double nx = 0.0, ny = 0.0, nz = 0.0;
+    unsigned flags = 0;
+#pragma unroll 1
+    for (int si = 0; si < SOSAT_NUM_SURFACES; ++si) {
+        const SurfC &S = g.s[si];
+        const double y0Py = S.y0 - Py;
+        double t = y0Py * rcp_half(dy);  // vertex-plane guess
+        if (N32 > 0) {
+            const SurfF &F = g.f[si];
+            const float fPx = (float)Px, fPz = (float)Pz, fdx = (float)dx, fdy = (float)dy,
+                        fdz = (float)dz, fy0 = (float)y0Py;
+            float tf = (float)t;
+#pragma unroll
+            for (int it = 0; it < N32; ++it) {
+                float f, fp;
+                surf_eval_f32(F, fPx, fPz, fdx, fdy, fdz, fy0, tf, f, fp);
+                tf = fmaf(-f, rcp_f32(fp), tf);
+            }
+            t = (double)tf;
+        }
+        double X, Z, G, w, step = 0.0;
+#pragma unroll
+        for (int it = 0; it < N64; ++it) {
+            double f, fp;
+            surf_eval(S, Px, Pz, dx, dy, dz, y0Py, t, f, fp, X, Z, G, w);
+            step = f * rcp_half(fp);
+            t -= step;
+        }
+        if (!(fabs(step) <= SOSAT_NEWTON_TOL)) flags |= RAY_FLAGGED;
+        if (S.Kp > 0.0 && !(w >= SOSAT_EDGE_W)) flags |= RAY_FLAGGED;
+        // hit point (ray_trace.py:1133-1136 and equivalents)
+        Px = fma(dx, t, Px);
+        Py = fma(dy, t, Py);
+        Pz = fma(dz, t, Pz);
+        if (si == 0 && fma(Px, Px, Pz * Pz) >= g.clip_l3_sq) {
+            r.flags = RAY_CLIPPED_L3;
+            r.valid = false;
+            return;
+        }
+        if (si == 3) r2a_sq = fma(Px, Px, Pz * Pz);
+        opl = fma(t, S.n_in, opl);  // dist_* = |hit - previous| = t for unit d
+        refract(S, X, Z, G, dx, dy, dz, nx, ny, nz);
+    }
+    r.nx = nx;
+    r.ny = ny;
+    r.nz = nz;
+    r.flags = flags;
+    finish_ray(g, Px, Py, Pz, dx, dy, dz, opl, r2a_sq, r);
+}
+
+// ---- slow path: the reference's bracketed solve ---------------------------------------------
+// root_z?? with its "sag NaN -> 0" rule (ray_trace.py:1125-1126): outside the conic domain
+// the function degenerates to the vertex plane.
+__device__ __forceinline__ double root_fn_ref(const SurfC &S, double Px, double Pz, double dx,
+                                              double dy, double dz, double y0Py, double t) {
+    const double X = fma(dx, t, Px), Z = fma(dz, t, Pz);
+    const double u = fma(X, X, Z * Z);
+    const double w = fma(-S.Kp, u, 1.0);
+    double sag = 0.0;
+    if (w >= 0.0) {
+        const double s = sqrt(w);
+        sag = u * (S.cp / (1.0 + s) + fma(fma(S.a3p, u, S.a2p), u, S.a1p));
+    }
+    return fma(-dy, t, y0Py) - sag;
+}
+
+// Brent's method as published (Brent 1973) and as scipy.optimize.brentq applies it with its
+// defaults xtol = 2e-12, rtol = 4 eps, maxiter = 100; the reference calls it with exactly
+// those defaults.  Returns NaN when f is NaN at a bracket end or the signs agree.
+__device__ __noinline__ double brent_solve(const SurfC &S, double Px, double Pz, double dx,
+                                           double dy, double dz, double y0Py,
+                                           unsigned &flags) {
+    const double xtol = 2e-12, rtol = 8.881784197001252e-16;
+    double xpre = S.t_lo, xcur = S.t_hi;
+    double xblk = 0.0, fblk = 0.0, spre = 0.0, scur = 0.0;
+    double fpre = root_fn_ref(S, Px, Pz, dx, dy, dz, y0Py, xpre);
+    double fcur = root_fn_ref(S, Px, Pz, dx, dy, dz, y0Py, xcur);
+    if (fpre != fpre || fcur != fcur) return nan("");
+    if (fpre == 0.0) return xpre;
+    if (fcur == 0.0) return xcur;
+    if ((fpre < 0.0) == (fcur < 0.0)) {
+        flags |= RAY_BRACKET_FAIL;
+        return nan("");
+    }
+    for (int i = 0; i < 100; ++i) {
+        if (fpre != 0.0 && fcur != 0.0 && ((fpre < 0.0) != (fcur < 0.0))) {
+            xblk = xpre;
+            fblk = fpre;
+            spre = scur = xcur - xpre;
+        }
+        if (fabs(fblk) < fabs(fcur)) {
+            xpre = xcur; xcur = xblk; xblk = xpre;
+            fpre = fcur; fcur = fblk; fblk = fpre;
+        }
+        const double delta = (xtol + rtol * fabs(xcur)) / 2;
+        const double sbis = (xblk - xcur) / 2;
+        if (fcur == 0.0 || fabs(sbis) < delta) return xcur;
+        if (fabs(spre) > delta && fabs(fcur) < fabs(fpre)) {
+            double stry;
+            if (xpre == xblk) {
+                stry = -fcur * (xcur - xpre) / (fcur - fpre);
+            } else {
+                const double dpre = (fpre - fcur) / (xpre - xcur);
+                const double dblk = (fblk - fcur) / (xblk - xcur);
+                stry = -fcur * (fblk * dblk - fpre * dpre) / (dblk * dpre * (fblk - fpre));
+            }
+            if (2 * fabs(stry) < fmin(fabs(spre), 3 * fabs(sbis) - delta)) {
+                spre = scur;
+                scur = stry;
+            } else {
+                spre = sbis;
+                scur = sbis;
+            }
+        } else {
+            spre = sbis;
+            scur = sbis;
+        }
+        xpre = xcur;
+        fpre = fcur;
+        if (fabs(scur) > delta) xcur += scur;
+        else xcur += (sbis > 0 ? delta : -delta);
+        fcur = root_fn_ref(S, Px, Pz, dx, dy, dz, y0Py, xcur);
+        if (fcur != fcur) return nan("");
+    }
+    return xcur;
+}
+
+__device__ __noinline__ void trace_ray_bracketed(const GeomC &g, double Px, double Py,
+                                                 double Pz, double dx, double dy, double dz,
+                                                 RayResult &r) {
+    double opl = 0.0, r2a_sq = 0.0;
+    double nx = 0.0, ny = 0.0, nz = 0.0;
+    unsigned flags = 0;
+#pragma unroll 1
+    for (int si = 0; si < SOSAT_NUM_SURFACES; ++si) {
+        const SurfC &S = g.s[si];
+        const double y0Py = S.y0 - Py;
+        const double t = brent_solve(S, Px, Pz, dx, dy, dz, y0Py, flags);
+        double f, fp, X, Z, G, w;
+        surf_eval(S, Px, Pz, dx, dy, dz, y0Py, t, f, fp, X, Z, G, w);  // slope at the hit
+        Px = fma(dx, t, Px);
+        Py = fma(dy, t, Py);
+        Pz = fma(dz, t, Pz);
+        if (si == 0 && fma(Px, Px, Pz * Pz) >= g.clip_l3_sq) {
+            r.flags = RAY_CLIPPED_L3;
+            r.valid = false;
+            return;
+        }
+        if (si == 3) r2a_sq = fma(Px, Px, Pz * Pz);
+        opl = fma(t, S.n_in, opl);
+        refract(S, X, Z, G, dx, dy, dz, nx, ny, nz);
+    }
+    r.nx = nx;
+    r.ny = ny;
+    r.nz = nz;
+    r.flags = flags;
+    finish_ray(g, Px, Py, Pz, dx, dy, dz, opl, r2a_sq, r);
+}
+
+// Fast path, then the slow path for rays that came out valid but were flagged.
+template <int N32, int N64>
+__device__ __forceinline__ void trace_ray(const GeomC &g, double Px, double Py, double Pz,
+                                          double dx, double dy, double dz, RayResult &r,
+                                          unsigned &n_slow) {
+    trace_ray_newton<N32, N64>(g, Px, Py, Pz, dx, dy, dz, r);
+    if (r.valid && (r.flags & RAY_FLAGGED)) {
+        trace_ray_bracketed(g, Px, Py, Pz, dx, dy, dz, r);
+        r.flags |= RAY_FLAGGED;
+        ++n_slow;
+    }
+}
+
+}  // namespace sosat

@@ -1,0 +1,176 @@
+"""Drop-in for the hot-path functions of the reference's ``sosat_optics/opt_analyze.py``.
+
+======================  =======================  ==============================================
+function                reference                device code
+======================  =======================  ==============================================
+``a2b``                 opt_analyze.py:220-230   ``sosat_a2b``: tcgen05 bf16x3 DFT-GEMM (dft_gemm.cu)
+``far_field``           -- (north_star)          ``sosat_dft2_gemm`` on complex64 device/host data
+``far_field_irregular`` -- (north_star)          ``sosat_nudft_direct`` direct sum (nudft.cu)
+``zero_pad``            opt_analyze.py:20-32     host index bookkeeping (np.pad + coordinates)
+``coords_spat_to_ang``  opt_analyze.py:274-299   host label arithmetic on N values
+``ghz_to_m, m_to_ghz``  opt_analyze.py:42-57     scalar helpers
+======================  =======================  ==============================================
+"""
+from __future__ import annotations
+
+import ctypes
+import weakref
+
+import numpy as np
+
+from . import _lib
+from .ray_trace import _stream, _torch
+
+__all__ = ["a2b", "far_field", "far_field_irregular", "zero_pad", "coords_spat_to_ang",
+           "ghz_to_m", "m_to_ghz", "rad_to_arcmin"]
+
+
+def rad_to_arcmin(rads):
+    return rads * 180 * 60 / np.pi
+
+
+def ghz_to_m(freq_ghz):
+    """Frequency [GHz] -> wavelength [m] with c = 3e8 exactly (opt_analyze.py:42-48)."""
+    ff_hz = freq_ghz * 1e9
+    return (3 * 10 ** 8) / ff_hz
+
+
+def m_to_ghz(wavelength):
+    ff_hz = (3 * 10 ** 8) / wavelength
+    return ff_hz / 1e9
+
+
+def zero_pad(x_in, y_in, beam_in, pts):
+    """Pad ``beam_in`` by ``pts`` zeros on every side, rebuild the coordinate grids with the
+    reference's diagonal spacing ``|x[0,0]-x[1,1]|``, map NaN -> 0 and return the TRANSPOSED
+    field -- all quirks of opt_analyze.py:20-32 kept."""
+    x_int = abs(x_in[0, 0] - x_in[1, 1])
+    y_int = abs(y_in[0, 0] - y_in[1, 1])
+    beam_out = np.pad(beam_in, pts, mode="constant")
+    x_new = np.array(np.arange(len(beam_out))) * x_int
+    y_new = np.array(np.arange(len(beam_out))) * y_int
+    x_new -= np.mean(x_new)
+    y_new -= np.mean(y_new)
+    x_new, y_new = np.meshgrid(x_new, y_new)
+    beam_out = np.where(np.isnan(beam_out) == True, 0, beam_out)  # noqa: E712
+    return x_new + np.mean(x_in), y_new + np.mean(y_in), beam_out.T
+
+
+def coords_spat_to_ang(x, y, freq):
+    """Angle labels of the far-field grid (opt_analyze.py:274-299).  Kept bit-for-bit,
+    including ``len(x)`` for both axes and the N/(N-1) stretch of the linspace labels."""
+    ff_ghz = freq * 1e9
+    lam = (3 * 10 ** 8) / ff_ghz
+    delta_x = abs(np.max(x) - np.min(x)) / (len(x) - 1)
+    delta_y = abs(np.max(y) - np.min(y)) / (len(y) - 1)
+    x_len = len(x)
+    y_len = len(y)
+    alpha = lam / delta_x
+    beta = lam / delta_y
+    delta_th = alpha / x_len
+    delta_ph = beta / y_len
+    x_ang = np.linspace(-int((len(x) / 2)), int((len(x) / 2)), int((len(x)))) * delta_th
+    y_ang = np.linspace(-int((len(x) / 2)), int((len(x) / 2)), int((len(x)))) * delta_ph
+    x_ang, y_ang = np.meshgrid(x_ang, y_ang)
+    return x_ang, y_ang
+
+
+# --- DFT-GEMM workspaces: one per (device, n), kept alive so twiddles are generated once ----
+_workspaces = {}
+
+
+def _workspace(lib, torch, n: int):
+    key = (torch.cuda.current_device(), int(n))
+    ws = _workspaces.get(key)
+    if ws is None:
+        nbytes = int(lib.sosat_dft2_workspace_bytes(int(n)))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        ptr = ws.data_ptr()
+        weakref.finalize(ws, lambda p=ptr: lib.sosat_dft2_forget(ctypes.c_void_p(p)))
+        _workspaces[key] = ws
+    return ws
+
+
+def release_workspaces():
+    _workspaces.clear()
+
+
+def a2b(apert, phi):
+    """FFT aperture plane to angular space (opt_analyze.py:220-230).
+
+    ``apert``: real [N, N] amplitude (``abs`` is taken), ``phi``: phase in DEGREES.  Returns
+    ``(beam_complex complex128 [N, N], phase float64 [N, N])`` with
+    ``beam_complex = fftshift(fft2(fftshift(|A| exp(i phi pi/180))))`` computed as the dense
+    separable contraction W b W^T on tensor cores, and ``phase = arctan2(imag, real)``."""
+    lib = _lib.require_gpu()
+    torch = _torch()
+    apert = np.asarray(apert, dtype=np.float64)
+    phi = np.asarray(phi, dtype=np.float64)
+    if apert.ndim != 2 or apert.shape[0] != apert.shape[1] or apert.shape != phi.shape:
+        raise ValueError("a2b expects square [N, N] amplitude and phase arrays of equal shape")
+    n = apert.shape[0]
+    d_a = torch.from_numpy(np.ascontiguousarray(apert)).to("cuda")
+    d_p = torch.from_numpy(np.ascontiguousarray(phi)).to("cuda")
+    beam = torch.empty((n, n, 2), dtype=torch.float64, device="cuda")
+    phase = torch.empty((n, n), dtype=torch.float64, device="cuda")
+    ws = _workspace(lib, torch, n)
+    _lib.check(lib.sosat_a2b(ctypes.c_void_p(d_a.data_ptr()), ctypes.c_void_p(d_p.data_ptr()), n,
+                             ctypes.c_void_p(beam.data_ptr()), ctypes.c_void_p(phase.data_ptr()),
+                             ctypes.c_void_p(ws.data_ptr()), ws.numel(), _stream(torch)))
+    return torch.view_as_complex(beam).cpu().numpy(), phase.cpu().numpy()
+
+
+def far_field(b, *, device: bool = False):
+    """Centred 2-D DFT of a complex near field ``b`` [N, N] (numpy complex or CUDA complex64
+    tensor): ``B = fftshift(fft2(fftshift(b)))``.  With ``device=True`` the input must be a
+    CUDA tensor and a CUDA complex64 tensor is returned (no host copies)."""
+    lib = _lib.require_gpu()
+    torch = _torch()
+    if isinstance(b, np.ndarray):
+        d_b = torch.from_numpy(np.ascontiguousarray(b.astype(np.complex64))).to("cuda")
+    else:
+        d_b = b.to(device="cuda", dtype=torch.complex64).contiguous()
+    if d_b.dim() != 2 or d_b.shape[0] != d_b.shape[1]:
+        raise ValueError("far_field expects a square [N, N] field")
+    n = d_b.shape[0]
+    out = torch.empty((n, n), dtype=torch.complex64, device="cuda")
+    ws = _workspace(lib, torch, n)
+    _lib.check(lib.sosat_dft2_gemm(ctypes.c_void_p(d_b.data_ptr()), n,
+                                   ctypes.c_void_p(out.data_ptr()),
+                                   ctypes.c_void_p(ws.data_ptr()), ws.numel(), _stream(torch)))
+    return out if device else out.cpu().numpy()
+
+
+def far_field_angles(n: int, dx_m: float, lam_m: float):
+    """True FFT-bin angles of the centred transform: theta_k = (k - floor(N/2)) lam / (N dx)
+    (from opt_analyze.py:283-294; the labels of ``coords_spat_to_ang`` are these stretched by
+    N/(N-1))."""
+    return (np.arange(n) - n // 2) * lam_m / (n * dx_m)
+
+
+def far_field_irregular(x, y, b, theta_x, theta_y, lam):
+    """Direct-sum far field of irregular samples: ``B_j = sum_p b_p exp(-2 pi i (x_p thx_j +
+    y_p thy_j) / lam)``; ``x, y, lam`` in the same length unit, angles in radians.  The sign
+    follows the reference's code path (numpy FFT), not README.md:24."""
+    lib = _lib.require_gpu()
+    torch = _torch()
+    x = np.asarray(x, dtype=np.float64).ravel()
+    y = np.asarray(y, dtype=np.float64).ravel()
+    b = np.asarray(b, dtype=np.complex128).ravel()
+    if not (x.size == y.size == b.size):
+        raise ValueError("x, y, b must have the same number of samples")
+    tx = np.asarray(theta_x, dtype=np.float64)
+    ty = np.asarray(theta_y, dtype=np.float64)
+    if tx.shape != ty.shape:
+        raise ValueError("theta_x and theta_y must have the same shape")
+    pts = np.stack([x, y, b.real, b.imag], axis=1).astype(np.float32)
+    th = np.stack([tx.ravel(), ty.ravel()], axis=1).astype(np.float32)
+    d_pts = torch.from_numpy(np.ascontiguousarray(pts)).to("cuda")
+    d_th = torch.from_numpy(np.ascontiguousarray(th)).to("cuda")
+    out = torch.empty((th.shape[0], 2), dtype=torch.float32, device="cuda")
+    _lib.check(lib.sosat_nudft_direct(ctypes.c_void_p(d_pts.data_ptr()), pts.shape[0],
+                                      ctypes.c_void_p(d_th.data_ptr()), th.shape[0],
+                                      1.0 / float(lam), ctypes.c_void_p(out.data_ptr()),
+                                      _stream(torch)))
+    res = out.cpu().numpy()
+    return (res[:, 0] + 1j * res[:, 1]).reshape(tx.shape)

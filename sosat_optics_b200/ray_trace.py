@@ -1,0 +1,296 @@
+"""Drop-in for the hot-path functions of the reference's ``sosat_optics/ray_trace.py``.
+
+Same names, arguments and return values as the reference; the arithmetic runs in
+libsosat_b200.so on the GPU (csrc/trace.cu).  PyTorch is used only to own device memory and
+the CUDA stream.
+
+======================  ==========================  ==========================================
+function                reference                   device code
+======================  ==========================  ==========================================
+``rx_to_lyot``          ray_trace.py:1070-1591      ``sosat_trace_rays``  (trace_rows_kernel)
+``getNearField``        ray_trace.py:1594-1614      ``sosat_near_field_arrays``
+``near_field_binned``   -- (north_star, row a7)     ``sosat_trace_bin``   (trace_bin_kernel)
+``get_fwhm`` etc.       ray_trace.py:1648-1672,     host numpy helpers (cheap reductions over the
+``ff_fwhm_est``         1757-1779                   returned arrays; out of scope for kernels)
+======================  ==========================  ==========================================
+
+``plot`` / ``col`` arguments are accepted and ignored (plotting is out of scope).
+"""
+from __future__ import annotations
+
+import ctypes
+from typing import Optional, Sequence
+
+import numpy as np
+
+from . import _lib, geometry
+
+__all__ = ["rx_to_lyot", "getNearField", "get_sim", "get_beam_cent", "get_fwhm",
+           "get_angle_out", "ff_fwhm_est", "near_field_binned", "trace_stats",
+           "SimOutput", "BinnedField"]
+
+
+def _torch():
+    import torch
+    if not torch.cuda.is_available():
+        raise _lib.SosatError("no CUDA device visible: sosat_optics_b200 runs only on the GPU "
+                              "(there is deliberately no CPU fallback)")
+    return torch
+
+
+def _stream(torch) -> ctypes.c_void_p:
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+_geom_cache = {}
+
+
+def _upload_geometry(lib, torch, tele_geo) -> None:
+    """sosat_set_geometry, skipped when this device already holds identical constants."""
+    g = geometry.make_geom(tele_geo)
+    dev = torch.cuda.current_device()
+    key = bytes(g)
+    if _geom_cache.get(dev) != key:
+        _lib.check(lib.sosat_set_device(dev))
+        _lib.check(lib.sosat_set_geometry(ctypes.byref(g), _stream(torch)))
+        _geom_cache[dev] = key
+
+
+def _rx_array(P_rx) -> np.ndarray:
+    rx = np.ascontiguousarray(np.asarray(P_rx, dtype=np.float64).reshape(-1))
+    if rx.size != 3:
+        raise ValueError("receiver position must have 3 components [x, y, z] in mm")
+    return rx
+
+
+def _trace_device(P_rx, tele_geo, ray_begin=0, ray_end=None):
+    """Run the tracer; returns (out [17, n] cuda float64 tensor, stats host ndarray)."""
+    lib = _lib.require_gpu()
+    torch = _torch()
+    n_scan = int(tele_geo.n_scan)
+    total = n_scan * n_scan
+    if ray_end is None:
+        ray_end = total
+    n = ray_end - ray_begin
+    _upload_geometry(lib, torch, tele_geo)
+    freq = geometry.make_freq(tele_geo)
+    rx = _rx_array(P_rx)
+    out = torch.empty((_lib.OUT_ROWS, max(n, 0)), dtype=torch.float64, device="cuda")
+    stats = torch.zeros(_lib.NUM_STATS, dtype=torch.float64, device="cuda")
+    _lib.check(lib.sosat_trace_rays(
+        rx.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.byref(freq), n_scan,
+        ray_begin, ray_end, ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(stats.data_ptr()),
+        _stream(torch)))
+    h_stats = stats.cpu().numpy()
+    if h_stats[_lib.STAT_N_BRACKET_FAIL] > 0:
+        # scipy.optimize.brentq's error, which aborts the reference's whole run
+        raise ValueError("f(a) and f(b) must have different signs")
+    return out, h_stats
+
+
+def rx_to_lyot(P_rx, tele_geo, plot=False, col="b"):
+    """Trace ``n_scan**2`` rays from the feed at ``P_rx`` [mm] through the three lenses and the
+    Lyot stop to the source plane (ray_trace.py:1070).  Returns ``out[17, n_scan**2]`` float64:
+    rows 0-2 position on the source plane, 3 optical path length, 4 amplitude, 5-7 last surface
+    normal, 8-10 exit direction, 11-16 zero."""
+    out, _ = _trace_device(P_rx, tele_geo)
+    return out.cpu().numpy()
+
+
+class SimOutput:
+    """Same attribute bag as the class defined inside the reference's getNearField
+    (ray_trace.py:1606-1612)."""
+
+    def __init__(self, x_sim, y_sim, a_sim, p_sim, tan_og):
+        self.a_sim = a_sim
+        self.p_sim = p_sim
+        self.x_sim = x_sim
+        self.y_sim = y_sim
+        self.tan_og = tan_og
+
+
+def getNearField(tele_geo, rx, plot=False):
+    """Get the near field of a receiver feed (ray_trace.py:1594-1614): positions [cm],
+    amplitude and mean-removed wrapped phase of the valid rays, and the mean exit direction."""
+    lib = _lib.require_gpu()
+    torch = _torch()
+    out, _ = _trace_device(rx, tele_geo)
+    n = out.shape[1]
+    xyap = torch.empty((4, n), dtype=torch.float64, device="cuda")
+    mask = torch.empty(n, dtype=torch.uint8, device="cuda")
+    tan_og = torch.empty(3, dtype=torch.float64, device="cuda")
+    work = torch.empty(_lib.NUM_STATS, dtype=torch.float64, device="cuda")
+    _lib.check(lib.sosat_near_field_arrays(
+        ctypes.c_void_p(out.data_ptr()), n, geometry.scalar(tele_geo.k),
+        ctypes.c_void_p(xyap.data_ptr()), ctypes.c_void_p(mask.data_ptr()),
+        ctypes.c_void_p(tan_og.data_ptr()), ctypes.c_void_p(work.data_ptr()), _stream(torch)))
+    sel = xyap[:, mask.bool()].cpu().numpy()  # xx = np.where(out[4] != 0): order-preserving
+    return SimOutput(sel[0].copy(), sel[1].copy(), sel[2].copy(), sel[3].copy(),
+                     tan_og.cpu().numpy())
+
+
+# --- host helpers over the returned arrays (ray_trace.py:1648-1672, 1757-1779) ------------
+def get_sim(sb):
+    return sb.a_sim, sb.p_sim, sb.x_sim, sb.y_sim
+
+
+def get_beam_cent(sb):
+    return [np.mean(sb.x_sim), np.mean(sb.y_sim)]
+
+
+def get_fwhm(sb):
+    """Half-extent of the rays above half power; note the reference's swapped x/y naming."""
+    a_sim, _, x_sim, y_sim = get_sim(sb)
+    beam_cent = get_beam_cent(sb)
+    above = np.where(a_sim ** 2 > np.max(a_sim ** 2) / 2)
+    fwhm_nf_x = abs(y_sim - beam_cent[1])[above].max()
+    fwhm_nf_y = abs(x_sim - beam_cent[0])[above].max()
+    return fwhm_nf_x, fwhm_nf_y
+
+
+def get_angle_out(sb):
+    theta_x = abs(90 - np.rad2deg(np.arctan2(sb.tan_og[1], sb.tan_og[2])))
+    theta_y = abs(90 - np.rad2deg(np.arctan2(sb.tan_og[1], sb.tan_og[0])))
+    return [theta_x, theta_y]
+
+
+def ff_fwhm_est(beam_fft, x_ang, y_ang):
+    """FWHM [arcmin] of |B|^2 through the peak row and column (ray_trace.py:1757-1779)."""
+    a = abs(beam_fft) ** 2 / np.max(abs(beam_fft) ** 2)
+    x_out, y_out = y_ang, x_ang
+    indx = np.where(abs(a) == np.max(abs(a)))
+    x = y_out[indx[0][0], :] * 60 * 180 / np.pi
+    y = abs(a)[indx[0][0], :] / np.max(abs(a))
+    fwhm1 = abs(x[np.where(y > 0.5)][0] - x[np.where(y > 0.5)][-1])
+    x = x_out[:, indx[1][0]] * 60 * 180 / np.pi
+    y = abs(a)[:, indx[1][0]] / np.max(abs(a))
+    fwhm2 = abs(x[np.where(y > 0.5)][0] - x[np.where(y > 0.5)][-1])
+    return (fwhm1 + fwhm2) / 2
+
+
+# --- fused trace + binning (north_star) -------------------------------------------------------
+class BinnedField:
+    """Result of :func:`near_field_binned`.
+
+    ``b``      complex64 ``[n_rx, n_freq, N, N]`` mean of ``a exp(i p)`` per cell (0 where empty),
+               phase referred to the mean optical path of the valid rays;
+    ``count``  float32 ``[n_rx, N, N]`` rays per cell;
+    ``stats``  float64 ``[n_rx, 8]`` (``_lib.STAT_*``);
+    ``x_cm`` / ``y_cm``  cell-centre coordinates (x_sim / y_sim convention, cm).
+    Arrays are numpy unless ``device=True`` was requested (then torch CUDA tensors).
+    """
+
+    def __init__(self, b, count, stats, extent_cm, grid_n, re=None, im=None):
+        self.b, self.count, self.stats = b, count, stats
+        self.extent_cm, self.grid_n = extent_cm, grid_n
+        self.re, self.im = re, im
+        edges = (np.arange(grid_n) + 0.5) * (extent_cm / grid_n) - extent_cm / 2
+        self.x_cm = edges
+        self.y_cm = edges.copy()
+
+    @property
+    def mean_opl(self):
+        return self.stats[:, _lib.STAT_SUM_OPL] / np.maximum(self.stats[:, _lib.STAT_N_VALID], 1)
+
+
+def trace_bin_device(tele_geo, rx_list, freq_specs, grid_n, extent_mm, *, opl_ref=0.0,
+                     row_begin=0, row_end=None, planes=None, stats=None, bins=True):
+    """Launch ``sosat_trace_bin`` on the current device/stream and return the raw accumulators
+    ``(re, im, cnt, stats)`` as CUDA tensors (accumulated into ``planes`` / ``stats`` when
+    given, so several row blocks -- or several GPUs after an all-reduce -- add up)."""
+    lib = _lib.require_gpu()
+    torch = _torch()
+    n_scan = int(tele_geo.n_scan)
+    if row_end is None:
+        row_end = n_scan
+    rx = np.ascontiguousarray(np.asarray(rx_list, dtype=np.float64).reshape(-1, 3))
+    n_rx = rx.shape[0]
+    freqs = geometry.make_freqs(freq_specs)
+    n_freq = len(freqs)
+    _upload_geometry(lib, torch, tele_geo)
+    d_rx = torch.from_numpy(rx).to("cuda")
+    if stats is None:
+        stats = torch.zeros((n_rx, _lib.NUM_STATS), dtype=torch.float64, device="cuda")
+    if bins:
+        if planes is None:
+            re = torch.zeros((n_rx, n_freq, grid_n, grid_n), dtype=torch.float32, device="cuda")
+            im = torch.zeros_like(re)
+            cnt = torch.zeros((n_rx, grid_n, grid_n), dtype=torch.float32, device="cuda")
+        else:
+            re, im, cnt = planes
+        ptrs = [ctypes.c_void_p(t.data_ptr()) for t in (re, im, cnt)]
+    else:
+        re = im = cnt = None
+        ptrs = [ctypes.c_void_p(0)] * 3
+    _lib.check(lib.sosat_trace_bin(
+        ctypes.c_void_p(d_rx.data_ptr()), n_rx, freqs, n_freq, n_scan, row_begin, row_end,
+        int(grid_n), float(extent_mm), float(opl_ref), *ptrs, ctypes.c_void_p(stats.data_ptr()),
+        _stream(torch)))
+    return re, im, cnt, stats
+
+
+def bins_to_field_device(re, im, cnt, stats, freq_specs, opl_ref=0.0):
+    """Normalise the accumulators to the mean field per cell and refer the phase to the mean
+    OPL of the valid rays (the reference's ``OPL - mean(OPL)``, ray_trace.py:1601)."""
+    lib = _lib.require_gpu()
+    torch = _torch()
+    n_rx, n_freq, n, _ = re.shape
+    b = torch.empty((n_rx, n_freq, n, n, 2), dtype=torch.float32, device="cuda")
+    h_stats = stats.cpu().numpy()
+    for i in range(n_rx):
+        nv = h_stats[i, _lib.STAT_N_VALID]
+        mean_opl = h_stats[i, _lib.STAT_SUM_OPL] / nv if nv > 0 else 0.0
+        for f, (k, _, _) in enumerate(freq_specs):
+            phi0 = geometry.scalar(k) / 1e3 / 2 * (mean_opl - opl_ref)
+            phi0 = float(np.mod(phi0, 2 * np.pi))
+            _lib.check(lib.sosat_bins_to_field(
+                ctypes.c_void_p(re[i, f].data_ptr()), ctypes.c_void_p(im[i, f].data_ptr()),
+                ctypes.c_void_p(cnt[i].data_ptr()), n * n, phi0,
+                ctypes.c_void_p(b[i, f].data_ptr()), _stream(torch)))
+    return torch.view_as_complex(b), h_stats
+
+
+def near_field_binned(tele_geo, rx, grid_n: int = 256, extent_cm: Optional[float] = None,
+                      freqs: Optional[Sequence] = None, *, device: bool = False,
+                      keep_sums: bool = False) -> BinnedField:
+    """Trace the ray bundle of one or several feeds and bin it into the complex near field
+    ``b(x, y)`` on a regular ``grid_n x grid_n`` grid over ``[-extent/2, extent/2)^2`` of the
+    source plane (default extent: ``tele_geo.diam`` = 42 cm, the stop diameter).
+
+    ``rx``     one position ``[x, y, z]`` mm or a sequence of them (focal-plane sweep);
+    ``freqs``  ``None`` -> the frequency currently set on ``tele_geo``; else a sequence of
+               ``(k, th_fwhp_x, th_fwhp_y)`` (see geometry.freq_specs_from_table).  The ray
+               geometry is frequency independent, so all frequencies share one trace.
+    """
+    if extent_cm is None:
+        extent_cm = geometry.scalar(getattr(tele_geo, "diam", 0.42)) * 100.0
+    specs = list(freqs) if freqs is not None else [
+        (tele_geo.k, tele_geo.th_fwhp_x, tele_geo.th_fwhp_y)]
+    out_b, out_c, out_s, out_re, out_im = [], [], [], [], []
+    rx_arr = np.asarray(rx, dtype=np.float64).reshape(-1, 3)
+    for f0 in range(0, len(specs), _lib.MAX_FREQS):
+        chunk = specs[f0:f0 + _lib.MAX_FREQS]
+        re, im, cnt, stats = trace_bin_device(tele_geo, rx_arr, chunk, grid_n, extent_cm * 10.0)
+        b, h_stats = bins_to_field_device(re, im, cnt, stats, chunk)
+        out_b.append(b)
+        out_c, out_s = cnt, h_stats
+        if keep_sums:
+            out_re.append(re)
+            out_im.append(im)
+    torch = _torch()
+    b = torch.cat(out_b, dim=1)
+    re = torch.cat(out_re, dim=1) if keep_sums else None
+    im = torch.cat(out_im, dim=1) if keep_sums else None
+    if not device:
+        b, out_c = b.cpu().numpy(), out_c.cpu().numpy()
+        re = re.cpu().numpy() if keep_sums else None
+        im = im.cpu().numpy() if keep_sums else None
+    return BinnedField(b, out_c, out_s, extent_cm, grid_n, re, im)
+
+
+def trace_stats(tele_geo, rx):
+    """Statistics-only pass (no binning): per-feed ``[n_valid, sum OPL, sum exit dir, ...]``."""
+    rx_arr = np.asarray(rx, dtype=np.float64).reshape(-1, 3)
+    spec = [(tele_geo.k, tele_geo.th_fwhp_x, tele_geo.th_fwhp_y)]
+    _, _, _, stats = trace_bin_device(tele_geo, rx_arr, spec, 0, 0.0, bins=False)
+    return stats.cpu().numpy()
