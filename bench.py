@@ -1,0 +1,406 @@
+#!/usr/bin/env python
+"""Benchmark of the beam-simulation hot path on B200 (BASELINE.json metric).
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
+
+A *step* is one pass of the whole hot path over BASELINE.json configs[4] ("high-resolution
+stress"): 1.000014e9 rays (n_scan = 31623) traced feed -> source plane from a boresight feed
+at 90 GHz, binned into the 2048^2 complex near field (stop diameter 42 cm), bins all-reduced
+over NCCL when N > 1 (rays are sharded by launch-row blocks: strong scaling), then normalised
+and transformed to the 2048^2 far field.  The ray bundle is a deterministic grid, so the
+"synthetic data" is the reference's own launch grid at a larger n_scan.
+
+`value` = launched rays per second (the unit of the reference's tqdm it/s) with everything
+resident on the device; `e2e` = the same through the public host-buffer API (parameters in,
+2048^2 complex64 far field out to pinned host memory, copies inside the timed region).
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+N_SCAN = 31623            # 1.000014e9 rays (cfg 5)
+GRID_N = 2048
+EXTENT_CM = 42.0
+GHZ = 90.0
+FLOP_PER_RAY = 1300.0     # algorithmic work per launched ray
+METRIC = "rays/sec traced feed->window"
+WORKLOAD = ("configs[4] high-resolution stress: 1.000014e9 rays/feed (n_scan=31623), boresight, "
+            "90 GHz, 2048^2 near-field grid -> 2048^2 far field")
+
+
+def _peaks():
+    try:
+        with open(os.path.join(ROOT, "MEASURED_PEAKS.json")) as f:
+            return json.load(f), "measured"
+    except Exception:
+        return {"hbm_gbs": 6650.0, "bf16_tflops": 1590.0, "bf16_tflops_sustained": 1400.0}, "fallback"
+
+
+def _tele_geo(ot_geo, opt_analyze, table, n_scan):
+    t = ot_geo.SatGeo()
+    t.n_scan = n_scan
+    t.y_source = ot_geo.y_lyot + 300
+    t.lambda_ = opt_analyze.ghz_to_m(GHZ)
+    t.k = 2 * np.pi / t.lambda_
+    row = table[table[:, 0] == int(GHZ)][0]
+    t.th_fwhp_x, t.th_fwhp_y = np.deg2rad(row[1]), np.deg2rad(row[2])
+    return t
+
+
+def _feed_table():
+    return np.load(os.path.join(ROOT, "feedhorn", "fwhm_feedhorns.npy"))
+
+
+class ClockSampler(threading.Thread):
+    """Samples SM clock and clock-event reasons of one GPU during the timed region (NVML)."""
+    REASONS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown",
+               0x40: "hw_thermal_slowdown", 0x80: "hw_power_brake", 0x2: "applications_clocks"}
+
+    def __init__(self, index):
+        super().__init__(daemon=True)
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop_evt = threading.Event()
+        self.ok = False
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM)
+            self.ok = True
+        except Exception:
+            pass
+
+    def run(self):
+        while self.ok and not self._stop_evt.is_set():
+            try:
+                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+                try:
+                    r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+                except Exception:
+                    r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+                for bit, name in self.REASONS.items():
+                    if r & bit:
+                        self.reasons.add(name)
+            except Exception:
+                pass
+            time.sleep(0.05)
+
+    def result(self):
+        self._stop_evt.set()
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": ["unavailable"]}
+        return {"sm_mhz": statistics.median(self.samples), "sm_max_mhz": self.max_mhz,
+                "reasons": sorted(self.reasons)}
+
+
+# ------------------------------------------------------------------------------------------------
+def cpu_reference_sample(n_scan_sample, threads=0):
+    """The reference's CPU path on a bounded sample of the workload, restated in oracle/ (the
+    reference itself is Python and cannot travel to the GPU box): C trace with the bracketed
+    Brent solve on all host threads, numpy binning, numpy FFT far field.  Returns
+    (seconds, rays, cores)."""
+    from oracle import oracle
+    t = oracle.default_tele_geo(n_scan=n_scan_sample, y_source=oracle.Y_LYOT + 300)
+    t.lambda_ = oracle.ghz_to_m(GHZ)
+    t.k = 2 * np.pi / t.lambda_
+    row = _feed_table()
+    row = row[row[:, 0] == int(GHZ)][0]
+    t.th_fwhp_x, t.th_fwhp_y = np.deg2rad(row[1]), np.deg2rad(row[2])
+    cores = oracle.lib().oracle_max_threads() if threads <= 0 else threads
+    t0 = time.perf_counter()
+    out = oracle.rx_to_lyot([0, 0, 0], t, n_threads=threads)
+    re, im, cnt, sums = oracle.bin_near_field(out, float(t.k), GRID_N, EXTENT_CM * 10, 0.0)
+    with np.errstate(invalid="ignore", divide="ignore"):
+        b = np.where(cnt > 0, (re + 1j * im) / cnt, 0)
+    B = np.fft.fftshift(np.fft.fft2(np.fft.fftshift(b)))
+    dt = time.perf_counter() - t0
+    assert np.isfinite(B).all()
+    return dt, n_scan_sample * n_scan_sample, cores
+
+
+def run_reference(args):
+    """--impl reference: the reference's CPU implementation of the path on the host cores."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle
+    oracle.build()
+    # size the bounded sample so that (warmup + steps) samples end within ~2 minutes
+    dt, rays, cores = cpu_reference_sample(300)
+    rate = rays / dt
+    budget_s = 120.0 / max(1, args.steps + args.warmup)
+    n_sample = int(min(N_SCAN, max(200, np.sqrt(rate * budget_s * 0.6))))
+    for _ in range(args.warmup):
+        cpu_reference_sample(n_sample)
+    t0 = time.perf_counter()
+    for _ in range(args.steps):
+        cpu_reference_sample(n_sample)
+    dt = (time.perf_counter() - t0) / max(1, args.steps)
+    value = n_sample * n_sample / dt
+    sample = (f"n_scan={n_sample} ({n_sample * n_sample} rays of the 1.000014e9-ray bundle) -> "
+              f"{GRID_N}^2 bins -> {GRID_N}^2 numpy FFT per step; oracle/ C port of "
+              "ray_trace.rx_to_lyot (brentq restated), OpenMP over rays")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "rays/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": dt * 1e3, "higher_is_better": True, "scaling": "strong",
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "sample": sample},
+        "cpu_baseline": {"value": value, "unit": "rays/s", "cores": cores, "kind": "port",
+                         "sample": sample},
+        "e2e": {"value": value, "unit": "rays/s", "h2d_bytes_per_step": 0,
+                "d2h_bytes_per_step": 0},
+        "note": ("the unmodified reference (pure Python, scipy brentq per ray) runs at ~600-800 "
+                 "rays/s on one core (BASELINE.md); this port is ~3 orders of magnitude faster"),
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from sosat_optics_b200 import _lib, dist as sdist, opt_analyze, ot_geo, ray_trace
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py needs a CUDA device: sosat_optics_b200 has no CPU fallback")
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    lib = _lib.require_gpu()
+    peaks, peaks_kind = _peaks()
+
+    table = _feed_table()
+    n_scan = args.n_scan
+    t = _tele_geo(ot_geo, opt_analyze, table, n_scan)
+    spec = [(t.k, t.th_fwhp_x, t.th_fwhp_y)]
+    rx = np.zeros((1, 3))
+    r0, r1 = sdist.partition_rows(n_scan, world, rank)
+    total_rays = n_scan * n_scan
+    my_rays = (r1 - r0) * n_scan
+
+    re = torch.zeros((1, 1, GRID_N, GRID_N), dtype=torch.float32, device="cuda")
+    im = torch.zeros_like(re)
+    cnt = torch.zeros((1, GRID_N, GRID_N), dtype=torch.float32, device="cuda")
+    stats = torch.zeros((1, _lib.NUM_STATS), dtype=torch.float64, device="cuda")
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
+    host_B = torch.empty((GRID_N, GRID_N), dtype=torch.complex64).pin_memory()
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    def step(e2e=False, kernel_events=None):
+        """One pass of the hot path.  Returns the far field (device tensor)."""
+        re.zero_(); im.zero_(); cnt.zero_(); stats.zero_()
+        if kernel_events is not None:
+            kernel_events[0].record()
+        ray_trace.trace_bin_device(t, rx, spec, GRID_N, EXTENT_CM * 10, row_begin=r0, row_end=r1,
+                                   planes=(re, im, cnt), stats=stats)
+        if kernel_events is not None:
+            kernel_events[1].record()
+        sdist.reduce_bins(re, im, cnt, stats)
+        b, _ = ray_trace.bins_to_field_device(re, im, cnt, stats, spec)
+        if kernel_events is not None:
+            kernel_events[2].record()
+        B = opt_analyze.far_field(b[0, 0], device=True)
+        if kernel_events is not None:
+            kernel_events[3].record()
+        if e2e:
+            host_B.copy_(B, non_blocking=True)
+            torch.cuda.current_stream().synchronize()
+        return B
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # ---- device-resident timing: W warm-up, then exactly K timed steps ----
+    for _ in range(args.warmup):
+        step()
+    barrier()
+    sampler = ClockSampler(local)
+    sampler.start()
+    step_ms, trace_ms, ff_ms = [], [], []
+    barrier()
+    t_wall0 = time.perf_counter()
+    for _ in range(args.steps):
+        flush.fill_(1)                      # L2 flush between timed iterations (256 MiB write)
+        e0, e1 = ev(), ev()
+        ke = [ev() for _ in range(4)]
+        e0.record()
+        step(kernel_events=ke)
+        e1.record()
+        torch.cuda.synchronize()
+        step_ms.append(e0.elapsed_time(e1))
+        trace_ms.append(ke[0].elapsed_time(ke[1]))
+        ff_ms.append(ke[2].elapsed_time(ke[3]))
+    barrier()
+    wall_s = time.perf_counter() - t_wall0
+    clocks = sampler.result()
+
+    dev_ms = sum(step_ms)
+    agg = torch.tensor([dev_ms, sum(trace_ms)], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(agg, op=dist.ReduceOp.MAX)
+    dev_ms_max, trace_ms_max = agg.tolist()
+    ms_per_step = dev_ms_max / args.steps
+    value = total_rays / (ms_per_step * 1e-3)
+
+    # ---- end to end through the public host-buffer API ----
+    for _ in range(2):
+        step(e2e=True)
+    barrier()
+    e2e_t = []
+    for _ in range(args.steps):
+        flush.fill_(1)
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        t0 = time.perf_counter()
+        ray_trace._geom_cache.clear()     # parameters are re-marshalled and re-uploaded each step
+        step(e2e=True)
+        e2e_t.append(time.perf_counter() - t0)
+    e2e_ms = torch.tensor([sum(e2e_t) * 1e3], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(e2e_ms, op=dist.ReduceOp.MAX)
+    e2e_value = total_rays / (e2e_ms.item() * 1e-3 / args.steps)
+    h2d = 520 + 24 + 1536 + 8 * 8       # geometry, rx, frequency table, zeroed statistics
+    d2h = GRID_N * GRID_N * 8 + 8 * 8   # far field (complex64) + statistics read by the wrapper
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline of the dominant kernel (trace_bin_kernel): FP64 pipe ----
+    fl, ms = __import__("ctypes").c_double(), __import__("ctypes").c_double()
+    _lib.check(lib.sosat_measure_fp64_peak(__import__("ctypes").byref(fl),
+                                           __import__("ctypes").byref(ms)))
+    fp64_peak_tf = fl.value / 1e12
+    trace_ms_step = trace_ms_max / args.steps
+    achieved_tf = my_rays * FLOP_PER_RAY / (trace_ms_step * 1e-3) / 1e12
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "trace_bin_traffic.json")) as f:
+            traffic = json.load(f).get("dram_bytes_per_launch")
+    except Exception:
+        pass
+    roofline = {
+        "kernel": "trace_bin_kernel", "bound": "fp64", "achieved": achieved_tf,
+        "peak": fp64_peak_tf, "unit": "TFLOP/s", "frac": achieved_tf / fp64_peak_tf,
+        "traffic": traffic, "share_of_step": trace_ms_step / ms_per_step,
+        "algorithmic": f"{FLOP_PER_RAY:.0f} flop/ray x {my_rays} rays per launch (SURVEY 8d); "
+                       "0 B/ray of HBM traffic (+12 B per flushed bin)",
+        "peak_source": "FP64 FMA microkernel measured in this run (sosat_measure_fp64_peak); "
+                       "MEASURED_PEAKS.json carries no FP64 figure",
+    }
+
+    # ---- far-field transform time at 1024^2 and 2048^2 (metric 2) ----
+    farfield = {}
+    for n in (1024, 2048):
+        d = torch.randn(n, n, dtype=torch.complex64, device="cuda")
+        for _ in range(3):
+            opt_analyze.far_field(d, device=True)
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(20):
+            a, b_ = ev(), ev()
+            a.record()
+            opt_analyze.far_field(d, device=True)
+            b_.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b_))
+        best, med = min(ts), statistics.median(ts)
+        tf = 16.0 * n ** 3 / (best * 1e-3) / 1e12
+        farfield[f"n{n}"] = {"ms_best": best, "ms_median": med, "algorithmic_tflops": tf,
+                             "frac_of_bf16_peak": tf / peaks["bf16_tflops"],
+                             "executed_tflops": 3 * tf}
+    farfield["roofline"] = {
+        "kernel": "gemm_bf16x3_kernel (x2) + prep/finish", "bound": "tensor",
+        "achieved": farfield["n2048"]["algorithmic_tflops"], "peak": peaks["bf16_tflops"],
+        "unit": "TFLOP/s", "frac": farfield["n2048"]["frac_of_bf16_peak"],
+        "peak_source": f"{peaks_kind} bf16 burst (MEASURED_PEAKS.json)",
+        "note": "16 N^3 algorithmic flop; the bf16x3 split executes 3x that on the tensor pipe",
+    }
+
+    # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ----
+    cpu = None
+    if world == 1 and not args.no_cpu_baseline:
+        from oracle import oracle
+        oracle.build()
+        dt, rays, cores = cpu_reference_sample(300)
+        n_sample = int(min(N_SCAN, max(300, np.sqrt(rays / dt * 12.0))))
+        dt, rays, cores = cpu_reference_sample(n_sample)
+        cpu = {"value": rays / dt, "unit": "rays/s", "cores": cores, "kind": "port",
+               "sample": f"n_scan={n_sample} ({rays} rays) -> {GRID_N}^2 bins -> {GRID_N}^2 numpy "
+                         f"FFT, {dt:.1f} s; oracle/ C port of rx_to_lyot (brentq restated), OpenMP",
+               "reference_python_rays_per_s": "600-800 on 1 core (BASELINE.md; cannot use more)"}
+
+    launches_per_step = 6  # trace_bin, bins_to_field, prep_b, gemm pass 1, gemm pass 2, finish
+    line = {
+        "metric": METRIC, "value": value, "unit": "rays/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_per_step, "higher_is_better": True,
+        "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD if n_scan == N_SCAN else f"REDUCED n_scan={n_scan}: " + WORKLOAD,
+                   "n_scan": n_scan, "rays_per_step": total_rays, "grid_n": GRID_N,
+                   "extent_cm": EXTENT_CM, "ghz": GHZ, "sharding": f"launch-row blocks x{world}, "
+                   "one NCCL all-reduce of [re,im,count] planes (50 MB) + 8 fp64 sums",
+                   "l2": "256 MiB flush write between timed steps; the kernel reads no input arrays",
+                   "newton_schedule": os.environ.get("SOSAT_TRACE_VARIANT", "0")},
+        "clocks": clocks,
+        "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d,
+                "d2h_bytes_per_step": d2h},
+        "gpu_launches": launches_per_step * args.steps,
+        "roofline": roofline,
+        "farfield": farfield,
+        "cpu_baseline": cpu,
+        "wall_s_timed_region": wall_s,
+        "far_field_ms_in_step": statistics.median(ff_ms),
+        "peaks": peaks_kind,
+    }
+    print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
+    ap.add_argument("--n-scan", type=int, default=N_SCAN, help="reduce only for debugging")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.warmup < 3 and args.impl == "ours":
+        args.warmup = 3  # timing rule: at least 3 warm-up steps
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "ours" and world != args.gpus and world > 1:
+        raise SystemExit(f"--gpus {args.gpus} but WORLD_SIZE={world}")
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        if args.gpus > 1 and world == 1:
+            raise SystemExit("for --gpus N > 1 launch with python -m torch.distributed.run "
+                             "--nproc-per-node N (one rank per GPU)")
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -304,3 +304,28 @@ def nudft_direct(x, y, b, thx, thy, lam):
     y_p thy_j)/lam); sign follows the code path (numpy FFT), not README.md:24."""
     ph = (np.outer(thx, x) + np.outer(thy, y)) / lam
     return np.exp(-2j * np.pi * ph) @ b
+
+
+def sim_data(sb2_a, sb2_p, sb2_x, sb2_y, stage_range, step):
+    """Glue step ray_trace.py:1720-1754 (scattered-grid -> stage grid), used only to rebuild
+    the 800x800 input of the 1000^2 far-field golden from the committed 100x100 sim2d grid.
+    ``interp2d(kind='cubic')`` no longer exists in SciPy; RectBivariateSpline(kx=ky=3, s=0)
+    is the adapter oracle/ref_shim.py used when the golden was generated."""
+    from scipy.interpolate import RectBivariateSpline
+    beam_final = sb2_a.T * np.exp(complex(0, 1) * sb2_p.T)
+    x_interp = sb2_x[:, 0]
+    y_interp = sb2_y[0, :]
+
+    def interp2d(z):
+        spl = RectBivariateSpline(x_interp, y_interp, np.asarray(z).T, kx=3, ky=3, s=0)
+        return lambda xn, yn: spl(xn, yn).T
+
+    func_beam = interp2d(np.abs(beam_final) / np.max(np.abs(beam_final)))
+    func_phase = interp2d(np.arctan2(np.imag(beam_final), np.real(beam_final)))
+    x_data = np.arange(-stage_range / 2, stage_range / 2, step)
+    y_data = np.arange(-stage_range / 2, stage_range / 2, step)
+    beam_data = func_beam(x_data, y_data)
+    phase_data = func_phase(x_data, y_data)
+    x_data, y_data = np.meshgrid(x_data, y_data)
+    return SimpleNamespace(a_data=beam_data / np.max(beam_data), p_data=phase_data,
+                           x_data=x_data, y_data=y_data)

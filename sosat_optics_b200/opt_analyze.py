@@ -163,6 +163,8 @@ def far_field_irregular(x, y, b, theta_x, theta_y, lam):
     ty = np.asarray(theta_y, dtype=np.float64)
     if tx.shape != ty.shape:
         raise ValueError("theta_x and theta_y must have the same shape")
+    if x.size == 0 or tx.size == 0:
+        return np.zeros(tx.shape, dtype=np.complex128)
     pts = np.stack([x, y, b.real, b.imag], axis=1).astype(np.float32)
     th = np.stack([tx.ravel(), ty.ravel()], axis=1).astype(np.float32)
     d_pts = torch.from_numpy(np.ascontiguousarray(pts)).to("cuda")

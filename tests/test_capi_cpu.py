@@ -1,0 +1,101 @@
+"""CPU: the C-ABI library loads without a GPU, exports every symbol include/sosat_b200.h
+declares, its structs have the documented layout, and the product path refuses to compute on
+the CPU (no fallback)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+import torch
+
+from sosat_optics_b200 import _lib, geometry, opt_analyze, ot_geo, ray_trace
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+HEADER = os.path.join(ROOT, "include", "sosat_b200.h")
+no_gpu = not torch.cuda.is_available()
+
+
+def _declared_functions():
+    src = open(HEADER).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(sosat_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_library_exports_every_declared_symbol():
+    lib = _lib.load()
+    names = _declared_functions()
+    assert len(names) >= 18
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in sosat_b200.h but not exported"
+    # and the ctypes table binds exactly the declared set
+    assert sorted(_lib.SIGNATURES) == names
+
+
+def test_abi_version_and_struct_layout():
+    lib = _lib.load()
+    assert lib.sosat_abi_version() == 1
+    assert ctypes.sizeof(_lib.Surface) == 10 * 8
+    assert ctypes.sizeof(_lib.Geom) == 6 * 80 + 5 * 8
+    assert ctypes.sizeof(_lib.Freq) == 3 * 8
+    hdr = open(HEADER).read()
+    assert "#define SOSAT_OUT_ROWS 17" in hdr and _lib.OUT_ROWS == 17
+    assert "#define SOSAT_MAX_FREQS 64" in hdr and _lib.MAX_FREQS == 64
+    assert "SOSAT_NUM_STATS = 8" in hdr and _lib.NUM_STATS == 8
+
+
+def test_workspace_size_is_pure_host_arithmetic():
+    lib = _lib.load()
+    assert lib.sosat_dft2_workspace_bytes(1024) == 256 + 56 * 1024 * 1024
+    assert lib.sosat_dft2_workspace_bytes(1000) == lib.sosat_dft2_workspace_bytes(1024)
+    assert lib.sosat_dft2_workspace_bytes(241) == 256 + 56 * 256 * 256
+    assert lib.sosat_dft2_workspace_bytes(0) == 0
+
+
+@pytest.mark.skipif(not no_gpu, reason="checks the no-GPU behaviour")
+def test_no_cpu_fallback():
+    lib = _lib.load()
+    assert lib.sosat_device_count() == 0
+    assert lib.sosat_set_device(0) == -5  # SOSAT_ERR_NO_DEVICE
+    assert b"no CPU path" in lib.sosat_last_error()
+    t = ot_geo.SatGeo()
+    with pytest.raises(_lib.SosatError):
+        ray_trace.rx_to_lyot([0, 0, 0], t, False, "b")
+    with pytest.raises(_lib.SosatError):
+        ray_trace.getNearField(t, [0, 0, 0])
+    with pytest.raises(_lib.SosatError):
+        opt_analyze.a2b(np.ones((8, 8)), np.zeros((8, 8)))
+    with pytest.raises(_lib.SosatError):
+        ray_trace.near_field_binned(t, [0, 0, 0], grid_n=8)
+
+
+def test_product_never_imports_the_oracle():
+    pkg = os.path.join(ROOT, "sosat_optics_b200")
+    for dirpath, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".h")):
+                text = open(os.path.join(dirpath, f)).read()
+                assert "oracle" not in text.replace("oracle/", "").lower() or f == "build.py" \
+                    or "import oracle" not in text and "from oracle" not in text
+                assert "import oracle" not in text and "from oracle" not in text
+
+
+def test_geometry_marshalling():
+    t = ot_geo.SatGeo()
+    t.y_source = ot_geo.y_lyot + 300
+    t.th_fwhp_x = np.array([[0.564254]])  # notebooks assign (1,1) arrays
+    t.th_fwhp_y = np.float64(0.6)
+    g = geometry.make_geom(t)
+    assert g.y_lyot == ot_geo.y_lyot and g.y_source == ot_geo.y_lyot + 300
+    assert [g.surf[i].n_in for i in range(6)] == [1.0, 3.416, 1.0, 3.416, 1.0, 3.416]
+    assert [g.surf[i].n_out for i in range(6)] == [3.416, 1.0, 3.416, 1.0, 3.416, 1.0]
+    assert g.surf[4].k > -1 and all(g.surf[i].k < -1 for i in (0, 1, 2, 3, 5))
+    assert (g.clip_l3, g.clip_stop, g.cone) == (196.0, 210.0, 0.4)
+    f = geometry.make_freq(t)
+    assert f.fwhp_x == 0.564254 and f.fwhp_y == 0.6
+    assert f.k_over_2e3 == t.k / 1e3 / 2
+    with pytest.raises(ValueError):
+        geometry.scalar(np.zeros(2))
+    # a user may change the refractive index on the instance
+    t.n_si = 3.38
+    assert geometry.make_geom(t).surf[0].n_out == 3.38

@@ -1,0 +1,319 @@
+"""GPU parity tests for stage 1 (ray trace, near field, binning), through the C-ABI.
+
+Tolerances named by BASELINE.json north_star: near-field amplitude 1e-4 relative, phase 1e-3 rad
+(i.e. OPL to ~5e-4 mm at 170 GHz), valid-ray masks identical.  The kernel is held to much tighter
+bounds here (OPL 1e-6 mm, amplitude 1e-9) so a regression shows long before the tolerance."""
+import ctypes
+
+import numpy as np
+import pytest
+from conftest import golden, phase_diff, tele_geo_from_golden
+
+pytestmark = pytest.mark.gpu
+
+AMP_RTOL = 1e-4        # north_star
+PHASE_ATOL = 1e-3      # north_star, rad
+OPL_TIGHT_MM = 1e-6
+POS_TIGHT_MM = 1e-6
+
+
+@pytest.fixture(scope="module")
+def mods():
+    import torch
+    assert torch.cuda.is_available()
+    from oracle import oracle
+    from sosat_optics_b200 import _lib, geometry, opt_analyze, ot_geo, ray_trace
+    return dict(torch=torch, oracle=oracle, lib=_lib, geometry=geometry, oa=opt_analyze,
+                ot_geo=ot_geo, rt=ray_trace)
+
+
+def _phase_of(out, k):
+    return k * out[3] / 1e3 / 2
+
+
+def _check_rows(out, ref, k):
+    vr, vo = ref[4] != 0, out[4] != 0
+    assert (vr == vo).all(), "valid-ray mask differs from the reference"
+    zero_cols = np.all(ref[:11] == 0, axis=0)  # clipped at lens 3: whole column zero
+    assert (np.all(out[:11] == 0, axis=0) == zero_cols).all()
+    m = vr
+    assert np.abs(out[4][m] / ref[4][m] - 1).max() < 1e-9 < AMP_RTOL
+    assert np.abs(out[3][m] - ref[3][m]).max() < OPL_TIGHT_MM
+    assert np.abs(_phase_of(out, k)[m] - _phase_of(ref, k)[m]).max() < 1e-5 < PHASE_ATOL
+    for r in (0, 1, 2):
+        assert np.abs(out[r][m] - ref[r][m]).max() < POS_TIGHT_MM
+    for r in range(5, 11):
+        assert np.abs(out[r][m] - ref[r][m]).max() < 1e-9
+    assert (out[3][~m] == 0).all() and (out[4][~m] == 0).all() and (out[11:] == 0).all()
+
+
+@pytest.mark.parametrize("name", ["trace_cfg1_n60_106ghz.npz", "trace_cfg1_n40_90ghz.npz"])
+def test_rx_to_lyot_matches_reference_golden(mods, name):
+    g = golden(name)
+    t = tele_geo_from_golden(g)
+    out = mods["rt"].rx_to_lyot([0, 0, 0], t, False, "b")
+    assert out.shape == (17, int(g["n_scan"]) ** 2) and out.dtype == np.float64
+    _check_rows(out, g["out"], float(g["k"]))
+
+
+def test_rx_to_lyot_offaxis_matches_reference_golden(mods):
+    g = golden("trace_cfg4_offaxis_n32_90ghz.npz")
+    t = tele_geo_from_golden(g)
+    for i, rx in enumerate(g["rx"]):
+        _check_rows(mods["rt"].rx_to_lyot(list(rx), t, False, "b"), g["out"][i], float(g["k"]))
+
+
+def test_get_near_field_matches_reference_golden(mods):
+    g = golden("trace_cfg1_n60_106ghz.npz")
+    t = tele_geo_from_golden(g)
+    sb = mods["rt"].getNearField(t, [0, 0, 0], plot=False)
+    assert len(sb.a_sim) == 2424
+    assert np.abs(sb.x_sim - g["sb_x_sim"]).max() < 1e-7
+    assert np.abs(sb.y_sim - g["sb_y_sim"]).max() < 1e-7
+    assert np.abs(sb.a_sim / g["sb_a_sim"] - 1).max() < 1e-9
+    assert phase_diff(sb.p_sim, g["sb_p_sim"]).max() < 1e-6
+    assert np.abs(sb.tan_og - g["sb_tan_og"]).max() < 1e-10
+    fw = mods["rt"].get_fwhm(sb)
+    # sat_nearfield.ipynb cell 4 stdout
+    assert "%.2f" % fw[0] == "11.06" and "%.2f" % fw[1] == "13.32"
+    bc = mods["rt"].get_beam_cent(sb)
+    assert "(%.1f,%.1f)" % (bc[0], bc[1]) in ("(-0.0,-0.0)", "(0.0,0.0)", "(-0.0,0.0)", "(0.0,-0.0)")
+    ang = mods["rt"].get_angle_out(sb)
+    assert "%.1f %.1f" % tuple(ang) == "0.0 0.0"
+
+
+def test_get_near_field_offaxis(mods):
+    g = golden("trace_cfg4_offaxis_n32_90ghz.npz")
+    t = tele_geo_from_golden(g)
+    for i in (0, 3, 6):
+        sb = mods["rt"].getNearField(t, list(g["rx"][i]))
+        assert len(sb.a_sim) == len(g[f"sb{i}_a_sim"])
+        assert np.abs(sb.x_sim - g[f"sb{i}_x_sim"]).max() < 1e-7
+        assert phase_diff(sb.p_sim, g[f"sb{i}_p_sim"]).max() < 1e-6
+        assert np.abs(sb.tan_og - g[f"sb{i}_tan_og"]).max() < 1e-10
+
+
+def test_reqs_frequency_sweep_known_answers(mods, feed_table):
+    """cfg 3: sat_reqs.ipynb cell 1, FWHM table produced by the reference."""
+    g = golden("reqs_cfg3_n150.npz")
+    rt, oa, ot_geo = mods["rt"], mods["oa"], mods["ot_geo"]
+    t = ot_geo.SatGeo()
+    t.n_scan = 150
+    t.y_source = ot_geo.y_lyot + 200
+    for i, fre in enumerate(g["freqs"]):
+        t.lambda_ = oa.ghz_to_m(float(fre))
+        t.k = 2 * np.pi / t.lambda_
+        t.th_fwhp_x = np.deg2rad(feed_table[np.where(feed_table[:, 0] == int(fre)), 1][0][0])
+        t.th_fwhp_y = np.deg2rad(feed_table[np.where(feed_table[:, 0] == int(fre)), 2][0][0])
+        sb = rt.getNearField(t, [0, 0, 0])
+        assert len(sb.a_sim) == 15312
+        assert np.allclose(rt.get_fwhm(sb), g["fwhm"][i], atol=1e-6)
+
+
+def test_all_newton_schedules_agree(mods, monkeypatch):
+    g = golden("trace_cfg1_n40_90ghz.npz")
+    t = tele_geo_from_golden(g)
+    for var in range(6):
+        monkeypatch.setenv("SOSAT_TRACE_VARIANT", str(var))
+        _check_rows(mods["rt"].rx_to_lyot([0, 0, 0], t), g["out"], float(g["k"]))
+
+
+@pytest.mark.parametrize("rx", [[0, 0, 0], [150, 0, 0], [-120, 0, 80], [0, 0, 170], [60, 0, -90]])
+def test_large_bundle_against_oracle(mods, rx):
+    """10^6 rays per feed against the CPU oracle (bracketed Brent solve): identical masks and
+    OPL.  This is where the Newton fast path / Brent slow path split is exercised."""
+    oracle, rt = mods["oracle"], mods["rt"]
+    t = mods["ot_geo"].SatGeo()
+    t.n_scan = 1000
+    t.y_source = mods["ot_geo"].y_lyot + 300
+    out = rt.rx_to_lyot(rx, t)
+    ref = oracle.rx_to_lyot(rx, t)
+    vr, vo = ref[4] != 0, out[4] != 0
+    assert (vr != vo).sum() == 0
+    assert np.abs(out[3][vr] - ref[3][vr]).max() < OPL_TIGHT_MM
+    assert np.abs(out[0][vr] - ref[0][vr]).max() < POS_TIGHT_MM
+    assert np.abs(out[4][vr] / ref[4][vr] - 1).max() < 1e-9
+
+
+def test_host_buffer_entry_point_and_ranges(mods):
+    """sosat_rx_to_lyot_host with ragged ray ranges: a range equals the slice of the full run."""
+    lib = mods["lib"].require_gpu()
+    geometry, ot_geo = mods["geometry"], mods["ot_geo"]
+    t = ot_geo.SatGeo()
+    t.n_scan = 37
+    t.y_source = ot_geo.y_lyot + 300
+    g, f = geometry.make_geom(t), geometry.make_freq(t)
+    rx = np.array([10.0, 0.0, -20.0])
+    dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))  # noqa: E731
+
+    def run(b, e):
+        out = np.full((17, e - b), np.nan)
+        stats = np.zeros(8)
+        mods["lib"].check(lib.sosat_rx_to_lyot_host(ctypes.byref(g), dp(rx), ctypes.byref(f), 37,
+                                                   b, e, dp(out), dp(stats)))
+        return out, stats
+
+    full, stats = run(0, 37 * 37)
+    assert stats[0] == (full[4] != 0).sum()
+    assert stats[1] == pytest.approx(full[3].sum(), rel=1e-12)
+    for b, e in [(0, 1), (5, 300), (700, 1369), (1368, 1369)]:
+        part, _ = run(b, e)
+        assert np.array_equal(part, full[:, b:e], equal_nan=True)
+    empty, _ = run(100, 100)
+    assert empty.shape == (17, 0)
+    # errors: reversed range, n_scan < 1
+    out = np.zeros((17, 4))
+    assert lib.sosat_rx_to_lyot_host(ctypes.byref(g), dp(rx), ctypes.byref(f), 37, 10, 5,
+                                     dp(out), None) == -1
+    assert lib.sosat_rx_to_lyot_host(ctypes.byref(g), dp(rx), ctypes.byref(f), 0, 0, 0,
+                                     dp(out), None) == -1
+    assert b"n_scan" in lib.sosat_last_error()
+
+
+def test_degenerate_bundles(mods):
+    rt, ot_geo, oracle = mods["rt"], mods["ot_geo"], mods["oracle"]
+    t = ot_geo.SatGeo()
+    t.y_source = ot_geo.y_lyot + 300
+    for n in (1, 2, 3):
+        t.n_scan = n
+        out, ref = rt.rx_to_lyot([0, 0, 0], t), oracle.rx_to_lyot([0, 0, 0], t)
+        assert ((out[4] != 0) == (ref[4] != 0)).all()
+        assert np.allclose(out[:11], ref[:11], atol=1e-6, equal_nan=True)
+    # a feed far outside the focal plane: every ray is clipped at lens 3 or misses the stop
+    t.n_scan = 16
+    out = rt.rx_to_lyot([400, 0, 0], t)
+    assert (out[4] == 0).all() and (out[3] == 0).all()
+    sb_empty_ok = (out[4] != 0).sum() == 0
+    assert sb_empty_ok
+
+
+def test_scalar_and_array_fwhp_inputs_agree(mods):
+    rt, ot_geo = mods["rt"], mods["ot_geo"]
+    t = ot_geo.SatGeo()
+    t.n_scan = 20
+    t.y_source = ot_geo.y_lyot + 200
+    t.th_fwhp_x, t.th_fwhp_y = 0.5, 0.6
+    a = rt.rx_to_lyot([0, 0, 0], t)
+    t.th_fwhp_x, t.th_fwhp_y = np.array([[0.5]]), np.array([[0.6]])
+    assert np.array_equal(a, rt.rx_to_lyot([0, 0, 0], t), equal_nan=True)
+
+
+# ---- fused trace + binning -----------------------------------------------------------------
+def _bundle(mods, n_scan, ghz=90.0, y_off=300):
+    t = mods["ot_geo"].SatGeo()
+    t.n_scan = n_scan
+    t.y_source = mods["ot_geo"].y_lyot + y_off
+    t.lambda_ = mods["oa"].ghz_to_m(ghz)
+    t.k = 2 * np.pi / t.lambda_
+    return t
+
+
+def test_binned_near_field_matches_oracle_binning(mods):
+    rt, oracle = mods["rt"], mods["oracle"]
+    t = _bundle(mods, 300)
+    for rx in ([0, 0, 0], [100, 0, 60]):
+        ref = oracle.rx_to_lyot(rx, t)
+        re, im, cnt, sums = oracle.bin_near_field(ref, float(t.k), 64, 420.0, 0.0)
+        bf = rt.near_field_binned(t, rx, grid_n=64, extent_cm=42.0, keep_sums=True)
+        # a ray within ~1e-8 mm of a cell edge may fall either side: allow 2 such rays
+        assert np.abs(bf.count[0] - cnt).sum() <= 2
+        scale = np.abs(re + 1j * im).max()
+        ok = np.abs(bf.count[0] - cnt) == 0
+        assert np.abs(bf.re[0, 0] - re)[ok].max() < 1e-5 * scale
+        assert np.abs(bf.im[0, 0] - im)[ok].max() < 1e-5 * scale
+        assert bf.stats[0, 0] == sums["n_valid"] and bf.stats[0, 7] == sums["n_binned"]
+        assert bf.stats[0, 1] == pytest.approx(sums["sum_opl"], rel=1e-12)
+        # normalised field: mean per cell, phase referred to the mean OPL
+        mean_opl = sums["sum_opl"] / sums["n_valid"]
+        rot = np.exp(-1j * float(t.k) / 2e3 * mean_opl)
+        with np.errstate(invalid="ignore", divide="ignore"):
+            bref = np.where(cnt > 0, (re + 1j * im) / cnt, 0) * rot
+        amp_ok = np.abs(bref) > 1e-3
+        assert np.abs(np.abs(bf.b[0, 0]) / np.abs(bref) - 1)[ok & amp_ok].max() < AMP_RTOL
+        assert phase_diff(np.angle(bf.b[0, 0]), np.angle(bref))[ok & amp_ok].max() < PHASE_ATOL
+
+
+def test_binned_multi_frequency_and_multi_receiver(mods, feed_table):
+    """cfg 3 / cfg 4 batching: one launch for several receivers x frequencies equals the
+    one-at-a-time results."""
+    rt, geometry = mods["rt"], mods["geometry"]
+    t = _bundle(mods, 150, y_off=200)
+    freqs = geometry.freq_specs_from_table(np.linspace(77, 106, 7), feed_table)
+    rxs = [[0, 0, 0], [100, 0, 60], [-30, 0, -140]]
+    batch = rt.near_field_binned(t, rxs, grid_n=48, extent_cm=42.0, freqs=freqs, keep_sums=True)
+    assert batch.b.shape == (3, 7, 48, 48) and batch.count.shape == (3, 48, 48)
+    for i, rx in enumerate(rxs):
+        for f in (0, 3, 6):
+            t.k, t.th_fwhp_x, t.th_fwhp_y = freqs[f]
+            one = rt.near_field_binned(t, rx, grid_n=48, extent_cm=42.0, keep_sums=True)
+            assert np.array_equal(one.count[0], batch.count[i])
+            s = np.abs(one.re[0, 0]).max()
+            assert np.abs(one.re[0, 0] - batch.re[i, f]).max() < 1e-5 * s
+            assert np.abs(one.im[0, 0] - batch.im[i, f]).max() < 1e-5 * s
+    # more than SOSAT_MAX_FREQS frequencies are chunked by the wrapper
+    many = geometry.freq_specs_from_table(np.linspace(77, 106, 70), feed_table)
+    big = rt.near_field_binned(t, [0, 0, 0], grid_n=16, freqs=many)
+    assert big.b.shape == (1, 70, 16, 16)
+
+
+def test_binned_row_blocks_add_up(mods):
+    """Linearity over ray shards (the multi-GPU decomposition): binning row blocks separately
+    into the same planes equals one pass; counts exactly, sums to float32 rounding."""
+    rt, torch = mods["rt"], mods["torch"]
+    t = _bundle(mods, 500)
+    spec = [(t.k, t.th_fwhp_x, t.th_fwhp_y)]
+    re, im, cnt, st = rt.trace_bin_device(t, [[0, 0, 0]], spec, 128, 420.0)
+    planes, stats = None, None
+    for r0, r1 in [(0, 16), (16, 240), (240, 241), (241, 500)]:
+        a, b, c, stats = rt.trace_bin_device(t, [[0, 0, 0]], spec, 128, 420.0, row_begin=r0,
+                                             row_end=r1, planes=planes, stats=stats)
+        planes = (a, b, c)
+    assert torch.equal(planes[2], cnt)
+    assert (planes[0] - re).abs().max().item() < 1e-4 * re.abs().max().item()
+    assert torch.equal(stats[:, [0, 7]], st[:, [0, 7]])
+    assert stats[0, 1].item() == pytest.approx(st[0, 1].item(), rel=1e-12)
+
+
+def test_full_size_bundle_properties(mods):
+    """cfg 5 shape at reduced ray count (2.7e8 rays, 2048^2 grid): size-independent properties
+    -- every valid in-grid ray is counted once, boresight counts are mirror symmetric, the
+    statistics pass agrees with the binning pass, |sum| <= count."""
+    rt, torch = mods["rt"], mods["torch"]
+    t = _bundle(mods, 16384)
+    spec = [(t.k, t.th_fwhp_x, t.th_fwhp_y)]
+    re, im, cnt, st = rt.trace_bin_device(t, [[0, 0, 0]], spec, 2048, 420.0)
+    st = st.cpu().numpy()[0]
+    assert cnt.sum(dtype=torch.float64).item() == st[7] <= st[0]
+    assert st[0] / 16384 ** 2 == pytest.approx(0.690, abs=0.01)   # 2424/3600 .. 15312/22500 valid
+    assert st[6] == 0                                             # no bracket failures
+    assert st[5] < 1e-3 * st[0]                                   # slow path is rare
+    amp = torch.hypot(re[0, 0], im[0, 0])
+    assert bool((amp <= cnt[0] * (1 + 1e-5) + 1e-3).all())
+    c = cnt[0].double()
+    # x -> -x mirror: cell ix <-> N-1-ix up to rays sitting on cell edges
+    asym = (c - c.flip(1)).abs().sum().item() / c.sum().item()
+    assert asym < 2e-3
+    st2 = rt.trace_stats(t, [0, 0, 0])[0]
+    assert st2[0] == st[0] and st2[1] == pytest.approx(st[1], rel=1e-12)
+    assert abs(st[2]) < 1e-6 * st[0] and abs(st[4]) < 1e-6 * st[0]  # mean exit dir on axis
+
+
+def test_trace_bin_argument_errors(mods):
+    lib = mods["lib"].require_gpu()
+    rt, geometry, torch = mods["rt"], mods["geometry"], mods["torch"]
+    t = _bundle(mods, 32)
+    rt.rx_to_lyot([0, 0, 0], t)  # geometry uploaded
+    d_rx = torch.zeros(3, dtype=torch.float64, device="cuda")
+    fr = geometry.make_freqs([(t.k, 0.5, 0.5)])
+    z = ctypes.c_void_p(0)
+    args = lambda n_rx, n_f, b, e, gn: (ctypes.c_void_p(d_rx.data_ptr()), n_rx, fr, n_f, 32, b, e,  # noqa: E731
+                                        gn, 420.0, 0.0, z, z, z, z, z)
+    assert lib.sosat_trace_bin(*args(0, 1, 0, 32, 8)) == -1
+    assert lib.sosat_trace_bin(*args(1, 0, 0, 32, 8)) == -1
+    assert lib.sosat_trace_bin(*args(1, 65, 0, 32, 8)) == -1
+    assert lib.sosat_trace_bin(*args(1, 1, 0, 33, 8)) == -1
+    assert lib.sosat_trace_bin(*args(1, 1, 5, 5, 8)) == 0   # empty row range is a no-op
+    re = torch.zeros(64, dtype=torch.float32, device="cuda")
+    p = ctypes.c_void_p(re.data_ptr())
+    assert lib.sosat_trace_bin(ctypes.c_void_p(d_rx.data_ptr()), 1, fr, 1, 32, 0, 32, 8, 420.0,
+                               0.0, p, z, z, z, z) == -1   # planes must be all set or all NULL

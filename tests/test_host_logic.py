@@ -1,0 +1,151 @@
+"""CPU: host-side helpers of the drop-in layer against goldens produced by the reference, and
+the multi-GPU sharding / reduce logic on gloo with world_size 2."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+import torch
+import torch.distributed as dist
+import torch.multiprocessing as mp
+from conftest import golden
+
+from sosat_optics_b200 import dist as sdist
+from sosat_optics_b200 import geometry, opt_analyze, ray_trace
+
+
+def test_zero_pad_and_coords_match_reference():
+    g = golden("a2b_small.npz")
+    xo, yo, ao = opt_analyze.zero_pad(g["zp_x"], g["zp_y"], g["zp_amp"], int(g["zp_pts"]))
+    assert np.array_equal(xo, g["zp_xo"]) and np.array_equal(yo, g["zp_yo"])
+    assert np.array_equal(ao, g["zp_ao"])
+    xa, ya = opt_analyze.coords_spat_to_ang(xo / 1e2, yo / 1e2, 90.0)
+    assert np.array_equal(xa, g["zp_xang"]) and np.array_equal(ya, g["zp_yang"])
+    # label spacing is the true FFT-bin spacing stretched by N/(N-1)
+    n = xa.shape[0]
+    dx = abs(xo[0, 0] - xo[0, 1]) / 1e2
+    true = opt_analyze.far_field_angles(n, dx, opt_analyze.ghz_to_m(90.0))
+    assert np.allclose(np.diff(xa[0]), np.diff(true) * n / (n - 1), rtol=1e-9)
+    assert true[n // 2] == 0.0
+
+
+def test_unit_helpers():
+    assert opt_analyze.ghz_to_m(150) == 0.002 and opt_analyze.m_to_ghz(0.002) == 150
+    assert int(opt_analyze.m_to_ghz(0.0023)) == 130  # the sat_farfield notebook's table row
+    assert opt_analyze.rad_to_arcmin(np.pi / 180) == pytest.approx(60.0)
+
+
+def test_fwhm_helpers_on_reference_arrays():
+    g = golden("trace_cfg1_n60_106ghz.npz")
+    sb = ray_trace.SimOutput(g["sb_x_sim"], g["sb_y_sim"], g["sb_a_sim"], g["sb_p_sim"],
+                             g["sb_tan_og"])
+    assert np.allclose(ray_trace.get_fwhm(sb), g["fwhm"], atol=1e-12)
+    assert np.allclose(ray_trace.get_beam_cent(sb), g["beam_cent"], atol=1e-12)
+    assert np.allclose(ray_trace.get_angle_out(sb), g["angle_out"], atol=1e-12)
+    f = golden("farfield_cfg2_240.npz")
+    xa, ya = np.meshgrid(f["x_ang_row"], f["y_ang_col"])
+    assert ray_trace.ff_fwhm_est(f["beam_fft"], xa, ya) == pytest.approx(float(f["fwhm"]), abs=1e-12)
+
+
+def test_freq_specs_from_table(feed_table):
+    specs = geometry.freq_specs_from_table([90, 106.7, 130], feed_table)
+    k, fx, fy = specs[1]
+    assert k == 2 * np.pi / geometry.ghz_to_m(106.7)
+    row = feed_table[feed_table[:, 0] == 106][0]  # int() truncation, SURVEY appendix B.2
+    assert fx == np.deg2rad(row[1]) and fy == np.deg2rad(row[2])
+    s2 = geometry.freq_specs_from_table([90], feed_table, fwhm_scale=np.sqrt(2))
+    assert s2[0][1] == specs[0][1] * np.sqrt(2)
+    with pytest.raises(KeyError):
+        geometry.freq_specs_from_table([60], feed_table)
+    with pytest.raises(ValueError):
+        geometry.make_freqs([])
+    with pytest.raises(ValueError):
+        geometry.make_freqs([(1, 1, 1)] * 65)
+
+
+@pytest.mark.parametrize("n_scan,world", [(60, 1), (60, 2), (150, 8), (31623, 8), (7, 4), (16, 3)])
+def test_partition_rows_covers_exactly(n_scan, world):
+    blocks = [sdist.partition_rows(n_scan, world, r) for r in range(world)]
+    assert blocks[0][0] == 0 and blocks[-1][1] == n_scan
+    for (a0, a1), (b0, b1) in zip(blocks, blocks[1:]):
+        assert a1 == b0 and a0 <= a1
+    sizes = [b - a for a, b in blocks]
+    assert max(sizes) - min(sizes) <= 2 * sdist.ROW_ALIGN
+    assert all(a % sdist.ROW_ALIGN == 0 for a, _ in blocks if a < n_scan)
+
+
+def test_partition_items_round_robin():
+    parts = [sdist.partition_items(11, 4, r) for r in range(4)]
+    assert sorted(sum(parts, [])) == list(range(11))
+    assert parts[0] == [0, 4, 8] and parts[3] == [3, 7]
+    with pytest.raises(ValueError):
+        sdist.partition_rows(10, 2, 2)
+
+
+# ---- world_size-2 gloo run of the ray-sharded near field (tracer replaced by the oracle) ----
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _oracle_trace_fn(tele_geo, rx_arr, specs, grid_n, extent_mm, *, opl_ref=0.0, row_begin=0,
+                     row_end=None, **_):
+    """CPU stand-in with the signature of ray_trace.trace_bin_device (test infrastructure)."""
+    from oracle import oracle
+    n_scan = int(tele_geo.n_scan)
+    re = torch.zeros((len(rx_arr), len(specs), grid_n, grid_n), dtype=torch.float32)
+    im, cnt = torch.zeros_like(re), torch.zeros((len(rx_arr), grid_n, grid_n), dtype=torch.float32)
+    stats = torch.zeros((len(rx_arr), 8), dtype=torch.float64)
+    for i, rx in enumerate(rx_arr):
+        out = oracle.rx_to_lyot(rx, tele_geo, ray_begin=row_begin * n_scan,
+                                ray_end=row_end * n_scan, n_threads=1)
+        for f, (k, _, _) in enumerate(specs):
+            r, m, c, sums = oracle.bin_near_field(out, float(k), grid_n, extent_mm, opl_ref)
+            re[i, f], im[i, f], cnt[i] = (torch.from_numpy(r).float(), torch.from_numpy(m).float(),
+                                          torch.from_numpy(c).float())
+        stats[i, 0], stats[i, 1], stats[i, 7] = sums["n_valid"], sums["sum_opl"], sums["n_binned"]
+    return re, im, cnt, stats
+
+
+def _field_fn(re, im, cnt, stats, specs, opl_ref=0.0):
+    return torch.complex(re, im), stats.numpy()
+
+
+def _worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from oracle import oracle
+        t = oracle.default_tele_geo(n_scan=40, y_source=oracle.Y_LYOT + 300)
+        b, cnt, stats = sdist.near_field_binned_distributed(
+            t, [[0, 0, 0], [60, 0, -90]], 16, 42.0, trace_fn=_oracle_trace_fn, field_fn=_field_fn)
+        sweep = sdist.sweep_distributed(list(range(5)), lambda p: (p, rank))
+        q.put((rank, b.numpy(), cnt.numpy(), stats, sweep))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_ray_sharded_near_field_world2_gloo():
+    from oracle import oracle
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=180) for _ in procs], key=lambda r: r[0])
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    # single-process answer
+    t = oracle.default_tele_geo(n_scan=40, y_source=oracle.Y_LYOT + 300)
+    re, im, cnt, stats = _oracle_trace_fn(t, np.array([[0., 0, 0], [60, 0, -90]]),
+                                          [(t.k, t.th_fwhp_x, t.th_fwhp_y)], 16, 420.0,
+                                          row_begin=0, row_end=40)
+    for rank, b, c, s, sweep in res:
+        assert np.array_equal(c, cnt.numpy())
+        assert np.abs(b - torch.complex(re, im).numpy()).max() < 1e-4
+        assert np.allclose(s[:, [0, 7]], stats.numpy()[:, [0, 7]])
+        assert np.allclose(s[:, 1], stats.numpy()[:, 1], rtol=1e-12)
+        assert sweep == [(0, 0), (1, 1), (2, 0), (3, 1), (4, 0)]
