@@ -344,9 +344,9 @@ def run_ours(args):
     if world == 1 and not args.no_cpu_baseline:
         from oracle import oracle
         oracle.build()
-        dt, rays, cores = cpu_reference_sample(300)
-        n_sample = int(min(N_SCAN, max(300, np.sqrt(rays / dt * 12.0))))
-        dt, rays, cores = cpu_reference_sample(n_sample)
+        dt, rays, cores = cpu_reference_sample(1000)   # sizing probe (fixed FFT cost included)
+        n_sample = int(min(N_SCAN, max(1000, np.sqrt(rays / dt * 40.0))))
+        dt, rays, cores = cpu_reference_sample(n_sample)  # ~10-30 s of CPU work
         cpu = {"value": rays / dt, "unit": "rays/s", "cores": cores, "kind": "port",
                "sample": f"n_scan={n_sample} ({rays} rays) -> {GRID_N}^2 bins -> {GRID_N}^2 numpy "
                          f"FFT, {dt:.1f} s; oracle/ C port of rx_to_lyot (brentq restated), OpenMP",

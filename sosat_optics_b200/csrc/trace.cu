@@ -482,10 +482,13 @@ extern "C" int sosat_trace_rays(const double *h_rx, const sosat_freq_t *h_freq, 
 extern "C" int sosat_rx_to_lyot_host(const sosat_geom_t *h_geom, const double *h_rx,
                                      const sosat_freq_t *h_freq, int n_scan, int64_t ray_begin,
                                      int64_t ray_end, double *h_out, double *h_stats) {
-    SOSAT_REQUIRE(h_geom && h_out, "sosat_rx_to_lyot_host: null pointer");
+    SOSAT_REQUIRE(h_geom && h_rx && h_freq && h_out, "sosat_rx_to_lyot_host: null pointer");
+    SOSAT_REQUIRE(n_scan >= 1, "n_scan must be >= 1 (got %d)", n_scan);
     if (int rc = sosat_set_geometry(h_geom, nullptr)) return rc;
     const int64_t n = ray_end - ray_begin;
-    SOSAT_REQUIRE(n >= 0, "empty or negative ray range");
+    SOSAT_REQUIRE(n >= 0 && ray_begin >= 0 && ray_end <= (int64_t)n_scan * n_scan,
+                  "ray range [%lld, %lld) outside [0, %lld]", (long long)ray_begin,
+                  (long long)ray_end, (long long)n_scan * n_scan);
     if (n == 0) return SOSAT_OK;
     double *d_out = nullptr, *d_stats = nullptr;
     SOSAT_CUDA_OK(cudaMalloc(&d_out, sizeof(double) * SOSAT_OUT_ROWS * n));
