@@ -28,7 +28,7 @@ def stage_trace():
     g = golden("trace_cfg1_n60_106ghz.npz")
     t = tele_geo_from_golden(g)
     ref = g["out"]
-    for var in range(6):
+    for var in range(8):
         os.environ["SOSAT_TRACE_VARIANT"] = str(var)
         out = ray_trace.rx_to_lyot([0, 0, 0], t, False, "b")
         vr, vo = ref[4] != 0, out[4] != 0
@@ -67,34 +67,35 @@ def stage_trace():
         np.abs(bf.re[0, 0] - re).max(), np.abs(bf.im[0, 0] - im).max(), np.abs(re).max()),
         "stats", bf.stats[0], "oracle", sums)
 
-    # timing
-    for var in (0, 5, 2, 3, 4, 1):
-        os.environ["SOSAT_TRACE_VARIANT"] = str(var)
-        t.n_scan = 8192
-        spec = [(t.k, t.th_fwhp_x, t.th_fwhp_y)]
-        planes = None
-        for rep in range(3):
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            re_, im_, cnt_, st_ = ray_trace.trace_bin_device(t, [[0, 0, 0]], spec, 2048, 420.0, planes=planes)
-            e1.record()
-            torch.cuda.synchronize()
-            planes = (re_, im_, cnt_)
-            ms = e0.elapsed_time(e1)
-        n = t.n_scan ** 2
-        print("variant", var, "bin-mode n_scan=8192: %.2f ms -> %.3e rays/s" % (ms, n / ms * 1e3),
-              "stats", st_.cpu().numpy()[0][[0, 5, 6, 7]])
-        for rep in range(2):
-            torch.cuda.synchronize()
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record()
-            _, _, _, st_ = ray_trace.trace_bin_device(t, [[0, 0, 0]], spec, 0, 0.0, bins=False)
-            e1.record()
-            torch.cuda.synchronize()
-            ms = e0.elapsed_time(e1)
-        print("      stats-only: %.2f ms -> %.3e rays/s" % (ms, n / ms * 1e3))
+    # slow-path fraction for off-axis feeds, default schedule
+    t.n_scan = 2000
+    for rx in ([0, 0, 0], [0, 0, 150], [150, 0, 0], [-120, 0, 80], [106, 0, 106], [0, 0, 170]):
+        st = ray_trace.trace_stats(t, rx)[0]
+        print("rx", rx, "n_valid %d n_slow %d (%.4f%%) bracket_fail %d" % (st[0], st[5], 100 * st[5] / max(st[0], 1), st[6]))
+    # timing: Newton schedule x resident CTAs/SM
+    t.n_scan = 8192
+    spec = [(t.k, t.th_fwhp_x, t.th_fwhp_y)]
+    n = t.n_scan ** 2
+    for minb in (2, 3, 4):
+        os.environ["SOSAT_TRACE_MINB"] = str(minb)
+        for var in (0, 5, 2, 6, 7, 4):
+            os.environ["SOSAT_TRACE_VARIANT"] = str(var)
+            planes = None
+            best = 1e9
+            for rep in range(4):
+                torch.cuda.synchronize()
+                e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+                e0.record()
+                re_, im_, cnt_, st_ = ray_trace.trace_bin_device(t, [[0, 0, 0]], spec, 2048, 420.0, planes=planes)
+                e1.record()
+                torch.cuda.synchronize()
+                planes = (re_, im_, cnt_)
+                if rep:
+                    best = min(best, e0.elapsed_time(e1))
+            print("minb", minb, "variant", var, "bin-mode n_scan=8192: %.2f ms -> %.3e rays/s" % (best, n / best * 1e3),
+                  "stats", st_.cpu().numpy()[0][[0, 5, 6, 7]], flush=True)
     os.environ["SOSAT_TRACE_VARIANT"] = "0"
+    os.environ.pop("SOSAT_TRACE_MINB", None)
 
 
 def stage_dft():

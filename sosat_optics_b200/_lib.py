@@ -17,7 +17,8 @@ NUM_STATS = 8
 (STAT_N_VALID, STAT_SUM_OPL, STAT_SUM_DX, STAT_SUM_DY, STAT_SUM_DZ, STAT_N_SLOW,
  STAT_N_BRACKET_FAIL, STAT_N_BINNED) = range(8)
 
-LIB_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "libsosat_b200.so")
+LIB_PATH = os.environ.get("SOSAT_LIB") or os.path.join(
+    os.path.dirname(os.path.abspath(__file__)), "libsosat_b200.so")
 
 
 class Surface(Structure):

@@ -134,8 +134,8 @@ struct BinParams {
     long long n_tiles;
 };
 
-template <int N32, int N64>
-__global__ void __launch_bounds__(256)
+template <int N32, int N64, int MINB>
+__global__ void __launch_bounds__(256, MINB)
 trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict__ re,
                  float *__restrict__ im, float *__restrict__ cnt, double *__restrict__ stats) {
     __shared__ double s_sin[2][kTile], s_cos[2][kTile], s_ang[2][kTile];
@@ -146,20 +146,39 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
     const int lth = (lane & 7) + 8 * (warp & 1);
     const int lph = (lane >> 3) + 4 * (warp >> 1);
 
-    double acc[SOSAT_NUM_STATS] = {0, 0, 0, 0, 0, 0, 0, 0};
+    // Per-thread running statistics: the four fp64 sums live in shared memory (one slot per
+    // thread, no conflicts) and the four counters in 32-bit registers, which keeps 12 registers
+    // out of the tracer's live range.
+    __shared__ double s_sum[4][256];
+    unsigned n_valid = 0, n_binned = 0, n_slow_acc = 0, n_fail = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) s_sum[q][tid] = 0.0;
     int acc_rx = -1;
     const long long tiles_per_rx = (long long)p.tiles_x * p.tiles_y;
     const long long plane = (long long)p.grid_n * p.grid_n;
+
+    auto flush_stats = [&](int irx_done) {
+        double acc[SOSAT_NUM_STATS];
+        acc[SOSAT_STAT_N_VALID] = (double)n_valid;
+        acc[SOSAT_STAT_SUM_OPL] = s_sum[0][tid];
+        acc[SOSAT_STAT_SUM_DX] = s_sum[1][tid];
+        acc[SOSAT_STAT_SUM_DY] = s_sum[2][tid];
+        acc[SOSAT_STAT_SUM_DZ] = s_sum[3][tid];
+        acc[SOSAT_STAT_N_SLOW] = (double)n_slow_acc;
+        acc[SOSAT_STAT_N_BRACKET_FAIL] = (double)n_fail;
+        acc[SOSAT_STAT_N_BINNED] = (double)n_binned;
+        if (stats) block_accumulate<SOSAT_NUM_STATS>(acc, stats + (long long)irx_done * SOSAT_NUM_STATS);
+        n_valid = n_binned = n_slow_acc = n_fail = 0;
+#pragma unroll
+        for (int q = 0; q < 4; ++q) s_sum[q][tid] = 0.0;
+    };
 
     for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
         const int irx = (int)(tile / tiles_per_rx);
         const long long trem = tile - (long long)irx * tiles_per_rx;
         const int ty = (int)(trem / p.tiles_x), tx = (int)(trem - (long long)ty * p.tiles_x);
         if (irx != acc_rx) {
-            if (acc_rx >= 0 && stats)
-                block_accumulate<SOSAT_NUM_STATS>(acc, stats + (long long)acc_rx * SOSAT_NUM_STATS);
-#pragma unroll
-            for (int q = 0; q < SOSAT_NUM_STATS; ++q) acc[q] = 0.0;
+            if (acc_rx >= 0) flush_stats(acc_rx);
             acc_rx = irx;
         }
         __syncthreads();  // previous tile done with the tables
@@ -204,15 +223,15 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
             const int ix = __double2int_rd((r.ax + p.half_extent) * p.inv_cell);
             const int iz = __double2int_rd((r.az + p.half_extent) * p.inv_cell);
             if (ix >= 0 && ix < p.grid_n && iz >= 0 && iz < p.grid_n) bin = iz * p.grid_n + ix;
-            acc[SOSAT_STAT_N_VALID] += 1.0;
-            acc[SOSAT_STAT_SUM_OPL] += r.opl;
-            acc[SOSAT_STAT_SUM_DX] += r.dx;
-            acc[SOSAT_STAT_SUM_DY] += r.dy;
-            acc[SOSAT_STAT_SUM_DZ] += r.dz;
-            if (bin >= 0) acc[SOSAT_STAT_N_BINNED] += 1.0;
+            ++n_valid;
+            s_sum[0][tid] += r.opl;
+            s_sum[1][tid] += r.dx;
+            s_sum[2][tid] += r.dy;
+            s_sum[3][tid] += r.dz;
+            if (bin >= 0) ++n_binned;
         }
-        acc[SOSAT_STAT_N_SLOW] += (double)n_slow;
-        if (live && (r.flags & RAY_BRACKET_FAIL)) acc[SOSAT_STAT_N_BRACKET_FAIL] += 1.0;
+        n_slow_acc += n_slow;
+        if (live && (r.flags & RAY_BRACKET_FAIL)) ++n_fail;
         if (re == nullptr) continue;
 
         // ---- warp-level aggregation: lanes that share a bin are summed by shuffle, one
@@ -276,8 +295,7 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
             }
         }
     }
-    if (acc_rx >= 0 && stats)
-        block_accumulate<SOSAT_NUM_STATS>(acc, stats + (long long)acc_rx * SOSAT_NUM_STATS);
+    if (acc_rx >= 0) flush_stats(acc_rx);
 }
 
 // ---- getNearField post-processing (ray_trace.py:1599-1614) ---------------------------------
@@ -372,7 +390,7 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
 // another compiled schedule for experiments.
 static int trace_variant() {
     const char *e = getenv("SOSAT_TRACE_VARIANT");
-    return e ? atoi(e) : 0;
+    return e ? atoi(e) : 6;
 }
 
 static void fill_linspace(double cone, int n_scan, double &start, double &stop, double &step) {
@@ -473,6 +491,8 @@ extern "C" int sosat_trace_rays(const double *h_rx, const sosat_freq_t *h_freq, 
         case 3: launch_rows<3, 3>(p, d_out, d_stats, st); break;
         case 4: launch_rows<2, 3>(p, d_out, d_stats, st); break;
         case 5: launch_rows<0, 4>(p, d_out, d_stats, st); break;
+        case 6: launch_rows<2, 2>(p, d_out, d_stats, st); break;
+        case 7: launch_rows<4, 2>(p, d_out, d_stats, st); break;
         default: launch_rows<0, 5>(p, d_out, d_stats, st); break;
     }
     SOSAT_CUDA_OK(cudaGetLastError());
@@ -511,10 +531,31 @@ extern "C" int sosat_rx_to_lyot_host(const sosat_geom_t *h_geom, const double *h
     return rc;
 }
 
+// Launch the persistent binning kernel with grid = SMs x resident CTAs per SM.
+template <int N32, int N64, int MINB>
+static void launch_bin(const BinParams &p, const double *rx, float *re, float *im, float *cnt,
+                       double *stats, cudaStream_t st) {
+    int occ = 0;
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_bin_kernel<N32, N64, MINB>, 256, 0);
+    const long long want = (long long)num_sms() * (occ > 0 ? occ : 1);
+    const int blocks = (int)(p.n_tiles < want ? p.n_tiles : want);
+    trace_bin_kernel<N32, N64, MINB><<<blocks, 256, 0, st>>>(p, rx, re, im, cnt, stats);
+}
+
 template <int N32, int N64>
-static void launch_bin(const BinParams &p, int blocks, const double *rx, float *re, float *im,
-                       float *cnt, double *stats, cudaStream_t st) {
-    trace_bin_kernel<N32, N64><<<blocks, 256, 0, st>>>(p, rx, re, im, cnt, stats);
+static void launch_bin_minb(int minb, const BinParams &p, const double *rx, float *re, float *im,
+                            float *cnt, double *stats, cudaStream_t st) {
+    switch (minb) {
+        case 2: launch_bin<N32, N64, 2>(p, rx, re, im, cnt, stats, st); break;
+        case 4: launch_bin<N32, N64, 4>(p, rx, re, im, cnt, stats, st); break;
+        default: launch_bin<N32, N64, 3>(p, rx, re, im, cnt, stats, st); break;
+    }
+}
+
+// resident CTAs per SM the binning kernel is compiled for (register budget 128 / 80 / 64)
+static int trace_minb() {
+    const char *e = getenv("SOSAT_TRACE_MINB");
+    return e ? atoi(e) : 4;
 }
 
 extern "C" int sosat_trace_bin(const double *d_rx, int n_rx, const sosat_freq_t *h_freq,
@@ -563,25 +604,16 @@ extern "C" int sosat_trace_bin(const double *d_rx, int n_rx, const sosat_freq_t 
     p.tiles_x = (n_scan + kTile - 1) / kTile;
     p.tiles_y = (p.n_rows + kTile - 1) / kTile;
     p.n_tiles = (long long)p.tiles_x * p.tiles_y * n_rx;
-    int occ = 0;
-    const int sms = num_sms();
-    long long want;
+    const int minb = trace_minb();
     switch (trace_variant()) {
-#define SOSAT_BIN_CASE(ID, A, B)                                                              \
-    case ID:                                                                                  \
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_bin_kernel<A, B>, 256, 0);  \
-        want = (long long)sms * (occ > 0 ? occ : 1);                                          \
-        launch_bin<A, B>(p, (int)(p.n_tiles < want ? p.n_tiles : want), d_rx, d_re, d_im,     \
-                         d_cnt, d_stats, st);                                                 \
-        break;
-        SOSAT_BIN_CASE(1, 0, 6)
-        SOSAT_BIN_CASE(2, 3, 2)
-        SOSAT_BIN_CASE(3, 3, 3)
-        SOSAT_BIN_CASE(4, 2, 3)
-        SOSAT_BIN_CASE(5, 0, 4)
-        default:
-            SOSAT_BIN_CASE(0, 0, 5)
-#undef SOSAT_BIN_CASE
+        case 1: launch_bin_minb<0, 6>(minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
+        case 2: launch_bin_minb<3, 2>(minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
+        case 3: launch_bin_minb<3, 3>(minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
+        case 4: launch_bin_minb<2, 3>(minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
+        case 5: launch_bin_minb<0, 4>(minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
+        case 6: launch_bin_minb<2, 2>(minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
+        case 7: launch_bin_minb<4, 2>(minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
+        default: launch_bin_minb<0, 5>(minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
     }
     SOSAT_CUDA_OK(cudaGetLastError());
     // bf lives on this stack frame: the async symbol copy from pageable memory is staged

@@ -47,10 +47,14 @@ struct GeomC {
     double y_lyot, y_source, clip_l3_sq, clip_stop_sq, cone;
 };
 
-// Newton acceptance: a surface whose last Newton step exceeds this [mm] (or is NaN) marks
-// the ray for the bracketed slow path.  The normal is taken at the iterate before the last
-// step, so this also bounds the normal error (curvature ~1e-2/mm  ->  <= 1e-8).
-#define SOSAT_NEWTON_TOL 1.0e-6
+// Newton acceptance.  The surface normal is taken at the iterate before the last step, so the
+// last step bounds the normal error (curvature ~1e-2/mm, up to ~1e2/mm for wild rays near the
+// lens-1b conic edge).  After the fixed schedule a ray whose last step exceeds REFINE gets up
+// to SOSAT_NEWTON_EXTRA more fp64 steps (rare, warp-divergent); one still above TOL (or NaN)
+// is marked for the bracketed slow path.
+#define SOSAT_NEWTON_REFINE 1.0e-9
+#define SOSAT_NEWTON_TOL 1.0e-8
+#define SOSAT_NEWTON_EXTRA 3
 // lens 1b is the only surface with a bounded conic domain (k > -1): hits
 // with w = 1 - K'u below this are within ~8 mm of the domain edge r = 300.4 mm, where the
 // reference's brentq converges onto the sag discontinuity instead of a root.
@@ -82,15 +86,19 @@ __device__ __forceinline__ double rsqrt_seed(double x) {
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
     return r;
 }
-// full precision (~1 ulp): seed is good to ~2^-22, two NR steps square that twice
-__device__ __forceinline__ double rcp_fast(double x) {
+// Measured on B200 (parity runs in DESIGN.md section 3): the rsqrt seed is good to ~1e-6 and
+// the rcp seed only to ~3e-5.  rsqrt_fast = seed + one Newton-Raphson step (~3e-12 relative:
+// <= 2e-10 mm on a 50 mm sag, far inside the 1e-3 rad phase tolerance) at half the DFMA count
+// of a fully rounded result; rcp_full = seed + two steps (~1e-18); the raw rcp seed is used
+// only for the Newton step quotient, where a 3e-5 relative error merely makes the last
+// iterations converge linearly with ratio 3e-5 instead of quadratically.
+__device__ __forceinline__ double rcp_full(double x) {
     double r = rcp_seed(x);
     double e = fma(-x, r, 1.0);
     r = fma(r, e, r);
     e = fma(-x, r, 1.0);
     return fma(r, e, r);
 }
-// ~2^-44: enough for a Newton step quotient
 __device__ __forceinline__ double rcp_half(double x) {
     double r = rcp_seed(x);
     double e = fma(-x, r, 1.0);
@@ -100,11 +108,23 @@ __device__ __forceinline__ double rsqrt_fast(double x) {
     double y = rsqrt_seed(x);
     double a = x * y;
     double e = fma(-a, y, 1.0);
-    y = fma(0.5 * y, e, y);
-    a = x * y;
-    e = fma(-a, y, 1.0);
     return fma(0.5 * y, e, y);
 }
+__device__ __forceinline__ double rsqrt_full(double x) {
+    double y = rsqrt_fast(x);
+    double a = x * y;
+    double e = fma(-a, y, 1.0);
+    return fma(0.5 * y, e, y);
+}
+// Where each precision is used (measured against the oracle on 2e6 rays):
+// the sag evaluation tolerates the one-step rsqrt (median |dOPL| 2e-12 mm), the normalisation
+// and the Snell radicand do not (one-step there: median 8e-9 mm, 3e-4 mm on wild marginal rays).
+#ifndef SOSAT_RSQRT_EVAL
+#define SOSAT_RSQRT_EVAL rsqrt_fast
+#endif
+#ifndef SOSAT_RSQRT_SNELL
+#define SOSAT_RSQRT_SNELL rsqrt_full
+#endif
 __device__ __forceinline__ float rcp_f32(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -127,9 +147,9 @@ __device__ __forceinline__ void surf_eval(const SurfC &S, double Px, double Pz, 
     Z = fma(dz, t, Pz);
     const double u = fma(X, X, Z * Z);
     w = fma(-S.Kp, u, 1.0);
-    const double rs = rsqrt_fast(w);
+    const double rs = SOSAT_RSQRT_EVAL(w);
     const double s = w * rs;
-    const double inv = rcp_fast(1.0 + s);
+    const double inv = rcp_full(1.0 + s);
     const double poly = fma(fma(S.a3p, u, S.a2p), u, S.a1p);
     const double q = S.cp * inv;
     f = fma(-dy, t, y0Py) - u * (q + poly);
@@ -163,14 +183,14 @@ __device__ __forceinline__ void refract(const SurfC &S, double X, double Z, doub
                                         double &dx, double &dy, double &dz, double &nx,
                                         double &ny, double &nz) {
     const double gx = G * X, gz = G * Z;
-    const double rn = rsqrt_fast(fma(gx, gx, fma(gz, gz, 1.0)));
+    const double rn = SOSAT_RSQRT_SNELL(fma(gx, gx, fma(gz, gz, 1.0)));
     // local normal (-gx, -gy, 1)/|.| maps to tele (-gx, -1, -gz)/|.| (ray_trace.py:1162-1166)
     nx = -gx * rn;
     ny = -rn;
     nz = -gz * rn;
     const double ci = -fma(nx, dx, fma(ny, dy, nz * dz));
     const double rad2 = fma(S.mu2, fma(ci, ci, -1.0), 1.0);
-    const double rad = rad2 * rsqrt_fast(rad2);
+    const double rad = rad2 * SOSAT_RSQRT_SNELL(rad2);
     const double kf = fma(S.mu, ci, -rad);
     dx = fma(S.mu, dx, kf * nx);
     dy = fma(S.mu, dy, kf * ny);
@@ -228,7 +248,14 @@ __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, doub
         for (int it = 0; it < N64; ++it) {
             double f, fp;
             surf_eval(S, Px, Pz, dx, dy, dz, y0Py, t, f, fp, X, Z, G, w);
-            step = f * rcp_half(fp);
+            step = f * rcp_seed(fp);
+            t -= step;
+        }
+#pragma unroll 1
+        for (int extra = 0; extra < SOSAT_NEWTON_EXTRA && fabs(step) > SOSAT_NEWTON_REFINE; ++extra) {
+            double f, fp;
+            surf_eval(S, Px, Pz, dx, dy, dz, y0Py, t, f, fp, X, Z, G, w);
+            step = f * rcp_seed(fp);
             t -= step;
         }
         if (!(fabs(step) <= SOSAT_NEWTON_TOL)) flags |= RAY_FLAGGED;
