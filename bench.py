@@ -120,7 +120,9 @@ def cpu_reference_sample(n_scan_sample, threads=0):
     row = _feed_table()
     row = row[row[:, 0] == int(GHZ)][0]
     t.th_fwhp_x, t.th_fwhp_y = np.deg2rad(row[1]), np.deg2rad(row[2])
-    cores = oracle.lib().oracle_max_threads() if threads <= 0 else threads
+    if threads <= 0:  # all host threads, whatever OMP_NUM_THREADS says (torchrun sets it to 1)
+        threads = len(os.sched_getaffinity(0))
+    cores = threads
     t0 = time.perf_counter()
     out = oracle.rx_to_lyot([0, 0, 0], t, n_threads=threads)
     re, im, cnt, sums = oracle.bin_near_field(out, float(t.k), GRID_N, EXTENT_CM * 10, 0.0)
@@ -362,7 +364,7 @@ def run_ours(args):
                    "extent_cm": EXTENT_CM, "ghz": GHZ, "sharding": f"launch-row blocks x{world}, "
                    "one NCCL all-reduce of [re,im,count] planes (50 MB) + 8 fp64 sums",
                    "l2": "256 MiB flush write between timed steps; the kernel reads no input arrays",
-                   "newton_schedule": os.environ.get("SOSAT_TRACE_VARIANT", "0")},
+                   "newton_schedule": os.environ.get("SOSAT_TRACE_VARIANT", "default (2 fp32 + 2 fp64 steps, adaptive)")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},
