@@ -217,6 +217,14 @@ __device__ __forceinline__ void finish_ray(const GeomC &g, double Px, double Py,
               (r.opl == r.opl);
 }
 
+// The six-surface loop is kept rolled by default (constants fetched with LDC, ~6 KB of code);
+// -DSOSAT_UNROLL_SURFACES=1 unrolls it so the constants become immediate c[][] operands.
+#if defined(SOSAT_UNROLL_SURFACES) && SOSAT_UNROLL_SURFACES
+#define SOSAT_SURFACE_LOOP_PRAGMA _Pragma("unroll")
+#else
+#define SOSAT_SURFACE_LOOP_PRAGMA _Pragma("unroll 1")
+#endif
+
 // Fast path.  N32 Newton steps in fp32 from the vertex-plane guess, then N64 in fp64.
 template <int N32, int N64>
 __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, double Py,
@@ -225,7 +233,7 @@ __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, doub
     double opl = 0.0, r2a_sq = 0.0;
     double nx = 0.0, ny = 0.0, nz = 0.0;
     unsigned flags = 0;
-#pragma unroll 1
+    SOSAT_SURFACE_LOOP_PRAGMA
     for (int si = 0; si < SOSAT_NUM_SURFACES; ++si) {
         const SurfC &S = g.s[si];
         const double y0Py = S.y0 - Py;
