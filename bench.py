@@ -172,6 +172,57 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def other_configs(torch, ot_geo, opt_analyze, ray_trace, table):
+    """Device-timed one-liners for BASELINE.json configs[0..3] (parity for each is in tests/)."""
+    from sosat_optics_b200 import geometry
+    ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
+
+    def timed(fn, reps=5):
+        fn()
+        torch.cuda.synchronize()
+        best = 1e30
+        for _ in range(reps):
+            a, b = ev(), ev()
+            a.record()
+            fn()
+            b.record()
+            torch.cuda.synchronize()
+            best = min(best, a.elapsed_time(b))
+        return best
+
+    out = {}
+    # cfg 0: sat_nearfield notebook default through the drop-in call (host arrays in and out)
+    t = _tele_geo(ot_geo, opt_analyze, table, 60)
+    t0 = time.perf_counter()
+    for _ in range(5):
+        ray_trace.getNearField(t, [0, 0, 0])
+    wall = (time.perf_counter() - t0) / 5
+    out["cfg0_getNearField_n60"] = {"wall_ms": wall * 1e3, "rays_per_s": 3600 / wall,
+                                    "reference": "5 s (600 rays/s, notebook stderr)"}
+    # cfg 1: 1000^2 far field through a2b (host float64 arrays in, complex128 out)
+    amp = np.random.default_rng(1).uniform(size=(1000, 1000))
+    opt_analyze.a2b(amp, amp)
+    t0 = time.perf_counter()
+    opt_analyze.a2b(amp, amp)
+    out["cfg1_a2b_1000_host"] = {"wall_ms": (time.perf_counter() - t0) * 1e3,
+                                 "reference": "81 ms (BASELINE.md, numpy 1 core)"}
+    # cfg 2: 64-frequency sweep 77-106 GHz at n_scan=150, one fused launch
+    t = _tele_geo(ot_geo, opt_analyze, table, 150)
+    freqs = geometry.freq_specs_from_table(np.linspace(77, 106, 64), table)
+    ms = timed(lambda: ray_trace.trace_bin_device(t, [[0, 0, 0]], freqs, 256, 420.0))
+    out["cfg2_sweep_64freq_n150"] = {"ms": ms, "ray_freq_pairs_per_s": 22500 * 64 / (ms * 1e-3),
+                                     "reference": "64 x 32 s (re-traces every frequency)"}
+    # cfg 3: 8 x 8 focal-plane receiver sweep (|rx| <= 150 mm), n_scan = 1000, one launch
+    g = np.linspace(-150, 150, 8)
+    rxs = [[x, 0.0, z] for x in g for z in g if np.hypot(x, z) <= 150.0]
+    t = _tele_geo(ot_geo, opt_analyze, table, 1000)
+    spec = [(t.k, t.th_fwhp_x, t.th_fwhp_y)]
+    ms = timed(lambda: ray_trace.trace_bin_device(t, rxs, spec, 512, 420.0), reps=3)
+    out["cfg3_receiver_sweep_n1000"] = {"ms": ms, "receivers": len(rxs),
+                                        "rays_per_s": len(rxs) * 1e6 / (ms * 1e-3)}
+    return out
+
+
 # ------------------------------------------------------------------------------------------------
 def run_ours(args):
     import torch
@@ -341,6 +392,16 @@ def run_ours(args):
         "note": "16 N^3 algorithmic flop; the bf16x3 split executes 3x that on the tensor pipe",
     }
 
+    # ---- the other BASELINE.json configs, one line each (N = 1 only; not the headline) ----
+    configs = None
+    if world == 1:
+        configs = other_configs(torch, ot_geo, opt_analyze, ray_trace, table)
+        for n in (1024, 2048):   # reference far field on the host: opt_analyze.a2b = shifted fft2
+            fld = (np.random.default_rng(2).standard_normal((n, n)) + 0j)
+            t0 = time.perf_counter()
+            np.fft.fftshift(np.fft.fft2(np.fft.fftshift(fld)))
+            farfield[f"n{n}"]["cpu_numpy_fft2_ms"] = (time.perf_counter() - t0) * 1e3
+
     # ---- CPU baseline on a bounded sample (rank 0, N = 1 only) ----
     cpu = None
     if world == 1 and not args.no_cpu_baseline:
@@ -372,6 +433,7 @@ def run_ours(args):
         "roofline": roofline,
         "farfield": farfield,
         "cpu_baseline": cpu,
+        "configs": configs,
         "wall_s_timed_region": wall_s,
         "far_field_ms_in_step": statistics.median(ff_ms),
         "peaks": peaks_kind,

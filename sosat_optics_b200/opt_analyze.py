@@ -120,10 +120,11 @@ def a2b(apert, phi):
     return torch.view_as_complex(beam).cpu().numpy(), phase.cpu().numpy()
 
 
-def far_field(b, *, device: bool = False):
+def far_field(b, dx_cm=None, lam_m=None, *, device: bool = False):
     """Centred 2-D DFT of a complex near field ``b`` [N, N] (numpy complex or CUDA complex64
-    tensor): ``B = fftshift(fft2(fftshift(b)))``.  With ``device=True`` the input must be a
-    CUDA tensor and a CUDA complex64 tensor is returned (no host copies)."""
+    tensor): ``B = fftshift(fft2(fftshift(b)))``.  With ``device=True`` a CUDA complex64 tensor
+    is returned (no host copies).  If the cell size ``dx_cm`` and the wavelength ``lam_m`` are
+    given, returns ``(B, theta)`` with ``theta`` the true FFT-bin angles [rad] of both axes."""
     lib = _lib.require_gpu()
     torch = _torch()
     if isinstance(b, np.ndarray):
@@ -138,7 +139,10 @@ def far_field(b, *, device: bool = False):
     _lib.check(lib.sosat_dft2_gemm(ctypes.c_void_p(d_b.data_ptr()), n,
                                    ctypes.c_void_p(out.data_ptr()),
                                    ctypes.c_void_p(ws.data_ptr()), ws.numel(), _stream(torch)))
-    return out if device else out.cpu().numpy()
+    res = out if device else out.cpu().numpy()
+    if dx_cm is not None and lam_m is not None:
+        return res, far_field_angles(n, float(dx_cm) / 100.0, float(lam_m))
+    return res
 
 
 def far_field_angles(n: int, dx_m: float, lam_m: float):

@@ -330,3 +330,45 @@ def test_trace_bin_argument_errors(mods):
     p = ctypes.c_void_p(re.data_ptr())
     assert lib.sosat_trace_bin(ctypes.c_void_p(d_rx.data_ptr()), 1, fr, 1, 32, 0, 32, 8, 420.0,
                                0.0, p, z, z, z, z) == -1   # planes must be all set or all NULL
+
+
+def test_cfg3_64_frequency_sweep_in_one_launch(mods, feed_table):
+    """BASELINE.json configs[2]: 64 frequencies 77-106 GHz (table row int(f)) share one trace;
+    every frequency plane equals the oracle's binning of the same rays with that frequency's
+    feed taper and phase scale."""
+    rt, geometry, oracle = mods["rt"], mods["geometry"], mods["oracle"]
+    t = _bundle(mods, 150, y_off=200)
+    ghz = np.linspace(77, 106, 64)
+    freqs = geometry.freq_specs_from_table(ghz, feed_table)
+    bf = rt.near_field_binned(t, [0, 0, 0], grid_n=64, extent_cm=42.0, freqs=freqs, keep_sums=True)
+    assert bf.b.shape == (1, 64, 64, 64) and bf.stats[0, 0] == 15312
+    for f in (0, 17, 40, 63):
+        t.k, t.th_fwhp_x, t.th_fwhp_y = freqs[f]
+        ref = oracle.rx_to_lyot([0, 0, 0], t)
+        re, im, cnt, _ = oracle.bin_near_field(ref, float(t.k), 64, 420.0, 0.0)
+        ok = bf.count[0] == cnt
+        assert (~ok).sum() <= 2
+        s = np.abs(re + 1j * im).max()
+        assert np.abs(bf.re[0, f] - re)[ok].max() < 1e-5 * s
+        assert np.abs(bf.im[0, f] - im)[ok].max() < 1e-5 * s
+
+
+def test_cfg4_focal_plane_receiver_sweep(mods):
+    """BASELINE.json configs[3]: feeds on an 8 x 8 focal-plane grid with |rx| <= 150 mm, 90 GHz,
+    n_scan = 150, batched in one launch, against the oracle feed by feed."""
+    rt, oracle = mods["rt"], mods["oracle"]
+    t = _bundle(mods, 150, y_off=200)
+    g = np.linspace(-150, 150, 8)
+    rxs = [[x, 0.0, z] for x in g for z in g if np.hypot(x, z) <= 150.0]
+    assert len(rxs) == 32
+    bf = rt.near_field_binned(t, rxs, grid_n=32, extent_cm=42.0, keep_sums=True)
+    assert bf.stats[:, 6].sum() == 0
+    for i in range(0, len(rxs), 5):
+        ref = oracle.rx_to_lyot(rxs[i], t)
+        re, im, cnt, sums = oracle.bin_near_field(ref, float(t.k), 32, 420.0, 0.0)
+        assert bf.stats[i, 0] == sums["n_valid"] and bf.stats[i, 7] == sums["n_binned"]
+        assert bf.stats[i, 1] == pytest.approx(sums["sum_opl"], rel=1e-11)
+        ok = bf.count[i] == cnt
+        assert (~ok).sum() <= 2
+        s = np.abs(re + 1j * im).max()
+        assert np.abs(bf.re[i, 0] - re)[ok].max() < 1e-5 * s
