@@ -66,9 +66,11 @@ struct RowsParams {
 template <int N32, int N64>
 __global__ void __launch_bounds__(256)
 trace_rows_kernel(RowsParams p, double *__restrict__ out, double *__restrict__ stats) {
-    const long long j = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const bool live_thread = j0 < p.n;
+    const long long j = live_thread ? j0 : p.n - 1;  // idle lanes shadow the last ray: whole warps trace
     double acc[SOSAT_NUM_STATS] = {0, 0, 0, 0, 0, 0, 0, 0};
-    if (j < p.n) {
+    {
         const long long ii = p.ray_begin + j;
         const int ith = (int)(ii % p.n_scan), iph = (int)(ii / p.n_scan);
         const double th = linspace_at(p.lin_start, p.lin_stop, p.lin_step, p.n_scan, ith);
@@ -95,21 +97,24 @@ trace_rows_kernel(RowsParams p, double *__restrict__ out, double *__restrict__ s
                 const double hx = de_ho / p.fwhp_x, hy = de_ve / p.fwhp_y;
                 row[3] = r.opl;
                 row[4] = exp(-kFourLn2 * (hx * hx + hy * hy));
-                acc[SOSAT_STAT_N_VALID] = row[4] != 0.0 ? 1.0 : 0.0;
-                acc[SOSAT_STAT_SUM_OPL] = row[4] != 0.0 ? r.opl : 0.0;
-                acc[SOSAT_STAT_SUM_DX] = row[4] != 0.0 ? r.dx : 0.0;
-                acc[SOSAT_STAT_SUM_DY] = row[4] != 0.0 ? r.dy : 0.0;
-                acc[SOSAT_STAT_SUM_DZ] = row[4] != 0.0 ? r.dz : 0.0;
+                const bool count = live_thread && row[4] != 0.0;
+                acc[SOSAT_STAT_N_VALID] = count ? 1.0 : 0.0;
+                acc[SOSAT_STAT_SUM_OPL] = count ? r.opl : 0.0;
+                acc[SOSAT_STAT_SUM_DX] = count ? r.dx : 0.0;
+                acc[SOSAT_STAT_SUM_DY] = count ? r.dy : 0.0;
+                acc[SOSAT_STAT_SUM_DZ] = count ? r.dz : 0.0;
             }
             row[5] = r.nx; row[6] = r.ny; row[7] = r.nz;
             row[8] = r.dx; row[9] = r.dy; row[10] = r.dz;
         }
-        acc[SOSAT_STAT_N_SLOW] = (double)n_slow;
-        acc[SOSAT_STAT_N_BRACKET_FAIL] = (r.flags & RAY_BRACKET_FAIL) ? 1.0 : 0.0;
+        acc[SOSAT_STAT_N_SLOW] = live_thread ? (double)n_slow : 0.0;
+        acc[SOSAT_STAT_N_BRACKET_FAIL] = (live_thread && (r.flags & RAY_BRACKET_FAIL)) ? 1.0 : 0.0;
+        if (live_thread) {
 #pragma unroll
-        for (int q = 0; q < 11; ++q) out[(long long)q * p.n + j] = row[q];
+            for (int q = 0; q < 11; ++q) out[(long long)q * p.n + j] = row[q];
 #pragma unroll
-        for (int q = 11; q < SOSAT_OUT_ROWS; ++q) out[(long long)q * p.n + j] = 0.0;
+            for (int q = 11; q < SOSAT_OUT_ROWS; ++q) out[(long long)q * p.n + j] = 0.0;
+        }
     }
     if (stats) block_accumulate<SOSAT_NUM_STATS>(acc, stats);
 }
@@ -154,7 +159,9 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
 #pragma unroll
     for (int q = 0; q < 4; ++q) s_sum[q][tid] = 0.0;
     int acc_rx = -1;
-    const long long tiles_per_rx = (long long)p.tiles_x * p.tiles_y;
+    // tile bookkeeping in 32 bits (the host checks n_tiles < 2^31): 64-bit divisions cost
+    // ~100 instructions per tile otherwise
+    const unsigned tiles_per_rx = (unsigned)p.tiles_x * (unsigned)p.tiles_y;
     const long long plane = (long long)p.grid_n * p.grid_n;
 
     auto flush_stats = [&](int irx_done) {
@@ -173,10 +180,11 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
         for (int q = 0; q < 4; ++q) s_sum[q][tid] = 0.0;
     };
 
-    for (long long tile = blockIdx.x; tile < p.n_tiles; tile += gridDim.x) {
+    const unsigned n_tiles = (unsigned)p.n_tiles;
+    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int irx = (int)(tile / tiles_per_rx);
-        const long long trem = tile - (long long)irx * tiles_per_rx;
-        const int ty = (int)(trem / p.tiles_x), tx = (int)(trem - (long long)ty * p.tiles_x);
+        const unsigned trem = tile - (unsigned)irx * tiles_per_rx;
+        const int ty = (int)(trem / (unsigned)p.tiles_x), tx = (int)(trem - (unsigned)ty * (unsigned)p.tiles_x);
         if (irx != acc_rx) {
             if (acc_rx >= 0) flush_stats(acc_rx);
             acc_rx = irx;
@@ -184,9 +192,8 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
         __syncthreads();  // previous tile done with the tables
         if (tid < 2 * kTile) {
             const int which = tid / kTile, l = tid % kTile;  // 0: theta, 1: phi
-            const long long idx = which == 0 ? (long long)tx * kTile + l
-                                             : p.row_begin + (long long)ty * kTile + l;
-            const int ic = (int)(idx < p.n_scan ? idx : p.n_scan - 1);
+            const int idx = which == 0 ? tx * kTile + l : (int)p.row_begin + ty * kTile + l;
+            const int ic = idx < p.n_scan ? idx : p.n_scan - 1;
             const double a = linspace_at(p.lin_start, p.lin_stop, p.lin_step, p.n_scan, ic);
             double s, c;
             sincos(a, &s, &c);
@@ -204,19 +211,20 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
         }
         __syncthreads();
 
-        const long long ith = (long long)tx * kTile + lth;
-        const long long iph = (long long)ty * kTile + lph;  // relative to row_begin
+        const int ith = tx * kTile + lth;
+        const int iph = ty * kTile + lph;  // relative to row_begin
         const bool live = ith < p.n_scan && iph < p.n_rows;
         RayResult r;
-        r.valid = false;
-        r.flags = 0;
         unsigned n_slow = 0;
-        if (live) {
+        {
+            // lanes past the edge of the launch grid trace the clamped (edge) ray so that whole
+            // warps stay converged; their result is dropped
             const double sth = s_sin[0][lth], cth = s_cos[0][lth];
             const double sph = s_sin[1][lph], cph = s_cos[1][lph];
             const double *rx = d_rx + 3 * irx;
             trace_ray<N32, N64>(g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph, cth, r, n_slow);
         }
+        if (!live) n_slow = 0;
         const bool valid = live && r.valid;
         int bin = -1;
         if (valid) {
@@ -267,9 +275,9 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
             if (bin >= 0) {
                 const float a = s_amp[0][f][lth] * s_amp[1][f][lph];
                 double cyc = dopl * g_freq.kk[f];
-                cyc -= rint(cyc);
+                cyc -= rint(cyc);  // phase reduced to [-1/2, 1/2] cycles in fp64
                 float sn, cs;
-                sincospif(2.0f * (float)cyc, &sn, &cs);
+                __sincosf(6.2831853071795865f * (float)cyc, &sn, &cs);  // SFU, |err| < 1e-6
                 vre = a * cs;
                 vim = a * sn;
             }
@@ -386,8 +394,9 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-// Newton schedule (fp32 steps, fp64 steps) of the fast path; SOSAT_TRACE_VARIANT selects
-// another compiled schedule for experiments.
+// Newton schedule (fp32 steps, fp64 steps) of the fast path: default 2 + 2 plus the adaptive
+// refinement; SOSAT_TRACE_VARIANT = 0: 0+5, 2: 3+2, 5: 0+4 select the other compiled
+// schedules for experiments.
 static int trace_variant() {
     const char *e = getenv("SOSAT_TRACE_VARIANT");
     return e ? atoi(e) : 6;
@@ -486,14 +495,10 @@ extern "C" int sosat_trace_rays(const double *h_rx, const sosat_freq_t *h_freq, 
     SOSAT_REQUIRE((p.n + 255) / 256 < 2147483647LL, "too many rays for one launch");
     cudaStream_t st = (cudaStream_t)stream;
     switch (trace_variant()) {
-        case 1: launch_rows<0, 6>(p, d_out, d_stats, st); break;
+        case 0: launch_rows<0, 5>(p, d_out, d_stats, st); break;
         case 2: launch_rows<3, 2>(p, d_out, d_stats, st); break;
-        case 3: launch_rows<3, 3>(p, d_out, d_stats, st); break;
-        case 4: launch_rows<2, 3>(p, d_out, d_stats, st); break;
         case 5: launch_rows<0, 4>(p, d_out, d_stats, st); break;
-        case 6: launch_rows<2, 2>(p, d_out, d_stats, st); break;
-        case 7: launch_rows<4, 2>(p, d_out, d_stats, st); break;
-        default: launch_rows<0, 5>(p, d_out, d_stats, st); break;
+        default: launch_rows<2, 2>(p, d_out, d_stats, st); break;
     }
     SOSAT_CUDA_OK(cudaGetLastError());
     return SOSAT_OK;
@@ -546,13 +551,12 @@ template <int N32, int N64>
 static void launch_bin_minb(int minb, const BinParams &p, const double *rx, float *re, float *im,
                             float *cnt, double *stats, cudaStream_t st) {
     switch (minb) {
-        case 2: launch_bin<N32, N64, 2>(p, rx, re, im, cnt, stats, st); break;
-        case 4: launch_bin<N32, N64, 4>(p, rx, re, im, cnt, stats, st); break;
-        default: launch_bin<N32, N64, 3>(p, rx, re, im, cnt, stats, st); break;
+        case 3: launch_bin<N32, N64, 3>(p, rx, re, im, cnt, stats, st); break;
+        default: launch_bin<N32, N64, 4>(p, rx, re, im, cnt, stats, st); break;
     }
 }
 
-// resident CTAs per SM the binning kernel is compiled for (register budget 128 / 80 / 64)
+// resident CTAs per SM the binning kernel is compiled for (register budget 80 / 64)
 static int trace_minb() {
     const char *e = getenv("SOSAT_TRACE_MINB");
     return e ? atoi(e) : 4;
@@ -604,16 +608,14 @@ extern "C" int sosat_trace_bin(const double *d_rx, int n_rx, const sosat_freq_t 
     p.tiles_x = (n_scan + kTile - 1) / kTile;
     p.tiles_y = (p.n_rows + kTile - 1) / kTile;
     p.n_tiles = (long long)p.tiles_x * p.tiles_y * n_rx;
+    SOSAT_REQUIRE(p.n_tiles < 2147483647LL, "too many ray tiles for one launch (%lld): split the "
+                  "receiver list or the row range", p.n_tiles);
     const int minb = trace_minb();
     switch (trace_variant()) {
-        case 1: launch_bin_minb<0, 6>(minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
+        case 0: launch_bin_minb<0, 5>(minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
         case 2: launch_bin_minb<3, 2>(minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
-        case 3: launch_bin_minb<3, 3>(minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
-        case 4: launch_bin_minb<2, 3>(minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
         case 5: launch_bin_minb<0, 4>(minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
-        case 6: launch_bin_minb<2, 2>(minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
-        case 7: launch_bin_minb<4, 2>(minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
-        default: launch_bin_minb<0, 5>(minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
+        default: launch_bin_minb<2, 2>(minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
     }
     SOSAT_CUDA_OK(cudaGetLastError());
     // bf lives on this stack frame: the async symbol copy from pageable memory is staged

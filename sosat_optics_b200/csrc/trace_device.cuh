@@ -217,9 +217,10 @@ __device__ __forceinline__ void finish_ray(const GeomC &g, double Px, double Py,
               (r.opl == r.opl);
 }
 
-// The six-surface loop is kept rolled by default (constants fetched with LDC, ~6 KB of code);
-// -DSOSAT_UNROLL_SURFACES=1 unrolls it so the constants become immediate c[][] operands.
-#if defined(SOSAT_UNROLL_SURFACES) && SOSAT_UNROLL_SURFACES
+// The six-surface loop is unrolled so that the per-surface constants become immediate c[][]
+// operands of the DFMAs and the si == 0 / si == 3 / conic-edge tests fold away (+4 % over the
+// rolled loop with its LDC fetches, measured); -DSOSAT_UNROLL_SURFACES=0 keeps it rolled.
+#if !defined(SOSAT_UNROLL_SURFACES) || SOSAT_UNROLL_SURFACES
 #define SOSAT_SURFACE_LOOP_PRAGMA _Pragma("unroll")
 #else
 #define SOSAT_SURFACE_LOOP_PRAGMA _Pragma("unroll 1")
@@ -259,8 +260,11 @@ __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, doub
             step = f * rcp_seed(fp);
             t -= step;
         }
+        // warp-uniform refinement: every lane repeats the step while any lane still moves by
+        // more than REFINE (a converged lane just re-evaluates at its root); NaN lanes never ask
 #pragma unroll 1
-        for (int extra = 0; extra < SOSAT_NEWTON_EXTRA && fabs(step) > SOSAT_NEWTON_REFINE; ++extra) {
+        for (int extra = 0; extra < SOSAT_NEWTON_EXTRA &&
+                            __any_sync(0xffffffffu, fabs(step) > SOSAT_NEWTON_REFINE); ++extra) {
             double f, fp;
             surf_eval(S, Px, Pz, dx, dy, dz, y0Py, t, f, fp, X, Z, G, w);
             step = f * rcp_seed(fp);
@@ -272,11 +276,9 @@ __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, doub
         Px = fma(dx, t, Px);
         Py = fma(dy, t, Py);
         Pz = fma(dz, t, Pz);
-        if (si == 0 && fma(Px, Px, Pz * Pz) >= g.clip_l3_sq) {
-            r.flags = RAY_CLIPPED_L3;
-            r.valid = false;
-            return;
-        }
+        // lens-3 clip (ray_trace.py:1138-1140): the reference skips the ray; here the lane keeps
+        // tracing so that the warp stays converged, and the result is discarded at the end
+        if (si == 0 && fma(Px, Px, Pz * Pz) >= g.clip_l3_sq) flags |= RAY_CLIPPED_L3;
         if (si == 3) r2a_sq = fma(Px, Px, Pz * Pz);
         opl = fma(t, S.n_in, opl);  // dist_* = |hit - previous| = t for unit d
         refract(S, X, Z, G, dx, dy, dz, nx, ny, nz);
@@ -284,8 +286,12 @@ __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, doub
     r.nx = nx;
     r.ny = ny;
     r.nz = nz;
-    r.flags = flags;
     finish_ray(g, Px, Py, Pz, dx, dy, dz, opl, r2a_sq, r);
+    r.flags = flags;
+    if (flags & RAY_CLIPPED_L3) {
+        r.flags = RAY_CLIPPED_L3;
+        r.valid = false;
+    }
 }
 
 // ---- slow path: the reference's bracketed solve ---------------------------------------------
@@ -397,7 +403,8 @@ __device__ __noinline__ void trace_ray_bracketed(const GeomC &g, double Px, doub
     finish_ray(g, Px, Py, Pz, dx, dy, dz, opl, r2a_sq, r);
 }
 
-// Fast path, then the slow path for rays that came out valid but were flagged.
+// Fast path, then the slow path for rays that came out valid but were flagged.  Must be called
+// by all 32 lanes of a warp (the fast path votes with __any_sync).
 template <int N32, int N64>
 __device__ __forceinline__ void trace_ray(const GeomC &g, double Px, double Py, double Pz,
                                           double dx, double dy, double dz, RayResult &r,

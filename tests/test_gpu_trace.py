@@ -169,9 +169,13 @@ def test_host_buffer_entry_point_and_ranges(mods):
     full, stats = run(0, 37 * 37)
     assert stats[0] == (full[4] != 0).sum()
     assert stats[1] == pytest.approx(full[3].sum(), rel=1e-12)
+    # a sub-range equals the slice of the full run up to rounding: the adaptive Newton
+    # refinement is voted per warp, so a ray's last-bit result depends on its warp-mates
     for b, e in [(0, 1), (5, 300), (700, 1369), (1368, 1369)]:
         part, _ = run(b, e)
-        assert np.array_equal(part, full[:, b:e], equal_nan=True)
+        assert np.array_equal(np.isnan(part), np.isnan(full[:, b:e]))
+        assert np.array_equal(part[4] != 0, full[4, b:e] != 0)
+        assert np.allclose(part, full[:, b:e], rtol=1e-12, atol=1e-9, equal_nan=True)
     empty, _ = run(100, 100)
     assert empty.shape == (17, 0)
     # errors: reversed range, n_scan < 1
