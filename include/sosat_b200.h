@@ -159,11 +159,31 @@ int sosat_dft2_forget(const void *d_workspace);
 int sosat_dft2_gemm(const float *d_b, int n, float *d_B, void *d_workspace,
                     size_t workspace_bytes, void *stream);
 
+/* The other centred transforms of opt_analyze.py on the same GEMM path (a workspace holds the
+ * twiddles of one kind at a time and is re-planned when the kind changes):
+ *   SOSAT_DFT_FORWARD  fftshift(fft2(fftshift(x)))      a2b :225-228, beam_convolve :76-82
+ *   SOSAT_DFT_INVERSE  ifftshift(ifft2(ifftshift(x)))   beam_convolve :86-88
+ *   SOSAT_DFT_B2A      fftshift(ifft2(x))               b2a :213-215 (line :213's shifted copy
+ *                                                       is discarded by :214; quirk kept) */
+enum { SOSAT_DFT_FORWARD = 0, SOSAT_DFT_INVERSE = 1, SOSAT_DFT_B2A = 2 };
+int sosat_dft2_gemm_kind(const float *d_b, int n, float *d_B, int kind, void *d_workspace,
+                         size_t workspace_bytes, void *stream);
+
 /* a2b with the reference's argument meaning: d_apert (amplitude, abs() is taken) and
  * d_phi_deg (phase in degrees) are [n][n] float64; outputs d_beam [n][n][2] float64
  * (complex128) and d_phase [n][n] float64 = arctan2(imag, real). */
 int sosat_a2b(const double *d_apert, const double *d_phi_deg, int n, double *d_beam,
               double *d_phase, void *d_workspace, size_t workspace_bytes, void *stream);
+/* b2a (opt_analyze.py:208-217), same argument meaning as the reference: |beam| and phase in
+ * degrees in, complex128 aperture field and its arctan2 phase out. */
+int sosat_b2a(const double *d_beam, const double *d_phase_deg, int n, double *d_aper,
+              double *d_aper_phase, void *d_workspace, size_t workspace_bytes, void *stream);
+/* beam_convolve building blocks (opt_analyze.py:60-88): the cos-tapered rectangular horn
+ * aperture on the caller's coordinate grids (complex64 out, n = number of cells) and a
+ * pointwise complex product; the three transforms go through sosat_dft2_gemm_kind. */
+int sosat_horn_aperture(const double *d_x, const double *d_y, int64_t n, double apert1,
+                        double apert2, float *d_out, void *stream);
+int sosat_cmul(const float *d_a, const float *d_b, int64_t n, float *d_out, void *stream);
 /* Host-buffer form (synchronous): allocates and frees device temporaries. */
 int sosat_a2b_host(const double *h_apert, const double *h_phi_deg, int n, double *h_beam,
                    double *h_phase);

@@ -201,7 +201,37 @@ def gen_a2b(mods, fw):
     np.savez_compressed(os.path.join(GOLD, "a2b_small.npz"), **store)
 
 
-GENS = dict(feedhorn=gen_feedhorn, trace=gen_trace, a2b=gen_a2b, farfield=gen_farfield,
+def gen_convolve(mods, fw):
+    """b2a, beam_convolve and coords_ang_to_spat (rows f3/f4) on small fields, odd and even N."""
+    ot_geo, ray_trace, opt_analyze = mods
+    rng = np.random.default_rng(7)
+    store = {}
+    for n in (16, 65, 96, 129):
+        amp = rng.uniform(0, 1, (n, n))
+        amp[rng.uniform(size=(n, n)) < 0.1] *= -1  # b2a takes abs()
+        phi = rng.uniform(-180, 180, (n, n))
+        af, ap = opt_analyze.b2a(amp, phi)
+        store[f"b2a_amp_{n}"], store[f"b2a_phi_{n}"] = amp, phi
+        store[f"b2a_field_{n}"], store[f"b2a_phase_{n}"] = af, ap
+    # a2b -> b2a on a smooth aperture (what a holography analysis does)
+    for n, dx in ((64, 0.5), (101, 0.4)):
+        x = (np.arange(n) - n // 2) * dx
+        X, Y = np.meshgrid(x, x)
+        R = np.hypot(X, Y)
+        beam = np.exp(-R ** 2 / (2 * 5.0 ** 2)) * np.exp(1j * (0.4 * np.cos(X / 4) + 0.02 * Y))
+        beam[R > 14] = 0
+        for (a1, a2) in ((2.0, 3.0), (3.5, 1.5), (2.0, 2.0)):
+            _, _, bf = opt_analyze.beam_convolve(X, Y, beam, a1, a2, 0)
+            store[f"conv_{n}_{a1}_{a2}"] = bf
+        store[f"conv_x_{n}"], store[f"conv_y_{n}"], store[f"conv_beam_{n}"] = X, Y, beam
+    th = np.linspace(-0.2, 0.2, 81)
+    TX, TY = np.meshgrid(th, 1.5 * th)
+    xs, ys = opt_analyze.coords_ang_to_spat(TX, TY, 90.0)
+    store.update(a2s_tx=TX, a2s_ty=TY, a2s_x=xs, a2s_y=ys)
+    np.savez_compressed(os.path.join(GOLD, "b2a_convolve_small.npz"), **store)
+
+
+GENS = dict(convolve=gen_convolve, feedhorn=gen_feedhorn, trace=gen_trace, a2b=gen_a2b, farfield=gen_farfield,
             reqs=gen_reqs)
 
 if __name__ == "__main__":

@@ -13,6 +13,9 @@ What is restated here (reference file:line, relative to the reference checkout):
 * ``zero_pad``                         opt_analyze.py:20-32
 * ``a2b``                              opt_analyze.py:220-230  (numpy.fft, pocketfft)
 * ``coords_spat_to_ang``               opt_analyze.py:274-299
+* ``b2a``                              opt_analyze.py:208-217
+* ``beam_convolve``                    opt_analyze.py:60-88
+* ``coords_ang_to_spat``               opt_analyze.py:233-271
 * ``ghz_to_m`` / ``m_to_ghz``          opt_analyze.py:42-57
 * near-field binning b(x,y): no reference function exists (SURVEY.md section 8 row a7);
   :func:`bin_near_field` is the specification the CUDA kernel is held to.
@@ -258,6 +261,61 @@ def coords_spat_to_ang(x, y, freq):  # opt_analyze.py:274-299
     x_ang = np.linspace(-int(len(x) / 2), int(len(x) / 2), int(len(x))) * delta_th
     y_ang = np.linspace(-int(len(x) / 2), int(len(x) / 2), int(len(x))) * delta_ph
     return tuple(np.meshgrid(x_ang, y_ang))
+
+
+def b2a(beam, phase):  # opt_analyze.py:208-217
+    beam_complex = abs(beam) * np.exp(phase * np.pi / 180.0 * complex(0, 1))
+    # line 213 computes fftshift(beam_complex) and line 214 discards it: the input is NOT shifted
+    aper_field = np.fft.fftshift(np.fft.ifft2(beam_complex))
+    return aper_field, np.arctan2(np.imag(aper_field), np.real(aper_field))
+
+
+def horn_aperture(x, y, apert1, apert2):  # opt_analyze.py:65-73
+    if apert1 < apert2:
+        disc = np.cos(np.pi * y / apert2)
+        disc = np.where(abs(y) <= apert2 / 2, disc, 0)
+        disc = np.where(abs(x) <= apert1 / 2, disc, 0)
+    else:
+        disc = np.cos(np.pi * x / apert1)
+        disc = np.where(abs(x) <= apert1 / 2, disc, 0)
+        disc = np.where(abs(y) <= apert2 / 2, disc, 0)
+    return disc
+
+
+def beam_convolve(x, y, beam, apert1, apert2, plots=0):  # opt_analyze.py:60-88
+    disc = horn_aperture(x, y, apert1, apert2)
+    disc_fft = np.fft.fftshift(np.fft.fft2(np.fft.fftshift(disc)))
+    beam_fft = np.fft.fftshift(np.fft.fft2(np.fft.fftshift(beam)))
+    beam_conv = beam_fft * disc_fft
+    beam_final = np.fft.ifftshift(np.fft.ifft2(np.fft.ifftshift(beam_conv)))
+    return x, y, beam_final
+
+
+def coords_ang_to_spat(theta_x, theta_y, freq):  # opt_analyze.py:233-271
+    lam = (3 * 10 ** 8) / (freq * 1e9)
+    delta_th = abs(np.max(theta_y) - np.min(theta_y)) / (len(theta_y) - 1)  # :241 overwrites :238
+    delta_x = (lam / delta_th) / len(theta_x)
+    delta_y = (lam / delta_th) / len(theta_y)
+    half, cnt = int(len(theta_x) / 2), int(len(theta_x))
+    x_spat = np.linspace(-half, half, cnt) * delta_x * 1e2
+    y_spat = np.linspace(-half, half, cnt) * delta_y * 1e2
+    return tuple(np.meshgrid(x_spat, y_spat))
+
+
+def dft2_kind(b, kind):
+    """The three centred transforms of opt_analyze.py as dense contractions W b W^T with
+    W[k, m] = exp(sign 2 pi i (k - so)(m - si) / N) (exact integer phase) and a scale:
+    0 forward  fftshift(fft2(fftshift(b)))     so = floor(N/2), si = ceil(N/2), sign -, 1
+    1 inverse  ifftshift(ifft2(ifftshift(b)))  so = ceil(N/2),  si = floor(N/2), sign +, 1/N^2
+    2 b2a      fftshift(ifft2(b))              so = floor(N/2), si = 0,          sign +, 1/N^2"""
+    n = b.shape[0]
+    so, si, sign, scale = {0: (n // 2, (n + 1) // 2, -1, 1.0),
+                           1: ((n + 1) // 2, n // 2, 1, 1.0 / n ** 2),
+                           2: (n // 2, 0, 1, 1.0 / n ** 2)}[kind]
+    k = np.arange(n)[:, None] - so
+    m = np.arange(n)[None, :] - si
+    w = np.exp(sign * 2j * np.pi * ((k * m) % n) / n)
+    return (w @ b @ w.T) * scale
 
 
 def dft2_centered(b):

@@ -14,6 +14,7 @@ NUM_SURFACES = 6
 OUT_ROWS = 17
 MAX_FREQS = 64
 NUM_STATS = 8
+DFT_FORWARD, DFT_INVERSE, DFT_B2A = 0, 1, 2
 (STAT_N_VALID, STAT_SUM_OPL, STAT_SUM_DX, STAT_SUM_DY, STAT_SUM_DZ, STAT_N_SLOW,
  STAT_N_BRACKET_FAIL, STAT_N_BINNED) = range(8)
 
@@ -57,6 +58,13 @@ SIGNATURES = {
     "sosat_dft2_workspace_bytes": (c_size_t, [c_int]),
     "sosat_dft2_forget": (c_int, [c_void_p]),
     "sosat_dft2_gemm": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
+    "sosat_dft2_gemm_kind": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_size_t,
+                                     c_void_p]),
+    "sosat_b2a": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
+                          c_void_p]),
+    "sosat_horn_aperture": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_double, c_void_p,
+                                    c_void_p]),
+    "sosat_cmul": (c_int, [c_void_p, c_void_p, c_int64, c_void_p, c_void_p]),
     "sosat_a2b": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                           c_void_p]),
     "sosat_a2b_host": (c_int, [POINTER(c_double), POINTER(c_double), c_int, POINTER(c_double),

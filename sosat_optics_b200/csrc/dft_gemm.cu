@@ -231,17 +231,18 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bflo
 
 // Twiddle operands for both passes; np = padded size, rows/cols beyond n are zero.
 //   a1 (pass 1, K interleaved): a1[2l+c][2n+c'],   a2 (pass 2, K planar): a2[2k+c][c' np + m]
-__global__ void twiddle_kernel(int n, int np, __nv_bfloat16 *a1_hi, __nv_bfloat16 *a1_lo,
-                               __nv_bfloat16 *a2_hi, __nv_bfloat16 *a2_lo) {
+// W[k, m] = exp(sign 2 pi i ((k - so)(m - si) mod n) / n): the shifts express the fftshift /
+// ifftshift pairs of the reference (see dft_kind_params).
+__global__ void twiddle_kernel(int n, int np, int so, int si, int sign, __nv_bfloat16 *a1_hi,
+                               __nv_bfloat16 *a1_lo, __nv_bfloat16 *a2_hi, __nv_bfloat16 *a2_lo) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
     if (col >= np) return;
     float wr = 0.f, wi = 0.f;
     if (row < n && col < n) {
-        const long long so = n / 2, si = (n + 1) / 2;
         long long j = ((long long)(row - so) * (long long)(col - si)) % n;
         if (j < 0) j += n;
         double s, c;
-        sincospi(-2.0 * (double)j / (double)n, &s, &c);  // exact integer phase, SURVEY section 7
+        sincospi((double)sign * 2.0 * (double)j / (double)n, &s, &c);  // exact integer phase
         wr = (float)c;
         wi = (float)s;
     }
@@ -297,20 +298,21 @@ __global__ void prep_b_a2b_kernel(const double *__restrict__ amp, const double *
 }
 
 // d2 planar fp32 [2 np][np] (row 2k+c, column l) -> interleaved complex64 [n][n]
-__global__ void finish_c64_kernel(const float *__restrict__ d2, int n, int np,
+__global__ void finish_c64_kernel(const float *__restrict__ d2, int n, int np, float scale,
                                   float2 *__restrict__ out) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
     if (col >= n) return;
-    out[(size_t)row * n + col] = make_float2(d2[(size_t)(2 * row) * np + col],
-                                             d2[(size_t)(2 * row + 1) * np + col]);
+    out[(size_t)row * n + col] = make_float2(scale * d2[(size_t)(2 * row) * np + col],
+                                             scale * d2[(size_t)(2 * row + 1) * np + col]);
 }
 
 // a2b outputs: complex128 beam and phase = arctan2(imag, real), opt_analyze.py:228-229
-__global__ void finish_a2b_kernel(const float *__restrict__ d2, int n, int np,
+__global__ void finish_a2b_kernel(const float *__restrict__ d2, int n, int np, double scale,
                                   double2 *__restrict__ beam, double *__restrict__ phase) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
     if (col >= n) return;
-    const double re = d2[(size_t)(2 * row) * np + col], im = d2[(size_t)(2 * row + 1) * np + col];
+    const double re = scale * d2[(size_t)(2 * row) * np + col];
+    const double im = scale * d2[(size_t)(2 * row + 1) * np + col];
     beam[(size_t)row * n + col] = make_double2(re, im);
     phase[(size_t)row * n + col] = atan2(im, re);
 }
@@ -387,24 +389,42 @@ static int make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t col
 struct PlanEntry {
     int device;
     const void *ws;
-    int n;
+    int n, kind;
 };
 static PlanEntry g_plans[64];
 static int g_num_plans = 0;
 
-static int ensure_twiddles(const DftWorkspace &w, cudaStream_t st) {
-    int dev = 0;
+// The three centred transforms of opt_analyze.py as (output shift, input shift, sign, scale):
+//   FORWARD   fftshift(fft2(fftshift(x)))      a2b :225-228, beam_convolve :76-82
+//   INVERSE   ifftshift(ifft2(ifftshift(x)))   beam_convolve :86-88
+//   B2A       fftshift(ifft2(x))               b2a :213-215 (the shifted input of :213 is
+//                                              discarded by :214 -- quirk kept)
+static int dft_kind_params(int kind, int n, int &so, int &si, int &sign, double &scale) {
+    switch (kind) {
+        case SOSAT_DFT_FORWARD: so = n / 2; si = (n + 1) / 2; sign = -1; scale = 1.0; return 0;
+        case SOSAT_DFT_INVERSE: so = (n + 1) / 2; si = n / 2; sign = +1; scale = 1.0 / ((double)n * n); return 0;
+        case SOSAT_DFT_B2A: so = n / 2; si = 0; sign = +1; scale = 1.0 / ((double)n * n); return 0;
+    }
+    return set_error(SOSAT_ERR_INVALID_ARG, "unknown transform kind %d", kind);
+}
+
+static int ensure_twiddles(const DftWorkspace &w, int kind, cudaStream_t st) {
+    int dev = 0, so, si, sign;
+    double scale;
     SOSAT_CUDA_OK(cudaGetDevice(&dev));
+    if (int rc = dft_kind_params(kind, w.n, so, si, sign, scale)) return rc;
     for (int i = 0; i < g_num_plans; ++i)
-        if (g_plans[i].device == dev && g_plans[i].ws == w.base && g_plans[i].n == w.n) return 0;
+        if (g_plans[i].device == dev && g_plans[i].ws == w.base && g_plans[i].n == w.n &&
+            g_plans[i].kind == kind)
+            return 0;
     dim3 grid((w.np + 127) / 128, w.np);
-    twiddle_kernel<<<grid, 128, 0, st>>>(w.n, w.np, w.a1_hi, w.a1_lo, w.a2_hi, w.a2_lo);
+    twiddle_kernel<<<grid, 128, 0, st>>>(w.n, w.np, so, si, sign, w.a1_hi, w.a1_lo, w.a2_hi, w.a2_lo);
     SOSAT_CUDA_OK(cudaGetLastError());
     int slot = -1;
     for (int i = 0; i < g_num_plans; ++i)
-        if (g_plans[i].device == dev && g_plans[i].ws == w.base) slot = i;  // same buffer, new n
+        if (g_plans[i].device == dev && g_plans[i].ws == w.base) slot = i;  // same buffer, re-planned
     if (slot < 0) slot = g_num_plans < 64 ? g_num_plans++ : 0;
-    g_plans[slot] = PlanEntry{dev, w.base, w.n};
+    g_plans[slot] = PlanEntry{dev, w.base, w.n, kind};
     return 0;
 }
 
@@ -461,18 +481,47 @@ extern "C" int sosat_dft2_forget(const void *d_workspace) {
     return SOSAT_OK;
 }
 
-extern "C" int sosat_dft2_gemm(const float *d_b, int n, float *d_B, void *d_workspace,
-                               size_t workspace_bytes_, void *stream) {
+extern "C" int sosat_dft2_gemm_kind(const float *d_b, int n, float *d_B, int kind,
+                                    void *d_workspace, size_t workspace_bytes_, void *stream) {
     SOSAT_REQUIRE(d_b && d_B, "sosat_dft2_gemm: null pointer");
     if (int rc = check_ws(d_workspace, workspace_bytes_, n)) return rc;
+    int so, si, sign;
+    double scale;
+    if (int rc = dft_kind_params(kind, n, so, si, sign, scale)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     DftWorkspace w = carve(d_workspace, n);
-    if (int rc = ensure_twiddles(w, st)) return rc;
+    if (int rc = ensure_twiddles(w, kind, st)) return rc;
     dim3 grid((w.np + 127) / 128, w.np);
     prep_b_c64_kernel<<<grid, 128, 0, st>>>((const float2 *)d_b, n, w.np, w.b1_hi, w.b1_lo);
     if (int rc = run_passes(w, st)) return rc;
     dim3 g2((n + 127) / 128, n);
-    finish_c64_kernel<<<g2, 128, 0, st>>>(w.d2, n, w.np, (float2 *)d_B);
+    finish_c64_kernel<<<g2, 128, 0, st>>>(w.d2, n, w.np, (float)scale, (float2 *)d_B);
+    SOSAT_CUDA_OK(cudaGetLastError());
+    return SOSAT_OK;
+}
+
+extern "C" int sosat_dft2_gemm(const float *d_b, int n, float *d_B, void *d_workspace,
+                               size_t workspace_bytes_, void *stream) {
+    return sosat_dft2_gemm_kind(d_b, n, d_B, SOSAT_DFT_FORWARD, d_workspace, workspace_bytes_,
+                                stream);
+}
+
+static int amp_phase_transform(const double *d_amp, const double *d_phi_deg, int n, int kind,
+                               double *d_out, double *d_phase, void *d_workspace,
+                               size_t workspace_bytes_, void *stream) {
+    SOSAT_REQUIRE(d_amp && d_phi_deg && d_out && d_phase, "null pointer");
+    if (int rc = check_ws(d_workspace, workspace_bytes_, n)) return rc;
+    int so, si, sign;
+    double scale;
+    if (int rc = dft_kind_params(kind, n, so, si, sign, scale)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    DftWorkspace w = carve(d_workspace, n);
+    if (int rc = ensure_twiddles(w, kind, st)) return rc;
+    dim3 grid((w.np + 127) / 128, w.np);
+    prep_b_a2b_kernel<<<grid, 128, 0, st>>>(d_amp, d_phi_deg, n, w.np, w.b1_hi, w.b1_lo);
+    if (int rc = run_passes(w, st)) return rc;
+    dim3 g2((n + 127) / 128, n);
+    finish_a2b_kernel<<<g2, 128, 0, st>>>(w.d2, n, w.np, scale, (double2 *)d_out, d_phase);
     SOSAT_CUDA_OK(cudaGetLastError());
     return SOSAT_OK;
 }
@@ -480,18 +529,15 @@ extern "C" int sosat_dft2_gemm(const float *d_b, int n, float *d_B, void *d_work
 extern "C" int sosat_a2b(const double *d_apert, const double *d_phi_deg, int n, double *d_beam,
                          double *d_phase, void *d_workspace, size_t workspace_bytes_,
                          void *stream) {
-    SOSAT_REQUIRE(d_apert && d_phi_deg && d_beam && d_phase, "sosat_a2b: null pointer");
-    if (int rc = check_ws(d_workspace, workspace_bytes_, n)) return rc;
-    cudaStream_t st = (cudaStream_t)stream;
-    DftWorkspace w = carve(d_workspace, n);
-    if (int rc = ensure_twiddles(w, st)) return rc;
-    dim3 grid((w.np + 127) / 128, w.np);
-    prep_b_a2b_kernel<<<grid, 128, 0, st>>>(d_apert, d_phi_deg, n, w.np, w.b1_hi, w.b1_lo);
-    if (int rc = run_passes(w, st)) return rc;
-    dim3 g2((n + 127) / 128, n);
-    finish_a2b_kernel<<<g2, 128, 0, st>>>(w.d2, n, w.np, (double2 *)d_beam, d_phase);
-    SOSAT_CUDA_OK(cudaGetLastError());
-    return SOSAT_OK;
+    return amp_phase_transform(d_apert, d_phi_deg, n, SOSAT_DFT_FORWARD, d_beam, d_phase,
+                               d_workspace, workspace_bytes_, stream);
+}
+
+extern "C" int sosat_b2a(const double *d_beam, const double *d_phase_deg, int n, double *d_aper,
+                         double *d_aper_phase, void *d_workspace, size_t workspace_bytes_,
+                         void *stream) {
+    return amp_phase_transform(d_beam, d_phase_deg, n, SOSAT_DFT_B2A, d_aper, d_aper_phase,
+                               d_workspace, workspace_bytes_, stream);
 }
 
 extern "C" int sosat_a2b_host(const double *h_apert, const double *h_phi_deg, int n,
@@ -518,4 +564,54 @@ extern "C" int sosat_a2b_host(const double *h_apert, const double *h_phi_deg, in
     sosat_dft2_forget(buf);
     cudaFree(buf);
     return rc;
+}
+
+// ---- beam_convolve helpers (opt_analyze.py:60-88) ---------------------------------------------
+namespace sosat {
+// cos-tapered rectangular horn aperture "disc" (opt_analyze.py:65-73) as complex64
+__global__ void horn_aperture_kernel(const double *__restrict__ x, const double *__restrict__ y,
+                                     long long n, double apert1, double apert2,
+                                     float2 *__restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const double xv = x[i], yv = y[i];
+        double d = apert1 < apert2 ? cospi(yv / apert2) : cospi(xv / apert1);
+        if (!(fabs(xv) <= apert1 / 2) || !(fabs(yv) <= apert2 / 2)) d = 0.0;
+        out[i] = make_float2((float)d, 0.f);
+    }
+}
+__global__ void cmul_kernel(const float2 *__restrict__ a, const float2 *__restrict__ b, long long n,
+                            float2 *__restrict__ out) {
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float2 u = a[i], v = b[i];
+        out[i] = make_float2(u.x * v.x - u.y * v.y, u.x * v.y + u.y * v.x);
+    }
+}
+}  // namespace sosat
+
+extern "C" int sosat_horn_aperture(const double *d_x, const double *d_y, int64_t n, double apert1,
+                                   double apert2, float *d_out, void *stream) {
+    SOSAT_REQUIRE(d_x && d_y && d_out, "sosat_horn_aperture: null pointer");
+    SOSAT_REQUIRE(n >= 0, "negative size");
+    if (n == 0) return SOSAT_OK;
+    long long blocks = (n + 255) / 256;
+    if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+    horn_aperture_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        d_x, d_y, n, apert1, apert2, (float2 *)d_out);
+    SOSAT_CUDA_OK(cudaGetLastError());
+    return SOSAT_OK;
+}
+
+extern "C" int sosat_cmul(const float *d_a, const float *d_b, int64_t n, float *d_out,
+                          void *stream) {
+    SOSAT_REQUIRE(d_a && d_b && d_out, "sosat_cmul: null pointer");
+    SOSAT_REQUIRE(n >= 0, "negative size");
+    if (n == 0) return SOSAT_OK;
+    long long blocks = (n + 255) / 256;
+    if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+    cmul_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        (const float2 *)d_a, (const float2 *)d_b, n, (float2 *)d_out);
+    SOSAT_CUDA_OK(cudaGetLastError());
+    return SOSAT_OK;
 }

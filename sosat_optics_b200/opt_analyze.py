@@ -4,10 +4,14 @@
 function                reference                device code
 ======================  =======================  ==============================================
 ``a2b``                 opt_analyze.py:220-230   ``sosat_a2b``: tcgen05 bf16x3 DFT-GEMM (dft_gemm.cu)
+``b2a``                 opt_analyze.py:208-217   ``sosat_b2a``: same GEMM path, conjugate twiddles
+``beam_convolve``       opt_analyze.py:60-88     ``sosat_horn_aperture`` + 3 x ``sosat_dft2_gemm_kind``
+                                                 + ``sosat_cmul``
 ``far_field``           -- (north_star)          ``sosat_dft2_gemm`` on complex64 device/host data
 ``far_field_irregular`` -- (north_star)          ``sosat_nudft_direct`` direct sum (nudft.cu)
 ``zero_pad``            opt_analyze.py:20-32     host index bookkeeping (np.pad + coordinates)
 ``coords_spat_to_ang``  opt_analyze.py:274-299   host label arithmetic on N values
+``coords_ang_to_spat``  opt_analyze.py:233-271   host label arithmetic on N values
 ``ghz_to_m, m_to_ghz``  opt_analyze.py:42-57     scalar helpers
 ======================  =======================  ==============================================
 """
@@ -21,8 +25,8 @@ import numpy as np
 from . import _lib
 from .ray_trace import _stream, _torch
 
-__all__ = ["a2b", "far_field", "far_field_irregular", "zero_pad", "coords_spat_to_ang",
-           "ghz_to_m", "m_to_ghz", "rad_to_arcmin"]
+__all__ = ["a2b", "b2a", "beam_convolve", "far_field", "far_field_irregular", "zero_pad",
+           "coords_spat_to_ang", "coords_ang_to_spat", "ghz_to_m", "m_to_ghz", "rad_to_arcmin"]
 
 
 def rad_to_arcmin(rads):
@@ -75,12 +79,34 @@ def coords_spat_to_ang(x, y, freq):
     return x_ang, y_ang
 
 
-# --- DFT-GEMM workspaces: one per (device, n), kept alive so twiddles are generated once ----
+def coords_ang_to_spat(theta_x, theta_y, freq):
+    """Spatial labels [cm] of the aperture grid (opt_analyze.py:233-271).  Kept as written:
+    the second ``delta_th`` assignment (from ``theta_y``) overwrites the first, so both axes use
+    the theta_y increment, and ``len(theta_x)`` sizes both axes."""
+    ff_ghz = freq * 1e9
+    lam = (3 * 10 ** 8) / ff_ghz
+    delta_th = abs(np.max(theta_x) - np.min(theta_x)) / (len(theta_x) - 1)
+    delta_th = abs(np.max(theta_y) - np.min(theta_y)) / (len(theta_y) - 1)
+    x_len = len(theta_x)
+    y_len = len(theta_y)
+    alpha = lam / delta_th
+    beta = lam / delta_th
+    delta_x = alpha / x_len
+    delta_y = beta / y_len
+    half, cnt = int(len(theta_x) / 2), int(len(theta_x))
+    x_spat = np.linspace(-half, half, cnt) * delta_x * 1e2
+    y_spat = np.linspace(-half, half, cnt) * delta_y * 1e2
+    x_spat, y_spat = np.meshgrid(x_spat, y_spat)
+    return x_spat, y_spat
+
+
+# --- DFT-GEMM workspaces: one per (device, n, transform kind), kept alive so the twiddles of
+# each kind are generated once ------------------------------------------------------------------
 _workspaces = {}
 
 
-def _workspace(lib, torch, n: int):
-    key = (torch.cuda.current_device(), int(n))
+def _workspace(lib, torch, n: int, kind: int = _lib.DFT_FORWARD):
+    key = (torch.cuda.current_device(), int(n), int(kind))
     ws = _workspaces.get(key)
     if ws is None:
         nbytes = int(lib.sosat_dft2_workspace_bytes(int(n)))
@@ -102,22 +128,88 @@ def a2b(apert, phi):
     ``(beam_complex complex128 [N, N], phase float64 [N, N])`` with
     ``beam_complex = fftshift(fft2(fftshift(|A| exp(i phi pi/180))))`` computed as the dense
     separable contraction W b W^T on tensor cores, and ``phase = arctan2(imag, real)``."""
+    return _amp_phase_transform("a2b", apert, phi, _lib.DFT_FORWARD)
+
+
+def _amp_phase_transform(fn_name, amp, phase_deg, kind):
     lib = _lib.require_gpu()
     torch = _torch()
-    apert = np.asarray(apert, dtype=np.float64)
-    phi = np.asarray(phi, dtype=np.float64)
-    if apert.ndim != 2 or apert.shape[0] != apert.shape[1] or apert.shape != phi.shape:
-        raise ValueError("a2b expects square [N, N] amplitude and phase arrays of equal shape")
-    n = apert.shape[0]
-    d_a = torch.from_numpy(np.ascontiguousarray(apert)).to("cuda")
-    d_p = torch.from_numpy(np.ascontiguousarray(phi)).to("cuda")
-    beam = torch.empty((n, n, 2), dtype=torch.float64, device="cuda")
+    amp = np.asarray(amp, dtype=np.float64)
+    phase_deg = np.asarray(phase_deg, dtype=np.float64)
+    if amp.ndim != 2 or amp.shape[0] != amp.shape[1] or amp.shape != phase_deg.shape:
+        raise ValueError(f"{fn_name} expects square [N, N] amplitude and phase arrays of equal shape")
+    n = amp.shape[0]
+    d_a = torch.from_numpy(np.ascontiguousarray(amp)).to("cuda")
+    d_p = torch.from_numpy(np.ascontiguousarray(phase_deg)).to("cuda")
+    field = torch.empty((n, n, 2), dtype=torch.float64, device="cuda")
     phase = torch.empty((n, n), dtype=torch.float64, device="cuda")
-    ws = _workspace(lib, torch, n)
-    _lib.check(lib.sosat_a2b(ctypes.c_void_p(d_a.data_ptr()), ctypes.c_void_p(d_p.data_ptr()), n,
-                             ctypes.c_void_p(beam.data_ptr()), ctypes.c_void_p(phase.data_ptr()),
-                             ctypes.c_void_p(ws.data_ptr()), ws.numel(), _stream(torch)))
-    return torch.view_as_complex(beam).cpu().numpy(), phase.cpu().numpy()
+    ws = _workspace(lib, torch, n, kind)
+    fn = getattr(lib, "sosat_" + fn_name)
+    _lib.check(fn(ctypes.c_void_p(d_a.data_ptr()), ctypes.c_void_p(d_p.data_ptr()), n,
+                  ctypes.c_void_p(field.data_ptr()), ctypes.c_void_p(phase.data_ptr()),
+                  ctypes.c_void_p(ws.data_ptr()), ws.numel(), _stream(torch)))
+    return torch.view_as_complex(field).cpu().numpy(), phase.cpu().numpy()
+
+
+def b2a(beam, phase):
+    """FFT angular space to aperture plane (opt_analyze.py:208-217).
+
+    ``beam``: [N, N] (``abs`` is taken), ``phase`` in DEGREES.  Returns ``(aper_field complex128,
+    aper_phase float64)`` with ``aper_field = fftshift(ifft2(|beam| exp(i phase pi/180)))`` --
+    the reference computes ``fftshift(beam_complex)`` on line 213 and then discards it on line
+    214, so the input is NOT shifted; kept."""
+    return _amp_phase_transform("b2a", beam, phase, _lib.DFT_B2A)
+
+
+def _dft_kind(lib, torch, d_in, kind):
+    """Centred transform of a complex64 CUDA tensor [N, N] through sosat_dft2_gemm_kind."""
+    n = d_in.shape[0]
+    out = torch.empty((n, n), dtype=torch.complex64, device="cuda")
+    ws = _workspace(lib, torch, n, kind)
+    _lib.check(lib.sosat_dft2_gemm_kind(ctypes.c_void_p(d_in.data_ptr()), n,
+                                        ctypes.c_void_p(out.data_ptr()), int(kind),
+                                        ctypes.c_void_p(ws.data_ptr()), ws.numel(),
+                                        _stream(torch)))
+    return out
+
+
+def beam_convolve(x, y, beam, apert1, apert2, plots=0):
+    """Convolve ``beam`` with the cos-tapered rectangular horn aperture (opt_analyze.py:60-88):
+    ``ifftshift(ifft2(ifftshift(F(beam) * F(disc))))`` with ``F = fftshift . fft2 . fftshift``.
+    ``x``, ``y``: [N, N] coordinate grids, ``beam``: complex [N, N].  Returns
+    ``(x, y, beam_final complex128)``; ``plots`` is accepted and ignored."""
+    lib = _lib.require_gpu()
+    torch = _torch()
+    xa = np.ascontiguousarray(np.asarray(x, dtype=np.float64))
+    ya = np.ascontiguousarray(np.asarray(y, dtype=np.float64))
+    bm = np.asarray(beam)
+    if bm.ndim != 2 or bm.shape[0] != bm.shape[1] or xa.shape != bm.shape or ya.shape != bm.shape:
+        raise ValueError("beam_convolve expects square [N, N] x, y and beam arrays of equal shape")
+    n = bm.shape[0]
+    # fp32 storage on the device: normalise so that small-valued beams keep their precision
+    scale = float(np.max(np.abs(bm))) if bm.size else 0.0
+    if not np.isfinite(scale) or scale == 0.0:
+        scale = 1.0
+    d_beam = torch.from_numpy(np.ascontiguousarray((bm / scale).astype(np.complex64))).to("cuda")
+    d_x = torch.from_numpy(xa).to("cuda")
+    d_y = torch.from_numpy(ya).to("cuda")
+    disc = torch.empty((n, n), dtype=torch.complex64, device="cuda")
+    _lib.check(lib.sosat_horn_aperture(ctypes.c_void_p(d_x.data_ptr()),
+                                       ctypes.c_void_p(d_y.data_ptr()), n * n, float(apert1),
+                                       float(apert2), ctypes.c_void_p(disc.data_ptr()),
+                                       _stream(torch)))
+    disc_fft = _dft_kind(lib, torch, disc, _lib.DFT_FORWARD)
+    beam_fft = _dft_kind(lib, torch, d_beam, _lib.DFT_FORWARD)
+    # the product can reach N^2 * N^2: rescale before the fp32 inverse pass
+    peak = float(torch.view_as_real(disc_fft).abs().max())
+    peak = peak if peak > 0 else 1.0
+    conv = torch.empty_like(beam_fft)
+    disc_fft /= peak
+    _lib.check(lib.sosat_cmul(ctypes.c_void_p(beam_fft.data_ptr()),
+                              ctypes.c_void_p(disc_fft.data_ptr()), n * n,
+                              ctypes.c_void_p(conv.data_ptr()), _stream(torch)))
+    final = _dft_kind(lib, torch, conv, _lib.DFT_INVERSE)
+    return x, y, final.cpu().numpy().astype(np.complex128) * (scale * peak)
 
 
 def far_field(b, dx_cm=None, lam_m=None, *, device: bool = False):

@@ -198,3 +198,70 @@ def test_pipeline_binned_near_field_to_far_field(mods):
         bref = np.where(cnt > 0, (re + 1j * im) / cnt, 0) * rot
     Bref = np.fft.fftshift(np.fft.fft2(np.fft.fftshift(bref)))
     assert _rel_peak(B, Bref) < FF_TOL
+
+
+def test_b2a_matches_reference_golden(mods):
+    """Row f4: b2a (opt_analyze.py:208-217, unshifted-input quirk kept) against the reference's
+    own outputs, odd and even N, N not a tile multiple."""
+    g = golden("b2a_convolve_small.npz")
+    for n in (16, 65, 96, 129):
+        af, ap = mods["oa"].b2a(g[f"b2a_amp_{n}"], g[f"b2a_phi_{n}"])
+        ref = g[f"b2a_field_{n}"]
+        assert af.shape == (n, n) and af.dtype == np.complex128 and ap.dtype == np.float64
+        assert _rel_peak(af, ref) < FF_TOL
+        assert np.abs(ap - np.arctan2(af.imag, af.real)).max() < 1e-12
+
+
+def test_a2b_then_b2a_round_trip(mods):
+    """Size-independent property at 1024^2: b2a(a2b(x)) returns the aperture, up to the
+    reference's own shift conventions (a2b shifts its input, b2a does not)."""
+    n = 1024
+    x = (np.arange(n) - n // 2) * 0.25
+    X, Y = np.meshgrid(x, x)
+    R = np.hypot(X, Y)
+    amp = np.exp(-R ** 2 / (2 * 9.0 ** 2)) * (R < 20)
+    ph = np.rad2deg(0.3 * np.cos(X / 3) + 0.05 * (R / 20) ** 4)
+    oa = mods["oa"]
+    bc, bph = oa.a2b(amp, ph)
+    af, _ = oa.b2a(np.abs(bc), np.rad2deg(bph))
+    want = np.fft.fftshift(np.fft.ifft2(np.fft.fftshift(np.fft.fft2(np.fft.fftshift(
+        amp * np.exp(1j * np.deg2rad(ph)))))))
+    assert _rel_peak(af, want) < 2 * FF_TOL
+
+
+@pytest.mark.parametrize("n,a1,a2", [(64, 2.0, 3.0), (64, 3.5, 1.5), (64, 2.0, 2.0),
+                                      (101, 2.0, 3.0), (101, 3.5, 1.5), (101, 2.0, 2.0)])
+def test_beam_convolve_matches_reference_golden(mods, n, a1, a2):
+    """Row f3: beam_convolve (opt_analyze.py:60-88) against the reference's own outputs."""
+    g = golden("b2a_convolve_small.npz")
+    X, Y, beam = g[f"conv_x_{n}"], g[f"conv_y_{n}"], g[f"conv_beam_{n}"]
+    xo, yo, bf = mods["oa"].beam_convolve(X, Y, beam, a1, a2, 0)
+    assert xo is X and yo is Y and bf.dtype == np.complex128
+    assert _rel_peak(bf, g[f"conv_{n}_{a1}_{a2}"]) < FF_TOL
+
+
+def test_beam_convolve_1024_against_oracle(mods):
+    n = 1024
+    x = (np.arange(n) - n // 2) * 0.05
+    X, Y = np.meshgrid(x, x)
+    R = np.hypot(X, Y)
+    beam = 3e-3 * np.exp(-R ** 2 / (2 * 4.0 ** 2)) * np.exp(1j * 0.5 * np.sin(X / 2))
+    _, _, bf = mods["oa"].beam_convolve(X, Y, beam, 1.2, 2.0, 0)
+    _, _, ref = mods["oracle"].beam_convolve(X, Y, beam, 1.2, 2.0, 0)
+    assert _rel_peak(bf, ref) < FF_TOL
+
+
+def test_transform_kind_argument_errors(mods):
+    torch, lib = mods["torch"], mods["lib"]
+    L = lib.load()
+    n = 8
+    b = torch.zeros((n, n), dtype=torch.complex64, device="cuda")
+    ws = torch.empty(int(L.sosat_dft2_workspace_bytes(n)), dtype=torch.uint8, device="cuda")
+    rc = L.sosat_dft2_gemm_kind(ctypes.c_void_p(b.data_ptr()), n, ctypes.c_void_p(b.data_ptr()), 7,
+                                ctypes.c_void_p(ws.data_ptr()), ws.numel(), None)
+    assert rc == -1 and b"kind" in L.sosat_last_error()
+    L.sosat_dft2_forget(ctypes.c_void_p(ws.data_ptr()))
+    with pytest.raises(ValueError):
+        mods["oa"].beam_convolve(np.zeros((4, 4)), np.zeros((4, 4)), np.zeros((4, 5)), 1, 2, 0)
+    with pytest.raises(ValueError):
+        mods["oa"].b2a(np.zeros((4, 5)), np.zeros((4, 5)))
