@@ -76,7 +76,7 @@ def stage_trace():
     t.n_scan = 8192
     spec = [(t.k, t.th_fwhp_x, t.th_fwhp_y)]
     n = t.n_scan ** 2
-    for minb in (2, 3, 4):
+    for minb in (3, 4):
         os.environ["SOSAT_TRACE_MINB"] = str(minb)
         for var in (0, 5, 2, 6):
             os.environ["SOSAT_TRACE_VARIANT"] = str(var)

@@ -14,6 +14,9 @@ namespace sosat {
 
 __constant__ GeomC g_geom;
 static bool g_geom_set[64] = {false};
+// a near-parabolic surface on this device's geometry: use the kernels that keep the
+// u c'/(1+s) form of the conic sag (trace_device.cuh)
+static bool g_geom_generic[64] = {false};
 
 static constexpr double kHalfPi = 1.5707963267948966;
 static constexpr double kFourLn2 = 2.772588722239781;  // (1/2) / (1/sqrt(8 ln 2))^2
@@ -63,7 +66,7 @@ struct RowsParams {
 };
 
 // ---- K1a: reference table out[17][n] ----------------------------------------------------
-template <int N32, int N64>
+template <int N32, int N64, bool GENERIC>
 __global__ void __launch_bounds__(256)
 trace_rows_kernel(RowsParams p, double *__restrict__ out, double *__restrict__ stats) {
     const long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -82,7 +85,7 @@ trace_rows_kernel(RowsParams p, double *__restrict__ out, double *__restrict__ s
         const double d0x = sth * cph, d0y = sth * sph, d0z = cth;
         RayResult r;
         unsigned n_slow = 0;
-        trace_ray<N32, N64>(g_geom, p.rx[0], p.rx[1], p.rx[2], d0x, d0y, d0z, r, n_slow);
+        trace_ray<N32, N64, GENERIC>(g_geom, p.rx[0], p.rx[1], p.rx[2], d0x, d0y, d0z, r, n_slow);
         double row[11];
         if (r.flags & RAY_CLIPPED_L3) {
 #pragma unroll
@@ -139,7 +142,7 @@ struct BinParams {
     long long n_tiles;
 };
 
-template <int N32, int N64, int MINB>
+template <int N32, int N64, int MINB, bool GENERIC>
 __global__ void __launch_bounds__(256, MINB)
 trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict__ re,
                  float *__restrict__ im, float *__restrict__ cnt, double *__restrict__ stats) {
@@ -222,7 +225,8 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
             const double sth = s_sin[0][lth], cth = s_cos[0][lth];
             const double sph = s_sin[1][lph], cph = s_cos[1][lph];
             const double *rx = d_rx + 3 * irx;
-            trace_ray<N32, N64>(g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph, cth, r, n_slow);
+            trace_ray<N32, N64, GENERIC>(g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph, cth, r,
+                                         n_slow);
         }
         if (!live) n_slow = 0;
         const bool valid = live && r.valid;
@@ -426,6 +430,7 @@ extern "C" int sosat_set_geometry(const sosat_geom_t *h, void *stream) {
     if (int rc = current_device(&dev)) return rc;
     GeomC g;
     memset(&g, 0, sizeof g);
+    bool generic = false;
     for (int i = 0; i < SOSAT_NUM_SURFACES; ++i) {
         const sosat_surface_t &s = h->surf[i];
         SOSAT_REQUIRE(s.n_in > 0 && s.n_out > 0, "surface %d: refractive index <= 0", i);
@@ -444,6 +449,10 @@ extern "C" int sosat_set_geometry(const sosat_geom_t *h, void *stream) {
         c.n_in = s.n_in;
         c.t_lo = s.t_lo;
         c.t_hi = s.t_hi;
+        c.omm2 = 1.0 - c.mu2;
+        c.cK = c.Kp != 0.0 ? c.cp / c.Kp : 0.0;
+        c.refine = fabs(c.cK) > 300.0;
+        if (c.Kp == 0.0 ? c.cp != 0.0 : !(fabs(c.cK) <= 1e6)) generic = true;
         SurfF &f = g.f[i];
         f.Kp = (float)c.Kp; f.cp = (float)c.cp; f.a1p = (float)c.a1p; f.a2p = (float)c.a2p;
         f.a3p = (float)c.a3p; f.a1p2 = (float)c.a1p2; f.a2p4 = (float)c.a2p4;
@@ -460,14 +469,20 @@ extern "C" int sosat_set_geometry(const sosat_geom_t *h, void *stream) {
     SOSAT_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
     g_host_geom[dev] = *h;
     g_geom_set[dev] = true;
+    const char *force = getenv("SOSAT_TRACE_GENERIC");  // testing hook: exercise the generic kernels
+    g_geom_generic[dev] = generic || (force && atoi(force) != 0);
     return SOSAT_OK;
 }
 
 template <int N32, int N64>
-static void launch_rows(const RowsParams &p, double *out, double *stats, cudaStream_t st) {
+static void launch_rows(bool generic, const RowsParams &p, double *out, double *stats,
+                        cudaStream_t st) {
     const int threads = 256;
     const long long blocks = (p.n + threads - 1) / threads;
-    trace_rows_kernel<N32, N64><<<(unsigned)blocks, threads, 0, st>>>(p, out, stats);
+    if (generic)
+        trace_rows_kernel<N32, N64, true><<<(unsigned)blocks, threads, 0, st>>>(p, out, stats);
+    else
+        trace_rows_kernel<N32, N64, false><<<(unsigned)blocks, threads, 0, st>>>(p, out, stats);
 }
 
 extern "C" int sosat_trace_rays(const double *h_rx, const sosat_freq_t *h_freq, int n_scan,
@@ -494,11 +509,12 @@ extern "C" int sosat_trace_rays(const double *h_rx, const sosat_freq_t *h_freq, 
     if (p.n == 0) return SOSAT_OK;
     SOSAT_REQUIRE((p.n + 255) / 256 < 2147483647LL, "too many rays for one launch");
     cudaStream_t st = (cudaStream_t)stream;
+    const bool generic = g_geom_generic[dev];
     switch (trace_variant()) {
-        case 0: launch_rows<0, 5>(p, d_out, d_stats, st); break;
-        case 2: launch_rows<3, 2>(p, d_out, d_stats, st); break;
-        case 5: launch_rows<0, 4>(p, d_out, d_stats, st); break;
-        default: launch_rows<2, 2>(p, d_out, d_stats, st); break;
+        case 0: launch_rows<0, 5>(generic, p, d_out, d_stats, st); break;
+        case 2: launch_rows<3, 2>(generic, p, d_out, d_stats, st); break;
+        case 5: launch_rows<0, 4>(generic, p, d_out, d_stats, st); break;
+        default: launch_rows<2, 2>(generic, p, d_out, d_stats, st); break;
     }
     SOSAT_CUDA_OK(cudaGetLastError());
     return SOSAT_OK;
@@ -537,22 +553,24 @@ extern "C" int sosat_rx_to_lyot_host(const sosat_geom_t *h_geom, const double *h
 }
 
 // Launch the persistent binning kernel with grid = SMs x resident CTAs per SM.
-template <int N32, int N64, int MINB>
+template <int N32, int N64, int MINB, bool GENERIC>
 static void launch_bin(const BinParams &p, const double *rx, float *re, float *im, float *cnt,
                        double *stats, cudaStream_t st) {
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, trace_bin_kernel<N32, N64, MINB>, 256, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(
+        &occ, trace_bin_kernel<N32, N64, MINB, GENERIC>, 256, 0);
     const long long want = (long long)num_sms() * (occ > 0 ? occ : 1);
     const int blocks = (int)(p.n_tiles < want ? p.n_tiles : want);
-    trace_bin_kernel<N32, N64, MINB><<<blocks, 256, 0, st>>>(p, rx, re, im, cnt, stats);
+    trace_bin_kernel<N32, N64, MINB, GENERIC><<<blocks, 256, 0, st>>>(p, rx, re, im, cnt, stats);
 }
 
 template <int N32, int N64>
-static void launch_bin_minb(int minb, const BinParams &p, const double *rx, float *re, float *im,
-                            float *cnt, double *stats, cudaStream_t st) {
+static void launch_bin_minb(bool generic, int minb, const BinParams &p, const double *rx,
+                            float *re, float *im, float *cnt, double *stats, cudaStream_t st) {
+    if (generic) return launch_bin<N32, N64, 4, true>(p, rx, re, im, cnt, stats, st);
     switch (minb) {
-        case 3: launch_bin<N32, N64, 3>(p, rx, re, im, cnt, stats, st); break;
-        default: launch_bin<N32, N64, 4>(p, rx, re, im, cnt, stats, st); break;
+        case 3: launch_bin<N32, N64, 3, false>(p, rx, re, im, cnt, stats, st); break;
+        default: launch_bin<N32, N64, 4, false>(p, rx, re, im, cnt, stats, st); break;
     }
 }
 
@@ -611,11 +629,12 @@ extern "C" int sosat_trace_bin(const double *d_rx, int n_rx, const sosat_freq_t 
     SOSAT_REQUIRE(p.n_tiles < 2147483647LL, "too many ray tiles for one launch (%lld): split the "
                   "receiver list or the row range", p.n_tiles);
     const int minb = trace_minb();
+    const bool generic = g_geom_generic[dev];
     switch (trace_variant()) {
-        case 0: launch_bin_minb<0, 5>(minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
-        case 2: launch_bin_minb<3, 2>(minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
-        case 5: launch_bin_minb<0, 4>(minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
-        default: launch_bin_minb<2, 2>(minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
+        case 0: launch_bin_minb<0, 5>(generic, minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
+        case 2: launch_bin_minb<3, 2>(generic, minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
+        case 5: launch_bin_minb<0, 4>(generic, minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
+        default: launch_bin_minb<2, 2>(generic, minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
     }
     SOSAT_CUDA_OK(cudaGetLastError());
     // bf lives on this stack frame: the async symbol copy from pageable memory is staged

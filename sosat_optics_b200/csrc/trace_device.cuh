@@ -8,7 +8,13 @@
 // surface frame is x_l = x, y_l = z, z_l = -(y - y0) (ot_geo.py:449-458), so
 //     f(t) = (y0 - o_y) - d_y t - S(u),   u = X^2 + Z^2 [mm^2],  X = o_x + d_x t, Z = o_z + d_z t
 //     S(u) = u [ c'/(1+s) + a1' + a2' u + a3' u^2 ],  s = sqrt(1 - K' u)
-// with the cm->mm factors of ot_geo.py:54-55,69 folded into the primed constants.
+// with the cm->mm factors of ot_geo.py:54-55,69 folded into the primed constants.  Two exact
+// identities remove the reciprocal from the evaluation (1 - s^2 = K'u):
+//     u c'/(1+s) = (c'/K') (1 - s)              conic sag without a division
+//     dS/du * 2  = c'/s + 2 a1' + 4 a2' u + 6 a3' u^2    (the textbook c r / sqrt(1 - K r^2))
+// The first needs |c'/K'| = 10/|(1+k) c| mm to stay moderate (the rounding of s is amplified by
+// it); a near-parabolic surface (|c'/K'| > 1e6 mm, or K' = 0) selects the GENERIC kernels, which
+// keep the u c'/(1+s) form.
 // A ray whose Newton solve is not clearly converged, or that grazes the conic-domain edge
 // of lens 1b, is re-traced with a bracketed Brent solve that restates the reference's
 // brentq call (same brackets, same tolerances), so such rays get the reference's answer.
@@ -35,6 +41,10 @@ struct SurfC {
     double mu2;   // mu^2
     double n_in;  // OPL weight of the segment arriving at this surface
     double t_lo, t_hi;
+    double cK;    // c'/K' = 10 / ((1+k) c) [mm]: conic sag = cK (1 - s); 0 when K' = 0
+    double omm2;  // 1 - mu^2
+    int refine;   // |cK| > 300 mm: s needs the fully refined rsqrt in the division-free form
+    int pad_;
 };
 
 struct SurfF {
@@ -139,6 +149,7 @@ __device__ __forceinline__ float rsqrt_f32(float x) {
 // ---- surface function in the tele frame -------------------------------------------------
 // Returns f and df/dt at parameter t, plus X, Z of the point and G = (dS/dX)/X = (dS/dZ)/Z,
 // the slope factor of d_z?? (ot_geo.py:108-115): the surface gradient is (G X, G Z).
+template <bool GENERIC>
 __device__ __forceinline__ void surf_eval(const SurfC &S, double Px, double Pz, double dx,
                                           double dy, double dz, double y0Py, double t,
                                           double &f, double &fp, double &X, double &Z,
@@ -147,15 +158,22 @@ __device__ __forceinline__ void surf_eval(const SurfC &S, double Px, double Pz, 
     Z = fma(dz, t, Pz);
     const double u = fma(X, X, Z * Z);
     w = fma(-S.Kp, u, 1.0);
-    const double rs = SOSAT_RSQRT_EVAL(w);
-    const double s = w * rs;
-    const double inv = rcp_full(1.0 + s);
+    double rs = SOSAT_RSQRT_EVAL(w);
     const double poly = fma(fma(S.a3p, u, S.a2p), u, S.a1p);
-    const double q = S.cp * inv;
-    f = fma(-dy, t, y0Py) - u * (q + poly);
-    const double h = (1.0 - w) * inv * rs;  // K'u / (s (1+s))
-    G = fma(u, fma(S.a3p6, u, S.a2p4), S.a1p2) + q * (2.0 + h);
-    fp = -dy - G * fma(X, dx, Z * dz);
+    double conic;
+    if (GENERIC) {
+        const double s = w * rs;
+        conic = u * (S.cp * rcp_full(1.0 + s));
+    } else {
+        if (S.refine) {  // warp-uniform (constant bank): one more Newton-Raphson step on rs
+            const double a = w * rs;
+            rs = fma(0.5 * rs, fma(-a, rs, 1.0), rs);
+        }
+        conic = S.cK * fma(-w, rs, 1.0);  // (c'/K') (1 - s)
+    }
+    f = fma(-dy, t, y0Py) - fma(u, poly, conic);
+    G = fma(S.cp, rs, fma(u, fma(S.a3p6, u, S.a2p4), S.a1p2));  // c'/s + d(poly u)/du * 2
+    fp = fma(-G, fma(X, dx, Z * dz), -dy);
 }
 
 __device__ __forceinline__ void surf_eval_f32(const SurfF &S, float Px, float Pz, float dx,
@@ -166,42 +184,49 @@ __device__ __forceinline__ void surf_eval_f32(const SurfF &S, float Px, float Pz
     const float u = fmaf(X, X, Z * Z);
     const float w = fmaf(-S.Kp, u, 1.0f);
     const float rs = rsqrt_f32(w);
-    const float s = w * rs;
-    const float inv = rcp_f32(1.0f + s);
+    const float q = S.cp * rcp_f32(fmaf(w, rs, 1.0f));  // the division form: no cancellation
     const float poly = fmaf(fmaf(S.a3p, u, S.a2p), u, S.a1p);
-    const float q = S.cp * inv;
     f = fmaf(-dy, t, y0Py) - u * (q + poly);
-    const float h = (1.0f - w) * inv * rs;
-    const float G = fmaf(u, fmaf(S.a3p6, u, S.a2p4), S.a1p2) + q * (2.0f + h);
-    fp = -dy - G * fmaf(X, dx, Z * dz);
+    const float G = fmaf(S.cp, rs, fmaf(u, fmaf(S.a3p6, u, S.a2p4), S.a1p2));
+    fp = fmaf(-G, fmaf(X, dx, Z * dz), -dy);
 }
 
 // Vector Snell refraction, ray_trace.py:27-35 with N x (-N x s) = s - N (N.s) and
 // |N x s|^2 = 1 - (N.s)^2:  s2 = mu s + (mu cos_i - sqrt(1 - mu^2 (1 - cos_i^2))) N.
-// A negative radicand (total internal reflection) gives NaN, as in the reference.
+// Written on the UNNORMALISED normal n = (-gx, -1, -gz), |n|^2 = L2, m = -n.s = |n| cos_i:
+//     s2 = mu s + n (mu m - sqrt((1 - mu^2) L2 + mu^2 m^2)) / L2
+// which needs one reciprocal and one square root instead of two reciprocal square roots and
+// drops the three multiplications that normalise N.  A negative radicand (total internal
+// reflection) gives NaN, as in the reference.  (gx, gz, L2) are returned so that the unit
+// normal of the last surface (out rows 5-7) can be formed once at the end.
 __device__ __forceinline__ void refract(const SurfC &S, double X, double Z, double G,
-                                        double &dx, double &dy, double &dz, double &nx,
-                                        double &ny, double &nz) {
-    const double gx = G * X, gz = G * Z;
-    const double rn = SOSAT_RSQRT_SNELL(fma(gx, gx, fma(gz, gz, 1.0)));
-    // local normal (-gx, -gy, 1)/|.| maps to tele (-gx, -1, -gz)/|.| (ray_trace.py:1162-1166)
+                                        double &dx, double &dy, double &dz, double &gx,
+                                        double &gz, double &L2) {
+    gx = G * X;
+    gz = G * Z;
+    L2 = fma(gx, gx, fma(gz, gz, 1.0));
+    const double m = fma(gx, dx, fma(gz, dz, dy));
+    const double D = fma(S.mu2, m * m, S.omm2 * L2);
+    const double sqrtD = D * SOSAT_RSQRT_SNELL(D);
+    const double beta = fma(S.mu, m, -sqrtD) * rcp_full(L2);
+    dx = fma(S.mu, dx, -(gx * beta));
+    dy = fma(S.mu, dy, -beta);
+    dz = fma(S.mu, dz, -(gz * beta));
+}
+// local normal (-gx, -gy, 1)/|.| maps to tele (-gx, -1, -gz)/|.| (ray_trace.py:1162-1166)
+__device__ __forceinline__ void unit_normal(double gx, double gz, double L2, double &nx,
+                                            double &ny, double &nz) {
+    const double rn = rsqrt_full(L2);
     nx = -gx * rn;
     ny = -rn;
     nz = -gz * rn;
-    const double ci = -fma(nx, dx, fma(ny, dy, nz * dz));
-    const double rad2 = fma(S.mu2, fma(ci, ci, -1.0), 1.0);
-    const double rad = rad2 * SOSAT_RSQRT_SNELL(rad2);
-    const double kf = fma(S.mu, ci, -rad);
-    dx = fma(S.mu, dx, kf * nx);
-    dy = fma(S.mu, dy, kf * ny);
-    dz = fma(S.mu, dz, kf * nz);
 }
 
 // Stop / source planes, OPL total and validity: ray_trace.py:1510-1526, 1565-1580.
 __device__ __forceinline__ void finish_ray(const GeomC &g, double Px, double Py, double Pz,
                                            double dx, double dy, double dz, double opl,
                                            double r2a_sq, RayResult &r) {
-    const double idy = 1.0 / dy;
+    const double idy = rcp_full(dy);
     const double t1 = fabs((g.y_lyot - Py) * idy);
     const double Lx = fma(dx, t1, Px), Ly = fma(dy, t1, Py), Lz = fma(dz, t1, Pz);
     const double t2 = fabs((g.y_source - Ly) * idy);
@@ -227,23 +252,23 @@ __device__ __forceinline__ void finish_ray(const GeomC &g, double Px, double Py,
 #endif
 
 // Fast path.  N32 Newton steps in fp32 from the vertex-plane guess, then N64 in fp64.
-template <int N32, int N64>
+template <int N32, int N64, bool GENERIC>
 __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, double Py,
                                                  double Pz, double dx, double dy, double dz,
                                                  RayResult &r) {
     double opl = 0.0, r2a_sq = 0.0;
-    double nx = 0.0, ny = 0.0, nz = 0.0;
+    double gx = 0.0, gz = 0.0, L2 = 1.0;
     unsigned flags = 0;
     SOSAT_SURFACE_LOOP_PRAGMA
     for (int si = 0; si < SOSAT_NUM_SURFACES; ++si) {
         const SurfC &S = g.s[si];
         const double y0Py = S.y0 - Py;
-        double t = y0Py * rcp_half(dy);  // vertex-plane guess
+        double t;
         if (N32 > 0) {
             const SurfF &F = g.f[si];
             const float fPx = (float)Px, fPz = (float)Pz, fdx = (float)dx, fdy = (float)dy,
                         fdz = (float)dz, fy0 = (float)y0Py;
-            float tf = (float)t;
+            float tf = fy0 * rcp_f32(fdy);  // vertex-plane guess
 #pragma unroll
             for (int it = 0; it < N32; ++it) {
                 float f, fp;
@@ -251,12 +276,14 @@ __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, doub
                 tf = fmaf(-f, rcp_f32(fp), tf);
             }
             t = (double)tf;
+        } else {
+            t = y0Py * rcp_half(dy);  // vertex-plane guess
         }
         double X, Z, G, w, step = 0.0;
 #pragma unroll
         for (int it = 0; it < N64; ++it) {
             double f, fp;
-            surf_eval(S, Px, Pz, dx, dy, dz, y0Py, t, f, fp, X, Z, G, w);
+            surf_eval<GENERIC>(S, Px, Pz, dx, dy, dz, y0Py, t, f, fp, X, Z, G, w);
             step = f * rcp_seed(fp);
             t -= step;
         }
@@ -266,7 +293,7 @@ __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, doub
         for (int extra = 0; extra < SOSAT_NEWTON_EXTRA &&
                             __any_sync(0xffffffffu, fabs(step) > SOSAT_NEWTON_REFINE); ++extra) {
             double f, fp;
-            surf_eval(S, Px, Pz, dx, dy, dz, y0Py, t, f, fp, X, Z, G, w);
+            surf_eval<GENERIC>(S, Px, Pz, dx, dy, dz, y0Py, t, f, fp, X, Z, G, w);
             step = f * rcp_seed(fp);
             t -= step;
         }
@@ -281,11 +308,9 @@ __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, doub
         if (si == 0 && fma(Px, Px, Pz * Pz) >= g.clip_l3_sq) flags |= RAY_CLIPPED_L3;
         if (si == 3) r2a_sq = fma(Px, Px, Pz * Pz);
         opl = fma(t, S.n_in, opl);  // dist_* = |hit - previous| = t for unit d
-        refract(S, X, Z, G, dx, dy, dz, nx, ny, nz);
+        refract(S, X, Z, G, dx, dy, dz, gx, gz, L2);
     }
-    r.nx = nx;
-    r.ny = ny;
-    r.nz = nz;
+    unit_normal(gx, gz, L2, r.nx, r.ny, r.nz);
     finish_ray(g, Px, Py, Pz, dx, dy, dz, opl, r2a_sq, r);
     r.flags = flags;
     if (flags & RAY_CLIPPED_L3) {
@@ -375,7 +400,7 @@ __device__ __noinline__ void trace_ray_bracketed(const GeomC &g, double Px, doub
                                                  double Pz, double dx, double dy, double dz,
                                                  RayResult &r) {
     double opl = 0.0, r2a_sq = 0.0;
-    double nx = 0.0, ny = 0.0, nz = 0.0;
+    double gx = 0.0, gz = 0.0, L2 = 1.0;
     unsigned flags = 0;
 #pragma unroll 1
     for (int si = 0; si < SOSAT_NUM_SURFACES; ++si) {
@@ -383,7 +408,7 @@ __device__ __noinline__ void trace_ray_bracketed(const GeomC &g, double Px, doub
         const double y0Py = S.y0 - Py;
         const double t = brent_solve(S, Px, Pz, dx, dy, dz, y0Py, flags);
         double f, fp, X, Z, G, w;
-        surf_eval(S, Px, Pz, dx, dy, dz, y0Py, t, f, fp, X, Z, G, w);  // slope at the hit
+        surf_eval<true>(S, Px, Pz, dx, dy, dz, y0Py, t, f, fp, X, Z, G, w);  // slope at the hit
         Px = fma(dx, t, Px);
         Py = fma(dy, t, Py);
         Pz = fma(dz, t, Pz);
@@ -394,22 +419,20 @@ __device__ __noinline__ void trace_ray_bracketed(const GeomC &g, double Px, doub
         }
         if (si == 3) r2a_sq = fma(Px, Px, Pz * Pz);
         opl = fma(t, S.n_in, opl);
-        refract(S, X, Z, G, dx, dy, dz, nx, ny, nz);
+        refract(S, X, Z, G, dx, dy, dz, gx, gz, L2);
     }
-    r.nx = nx;
-    r.ny = ny;
-    r.nz = nz;
+    unit_normal(gx, gz, L2, r.nx, r.ny, r.nz);
     r.flags = flags;
     finish_ray(g, Px, Py, Pz, dx, dy, dz, opl, r2a_sq, r);
 }
 
 // Fast path, then the slow path for rays that came out valid but were flagged.  Must be called
 // by all 32 lanes of a warp (the fast path votes with __any_sync).
-template <int N32, int N64>
+template <int N32, int N64, bool GENERIC>
 __device__ __forceinline__ void trace_ray(const GeomC &g, double Px, double Py, double Pz,
                                           double dx, double dy, double dz, RayResult &r,
                                           unsigned &n_slow) {
-    trace_ray_newton<N32, N64>(g, Px, Py, Pz, dx, dy, dz, r);
+    trace_ray_newton<N32, N64, GENERIC>(g, Px, Py, Pz, dx, dy, dz, r);
     if (r.valid && (r.flags & RAY_FLAGGED)) {
         trace_ray_bracketed(g, Px, Py, Pz, dx, dy, dz, r);
         r.flags |= RAY_FLAGGED;
