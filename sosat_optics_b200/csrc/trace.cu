@@ -457,6 +457,7 @@ extern "C" int sosat_set_geometry(const sosat_geom_t *h, void *stream) {
         f.Kp = (float)c.Kp; f.cp = (float)c.cp; f.a1p = (float)c.a1p; f.a2p = (float)c.a2p;
         f.a3p = (float)c.a3p; f.a1p2 = (float)c.a1p2; f.a2p4 = (float)c.a2p4;
         f.a3p6 = (float)c.a3p6;
+        f.cK = (float)c.cK;
     }
     g.y_lyot = h->y_lyot;
     g.y_source = h->y_source;

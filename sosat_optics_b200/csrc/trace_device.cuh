@@ -48,7 +48,7 @@ struct SurfC {
 };
 
 struct SurfF {
-    float Kp, cp, a1p, a2p, a3p, a1p2, a2p4, a3p6;
+    float Kp, cp, a1p, a2p, a3p, a1p2, a2p4, a3p6, cK;
 };
 
 struct GeomC {
@@ -149,9 +149,12 @@ __device__ __forceinline__ float rsqrt_f32(float x) {
 // ---- surface function in the tele frame -------------------------------------------------
 // Returns f and df/dt at parameter t, plus X, Z of the point and G = (dS/dX)/X = (dS/dZ)/Z,
 // the slope factor of d_z?? (ot_geo.py:108-115): the surface gradient is (G X, G Z).
+// y0PyK = y0Py - cK in the division-free form (GENERIC: y0PyK = y0Py): the conic term is then
+// f = [y0PyK - d_y t - u poly] + (cK w) rs, i.e. one DFMA after the rsqrt chain ends, with the
+// bracket and cK w evaluated while the MUFU seed is in flight.
 template <bool GENERIC>
 __device__ __forceinline__ void surf_eval(const SurfC &S, double Px, double Pz, double dx,
-                                          double dy, double dz, double y0Py, double t,
+                                          double dy, double dz, double y0PyK, double t,
                                           double &f, double &fp, double &X, double &Z,
                                           double &G, double &w) {
     X = fma(dx, t, Px);
@@ -160,33 +163,39 @@ __device__ __forceinline__ void surf_eval(const SurfC &S, double Px, double Pz, 
     w = fma(-S.Kp, u, 1.0);
     double rs = SOSAT_RSQRT_EVAL(w);
     const double poly = fma(fma(S.a3p, u, S.a2p), u, S.a1p);
-    double conic;
+    const double base = fma(-u, poly, fma(-dy, t, y0PyK));
     if (GENERIC) {
         const double s = w * rs;
-        conic = u * (S.cp * rcp_full(1.0 + s));
+        f = fma(-u, S.cp * rcp_full(1.0 + s), base);
     } else {
+        const double B = S.cK * w;
         if (S.refine) {  // warp-uniform (constant bank): one more Newton-Raphson step on rs
             const double a = w * rs;
             rs = fma(0.5 * rs, fma(-a, rs, 1.0), rs);
         }
-        conic = S.cK * fma(-w, rs, 1.0);  // (c'/K') (1 - s)
+        f = fma(B, rs, base);  // ... - cK (1 - s)
     }
-    f = fma(-dy, t, y0Py) - fma(u, poly, conic);
     G = fma(S.cp, rs, fma(u, fma(S.a3p6, u, S.a2p4), S.a1p2));  // c'/s + d(poly u)/du * 2
     fp = fma(-G, fma(X, dx, Z * dz), -dy);
 }
 
+// fp32 pre-iterations: same two forms (REFINE surfaces keep the division, where the (1 - s)
+// cancellation would cost |cK| * 2^-22 mm).  y0PyK = y0Py - cK for the division-free form.
+template <bool DIVFREE>
 __device__ __forceinline__ void surf_eval_f32(const SurfF &S, float Px, float Pz, float dx,
-                                              float dy, float dz, float y0Py, float t,
+                                              float dy, float dz, float y0PyK, float t,
                                               float &f, float &fp) {
     const float X = fmaf(dx, t, Px);
     const float Z = fmaf(dz, t, Pz);
     const float u = fmaf(X, X, Z * Z);
     const float w = fmaf(-S.Kp, u, 1.0f);
     const float rs = rsqrt_f32(w);
-    const float q = S.cp * rcp_f32(fmaf(w, rs, 1.0f));  // the division form: no cancellation
     const float poly = fmaf(fmaf(S.a3p, u, S.a2p), u, S.a1p);
-    f = fmaf(-dy, t, y0Py) - u * (q + poly);
+    const float base = fmaf(-u, poly, fmaf(-dy, t, y0PyK));
+    if (DIVFREE)
+        f = fmaf(S.cK * w, rs, base);
+    else
+        f = fmaf(-u, S.cp * rcp_f32(fmaf(w, rs, 1.0f)), base);
     const float G = fmaf(S.cp, rs, fmaf(u, fmaf(S.a3p6, u, S.a2p4), S.a1p2));
     fp = fmaf(-G, fmaf(X, dx, Z * dz), -dy);
 }
@@ -269,21 +278,32 @@ __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, doub
             const float fPx = (float)Px, fPz = (float)Pz, fdx = (float)dx, fdy = (float)dy,
                         fdz = (float)dz, fy0 = (float)y0Py;
             float tf = fy0 * rcp_f32(fdy);  // vertex-plane guess
+            if (!GENERIC && !S.refine) {  // warp-uniform
+                const float fy0K = fy0 - F.cK;
 #pragma unroll
-            for (int it = 0; it < N32; ++it) {
-                float f, fp;
-                surf_eval_f32(F, fPx, fPz, fdx, fdy, fdz, fy0, tf, f, fp);
-                tf = fmaf(-f, rcp_f32(fp), tf);
+                for (int it = 0; it < N32; ++it) {
+                    float f, fp;
+                    surf_eval_f32<true>(F, fPx, fPz, fdx, fdy, fdz, fy0K, tf, f, fp);
+                    tf = fmaf(-f, rcp_f32(fp), tf);
+                }
+            } else {
+#pragma unroll
+                for (int it = 0; it < N32; ++it) {
+                    float f, fp;
+                    surf_eval_f32<false>(F, fPx, fPz, fdx, fdy, fdz, fy0, tf, f, fp);
+                    tf = fmaf(-f, rcp_f32(fp), tf);
+                }
             }
             t = (double)tf;
         } else {
             t = y0Py * rcp_half(dy);  // vertex-plane guess
         }
         double X, Z, G, w, step = 0.0;
+        const double y0PyK = GENERIC ? y0Py : y0Py - S.cK;
 #pragma unroll
         for (int it = 0; it < N64; ++it) {
             double f, fp;
-            surf_eval<GENERIC>(S, Px, Pz, dx, dy, dz, y0Py, t, f, fp, X, Z, G, w);
+            surf_eval<GENERIC>(S, Px, Pz, dx, dy, dz, y0PyK, t, f, fp, X, Z, G, w);
             step = f * rcp_seed(fp);
             t -= step;
         }
@@ -293,7 +313,7 @@ __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, doub
         for (int extra = 0; extra < SOSAT_NEWTON_EXTRA &&
                             __any_sync(0xffffffffu, fabs(step) > SOSAT_NEWTON_REFINE); ++extra) {
             double f, fp;
-            surf_eval<GENERIC>(S, Px, Pz, dx, dy, dz, y0Py, t, f, fp, X, Z, G, w);
+            surf_eval<GENERIC>(S, Px, Pz, dx, dy, dz, y0PyK, t, f, fp, X, Z, G, w);
             step = f * rcp_seed(fp);
             t -= step;
         }
