@@ -123,8 +123,7 @@ trace_rows_kernel(RowsParams p, double *__restrict__ out, double *__restrict__ s
 }
 
 // ---- K1b: fused trace + binning ------------------------------------------------------------
-constexpr int kTile = 16;      // rays per tile edge: a CTA traces a 16 x 16 patch of the launch grid
-constexpr int kMaxGroups = 4;  // distinct bins per warp aggregated by shuffle before atomics
+constexpr int kTile = 16;  // rays per tile edge: a CTA traces a 16 x 16 patch of the launch grid
 
 struct BinFreq {
     float neg_c_fx[SOSAT_MAX_FREQS];  // -4 ln2 / fwhp_x^2
@@ -142,25 +141,37 @@ struct BinParams {
     long long n_tiles;
 };
 
+// Persistent CTAs loop over 16 x 16 patches of the launch grid; a warp owns an 8 (theta) x 4
+// (phi) sub-patch, so its 32 rays land in a handful of neighbouring bins.  Binning is a
+// run-length aggregation along the lane order: every maximal run of consecutive lanes with the
+// same bin is summed into its first lane by a segmented shuffle reduction (5 steps whatever the
+// ray density), and that lane issues one red.global.add.f32 per plane.  Because the optical
+// map (theta, phi) -> (x, z) is smooth, the runs are long: 1-2 per warp at 240 rays/bin
+// (configs[4]), one per row of 8 at 15 rays/bin.  Any key sequence is handled correctly --
+// equal bins that are not adjacent in lane order simply become separate atomics.
 template <int N32, int N64, int MINB, bool GENERIC>
 __global__ void __launch_bounds__(256, MINB)
 trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict__ re,
                  float *__restrict__ im, float *__restrict__ cnt, double *__restrict__ stats) {
-    __shared__ double s_sin[2][kTile], s_cos[2][kTile], s_ang[2][kTile];
-    __shared__ float s_amp[2][SOSAT_MAX_FREQS][kTile];  // [theta|phi][freq][index in tile]
+    __shared__ double s_sin[2][kTile], s_cos[2][kTile];
+    __shared__ float s_amp[SOSAT_MAX_FREQS][2][kTile];  // [freq][theta|phi][index in tile]
+    // Running statistics.  fp64 sums: one shared-memory slot per thread (no conflicts, no
+    // registers held across the tracer).  Counters: warp ballots added by lane 0 to packed
+    // 64-bit shared counters; the rare slow-path events use plain shared atomics.
+    __shared__ double s_sum[4][256];
+    __shared__ unsigned long long s_valid_binned;  // n_valid | n_binned << 32
+    __shared__ unsigned s_rare[2];                 // n_slow, n_bracket_fail
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    // a warp covers 8 (theta) x 4 (phi) neighbouring rays so that they land in 1-2 bins
     const int lth = (lane & 7) + 8 * (warp & 1);
     const int lph = (lane >> 3) + 4 * (warp >> 1);
 
-    // Per-thread running statistics: the four fp64 sums live in shared memory (one slot per
-    // thread, no conflicts) and the four counters in 32-bit registers, which keeps 12 registers
-    // out of the tracer's live range.
-    __shared__ double s_sum[4][256];
-    unsigned n_valid = 0, n_binned = 0, n_slow_acc = 0, n_fail = 0;
 #pragma unroll
     for (int q = 0; q < 4; ++q) s_sum[q][tid] = 0.0;
+    if (tid == 0) {
+        s_valid_binned = 0ull;
+        s_rare[0] = s_rare[1] = 0u;
+    }
     int acc_rx = -1;
     // tile bookkeeping in 32 bits (the host checks n_tiles < 2^31): 64-bit divisions cost
     // ~100 instructions per tile otherwise
@@ -168,19 +179,26 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
     const long long plane = (long long)p.grid_n * p.grid_n;
 
     auto flush_stats = [&](int irx_done) {
+        __syncthreads();  // all counter updates of the finished receiver are in
+        const unsigned long long vb = s_valid_binned;
+        const bool t0 = tid == 0;
         double acc[SOSAT_NUM_STATS];
-        acc[SOSAT_STAT_N_VALID] = (double)n_valid;
+        acc[SOSAT_STAT_N_VALID] = t0 ? (double)(unsigned)(vb & 0xffffffffull) : 0.0;
         acc[SOSAT_STAT_SUM_OPL] = s_sum[0][tid];
         acc[SOSAT_STAT_SUM_DX] = s_sum[1][tid];
         acc[SOSAT_STAT_SUM_DY] = s_sum[2][tid];
         acc[SOSAT_STAT_SUM_DZ] = s_sum[3][tid];
-        acc[SOSAT_STAT_N_SLOW] = (double)n_slow_acc;
-        acc[SOSAT_STAT_N_BRACKET_FAIL] = (double)n_fail;
-        acc[SOSAT_STAT_N_BINNED] = (double)n_binned;
+        acc[SOSAT_STAT_N_SLOW] = t0 ? (double)s_rare[0] : 0.0;
+        acc[SOSAT_STAT_N_BRACKET_FAIL] = t0 ? (double)s_rare[1] : 0.0;
+        acc[SOSAT_STAT_N_BINNED] = t0 ? (double)(unsigned)(vb >> 32) : 0.0;
         if (stats) block_accumulate<SOSAT_NUM_STATS>(acc, stats + (long long)irx_done * SOSAT_NUM_STATS);
-        n_valid = n_binned = n_slow_acc = n_fail = 0;
+        __syncthreads();
 #pragma unroll
         for (int q = 0; q < 4; ++q) s_sum[q][tid] = 0.0;
+        if (t0) {
+            s_valid_binned = 0ull;
+            s_rare[0] = s_rare[1] = 0u;
+        }
     };
 
     const unsigned n_tiles = (unsigned)p.n_tiles;
@@ -194,90 +212,87 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
         }
         __syncthreads();  // previous tile done with the tables
         if (tid < 2 * kTile) {
-            const int which = tid / kTile, l = tid % kTile;  // 0: theta, 1: phi
+            const int which = tid >> 4, l = tid & (kTile - 1);  // 0: theta, 1: phi
             const int idx = which == 0 ? tx * kTile + l : (int)p.row_begin + ty * kTile + l;
             const int ic = idx < p.n_scan ? idx : p.n_scan - 1;
             const double a = linspace_at(p.lin_start, p.lin_stop, p.lin_step, p.n_scan, ic);
-            double s, c;
-            sincos(a, &s, &c);
-            s_sin[which][l] = s;
-            s_cos[which][l] = c;
-            s_ang[which][l] = a - kHalfPi;  // -de_ho (theta) / de_ve (phi), ray_trace.py:1529-1532
-        }
-        __syncthreads();
-        for (int e = tid; e < 2 * kTile * p.n_freq; e += blockDim.x) {
-            const int which = e / (kTile * p.n_freq), rem = e % (kTile * p.n_freq);
-            const int f = rem / kTile, l = rem % kTile;
-            const float ang = (float)s_ang[which][l];
-            const float cf = which == 0 ? g_freq.neg_c_fx[f] : g_freq.neg_c_fy[f];
-            s_amp[which][f][l] = expf(cf * ang * ang);
+            double sn, cs;
+            sincos(a, &sn, &cs);
+            s_sin[which][l] = sn;
+            s_cos[which][l] = cs;
+            const double ang = a - kHalfPi;  // -de_ho (theta) / de_ve (phi), ray_trace.py:1529-1532
+            // separable Gaussian feed taper a = A_theta[i] A_phi[j] (ray_trace.py:1573-1577)
+            const float af = (float)ang, a2 = af * af;
+            for (int f = 0; f < p.n_freq; ++f)
+                s_amp[f][which][l] = expf((which == 0 ? g_freq.neg_c_fx[f] : g_freq.neg_c_fy[f]) * a2);
         }
         __syncthreads();
 
         const int ith = tx * kTile + lth;
         const int iph = ty * kTile + lph;  // relative to row_begin
         const bool live = ith < p.n_scan && iph < p.n_rows;
+        const double *rx = d_rx + 3 * irx;
         RayResult r;
-        unsigned n_slow = 0;
         {
             // lanes past the edge of the launch grid trace the clamped (edge) ray so that whole
             // warps stay converged; their result is dropped
             const double sth = s_sin[0][lth], cth = s_cos[0][lth];
             const double sph = s_sin[1][lph], cph = s_cos[1][lph];
-            const double *rx = d_rx + 3 * irx;
-            trace_ray<N32, N64, GENERIC>(g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph, cth, r,
-                                         n_slow);
+            trace_ray_newton<N32, N64, GENERIC>(g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph,
+                                                cth, r);
         }
-        if (!live) n_slow = 0;
+        if (r.valid && (r.flags & RAY_FLAGGED)) {
+            // rare (< 0.15 % of rays): the reference's bracketed solve.  The launch direction is
+            // re-read here (volatile) instead of being kept live across the fast path, and the
+            // result goes through a local copy so that r itself stays in registers.
+            const double sth = *(volatile double *)&s_sin[0][lth], cth = *(volatile double *)&s_cos[0][lth];
+            const double sph = *(volatile double *)&s_sin[1][lph], cph = *(volatile double *)&s_cos[1][lph];
+            RayResult rs;
+            trace_ray_bracketed(g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph, cth, rs);
+            r.ax = rs.ax; r.az = rs.az; r.opl = rs.opl;
+            r.dx = rs.dx; r.dy = rs.dy; r.dz = rs.dz;
+            r.valid = rs.valid;
+            if (live) {
+                atomicAdd(&s_rare[0], 1u);
+                if (rs.flags & RAY_BRACKET_FAIL) atomicAdd(&s_rare[1], 1u);
+            }
+        }
         const bool valid = live && r.valid;
         int bin = -1;
         if (valid) {
             const int ix = __double2int_rd((r.ax + p.half_extent) * p.inv_cell);
             const int iz = __double2int_rd((r.az + p.half_extent) * p.inv_cell);
-            if (ix >= 0 && ix < p.grid_n && iz >= 0 && iz < p.grid_n) bin = iz * p.grid_n + ix;
-            ++n_valid;
+            if ((unsigned)ix < (unsigned)p.grid_n && (unsigned)iz < (unsigned)p.grid_n)
+                bin = iz * p.grid_n + ix;
             s_sum[0][tid] += r.opl;
             s_sum[1][tid] += r.dx;
             s_sum[2][tid] += r.dy;
             s_sum[3][tid] += r.dz;
-            if (bin >= 0) ++n_binned;
         }
-        n_slow_acc += n_slow;
-        if (live && (r.flags & RAY_BRACKET_FAIL)) ++n_fail;
-        if (re == nullptr) continue;
+        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+        const unsigned bmask = __ballot_sync(0xffffffffu, bin >= 0);
+        if (lane == 0 && vmask)
+            atomicAdd(&s_valid_binned, (unsigned long long)__popc(vmask) |
+                                           ((unsigned long long)__popc(bmask) << 32));
+        if (re == nullptr || bmask == 0u) continue;
 
-        // ---- warp-level aggregation: lanes that share a bin are summed by shuffle, one
-        // atomic per (bin, plane) and warp; lanes beyond kMaxGroups distinct bins go direct.
-        unsigned todo = __ballot_sync(0xffffffffu, bin >= 0);
-        if (todo == 0u) continue;
-        unsigned gmask[kMaxGroups];
-        int gbin[kMaxGroups];
-#pragma unroll
-        for (int gi = 0; gi < kMaxGroups; ++gi) {
-            gmask[gi] = 0u;
-            gbin[gi] = -1;
-            if (todo) {
-                const int leader = __ffs(todo) - 1;
-                const int b = __shfl_sync(0xffffffffu, bin, leader);
-                const unsigned m = __ballot_sync(0xffffffffu, bin == b);
-                gmask[gi] = m;
-                gbin[gi] = b;
-                todo &= ~m;
-            }
-        }
-        const bool direct = (todo >> lane) & 1u;
-        const long long base_cnt = (long long)irx * plane;
-#pragma unroll
-        for (int gi = 0; gi < kMaxGroups; ++gi)
-            if (gmask[gi] && lane == __ffs(gmask[gi]) - 1)
-                atomicAdd(cnt + base_cnt + gbin[gi], (float)__popc(gmask[gi]));
-        if (direct) atomicAdd(cnt + base_cnt + bin, 1.0f);
+        // ---- run-length aggregation along the lane order ------------------------------------
+        const int prev = __shfl_up_sync(0xffffffffu, bin, 1);
+        const bool head = lane == 0 || prev != bin;
+        const unsigned heads = __ballot_sync(0xffffffffu, head);
+        // bit q of m: lane + 1 + q starts a new run; a virtual head sits just past lane 31
+        const unsigned m = ((heads >> lane) >> 1) | (1u << (31 - lane));
+        const int rest = __ffs(m) - 1;  // lanes lane+1 .. lane+rest continue this lane's run
+        const bool flush = head && bin >= 0;
+        if (flush) atomicAdd(cnt + (long long)irx * plane + bin, (float)(rest + 1));
 
         const double dopl = r.opl - p.opl_ref;
-        for (int f = 0; f < p.n_freq; ++f) {
+        float *re_f = re + (long long)irx * p.n_freq * plane;
+        float *im_f = im + (long long)irx * p.n_freq * plane;
+        for (int f = 0; f < p.n_freq; ++f, re_f += plane, im_f += plane) {
             float vre = 0.f, vim = 0.f;
             if (bin >= 0) {
-                const float a = s_amp[0][f][lth] * s_amp[1][f][lph];
+                const float a = s_amp[f][0][lth] * s_amp[f][1][lph];
                 double cyc = dopl * g_freq.kk[f];
                 cyc -= rint(cyc);  // phase reduced to [-1/2, 1/2] cycles in fp64
                 float sn, cs;
@@ -285,25 +300,18 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
                 vre = a * cs;
                 vim = a * sn;
             }
-            const long long base = ((long long)irx * p.n_freq + f) * plane;
 #pragma unroll
-            for (int gi = 0; gi < kMaxGroups; ++gi) {
-                if (gmask[gi] == 0u) break;  // warp-uniform
-                const bool in = (gmask[gi] >> lane) & 1u;
-                float sre = in ? vre : 0.f, sim = in ? vim : 0.f;
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-                    sre += __shfl_xor_sync(0xffffffffu, sre, o);
-                    sim += __shfl_xor_sync(0xffffffffu, sim, o);
-                }
-                if (lane == __ffs(gmask[gi]) - 1) {
-                    atomicAdd(re + base + gbin[gi], sre);
-                    atomicAdd(im + base + gbin[gi], sim);
+            for (int o = 1; o < 32; o <<= 1) {
+                const float ore = __shfl_down_sync(0xffffffffu, vre, o);
+                const float oim = __shfl_down_sync(0xffffffffu, vim, o);
+                if (o <= rest) {
+                    vre += ore;
+                    vim += oim;
                 }
             }
-            if (direct) {
-                atomicAdd(re + base + bin, vre);
-                atomicAdd(im + base + bin, vim);
+            if (flush) {
+                atomicAdd(re_f + bin, vre);
+                atomicAdd(im_f + bin, vim);
             }
         }
     }
