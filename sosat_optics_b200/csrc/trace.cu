@@ -16,7 +16,7 @@ __constant__ GeomC g_geom;
 static bool g_geom_set[64] = {false};
 // a near-parabolic surface on this device's geometry: use the kernels that keep the
 // u c'/(1+s) form of the conic sag (trace_device.cuh)
-static bool g_geom_generic[64] = {false};
+static int g_geom_build[64] = {0};
 
 static constexpr double kHalfPi = 1.5707963267948966;
 static constexpr double kFourLn2 = 2.772588722239781;  // (1/2) / (1/sqrt(8 ln 2))^2
@@ -66,7 +66,15 @@ struct RowsParams {
 };
 
 // ---- K1a: reference table out[17][n] ----------------------------------------------------
-template <int N32, int N64, bool GENERIC>
+// GEO selects the surface-evaluation build (trace_device.cuh): 0 = division-free conic, only
+// lens 2b refined (the SAT prescription); 1 = division-free, every surface refined (any other
+// geometry); 2 = the u c'/(1+s) form (near-parabolic surfaces).
+template <int GEO> struct GeoBuild {
+    static constexpr bool generic = GEO == 2;
+    static constexpr int mask = GEO == 0 ? 0x04 : 0x3f;
+};
+
+template <int N32, int N64, int GEO>
 __global__ void __launch_bounds__(256)
 trace_rows_kernel(RowsParams p, double *__restrict__ out, double *__restrict__ stats) {
     const long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
@@ -85,7 +93,7 @@ trace_rows_kernel(RowsParams p, double *__restrict__ out, double *__restrict__ s
         const double d0x = sth * cph, d0y = sth * sph, d0z = cth;
         RayResult r;
         unsigned n_slow = 0;
-        trace_ray<N32, N64, GENERIC>(g_geom, p.rx[0], p.rx[1], p.rx[2], d0x, d0y, d0z, r, n_slow);
+        trace_ray<N32, N64, GeoBuild<GEO>::generic, GeoBuild<GEO>::mask>(g_geom, p.rx[0], p.rx[1], p.rx[2], d0x, d0y, d0z, r, n_slow);
         double row[11];
         if (r.flags & RAY_CLIPPED_L3) {
 #pragma unroll
@@ -149,11 +157,17 @@ struct BinParams {
 // map (theta, phi) -> (x, z) is smooth, the runs are long: 1-2 per warp at 240 rays/bin
 // (configs[4]), one per row of 8 at 15 rays/bin.  Any key sequence is handled correctly --
 // equal bins that are not adjacent in lane order simply become separate atomics.
-template <int N32, int N64, int MINB, bool GENERIC>
+template <int N32, int N64, int MINB, int GEO>
 __global__ void __launch_bounds__(256, MINB)
 trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict__ re,
                  float *__restrict__ im, float *__restrict__ cnt, double *__restrict__ stats) {
-    __shared__ double s_sin[2][kTile], s_cos[2][kTile];
+    __shared__ double s_sin[2][kTile], s_cos[2][kTile], s_rx[4];
+    // Launch-angle tables, filled once per CTA: sin/cos of  l step (l < 16),  16 j step (j < 64)
+    // and  start + 1024 k step (k < 64).  The angle of grid index i = l + 16 j + 1024 k is
+    // start + i step (numpy.linspace, ray_trace.py:1086-1087); its sine and cosine follow from
+    // two angle additions (8 DFMA/DMUL, ~3e-16 relative) instead of an fp64 sincos per tile
+    // edge on the critical path in front of the tile barrier.
+    __shared__ double2 s_rot[16 + 64 + 64];
     __shared__ float s_amp[SOSAT_MAX_FREQS][2][kTile];  // [freq][theta|phi][index in tile]
     // Running statistics.  fp64 sums: one shared-memory slot per thread (no conflicts, no
     // registers held across the tracer).  Counters: warp ballots added by lane 0 to packed
@@ -171,6 +185,15 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
     if (tid == 0) {
         s_valid_binned = 0ull;
         s_rare[0] = s_rare[1] = 0u;
+    }
+    const bool use_rot = p.n_scan <= 65536;
+    if (use_rot && tid < 16 + 64 + 64) {
+        const double a = tid < 16 ? (double)tid * p.lin_step
+                         : tid < 80 ? (double)(16 * (tid - 16)) * p.lin_step
+                                    : fma((double)(1024 * (tid - 80)), p.lin_step, p.lin_start);
+        double sn, cs;
+        sincos(a, &sn, &cs);
+        s_rot[tid] = make_double2(sn, cs);
     }
     int acc_rx = -1;
     // tile bookkeeping in 32 bits (the host checks n_tiles < 2^31): 64-bit divisions cost
@@ -210,14 +233,23 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
             if (acc_rx >= 0) flush_stats(acc_rx);
             acc_rx = irx;
         }
-        __syncthreads();  // previous tile done with the tables
+        __syncthreads();  // previous tile done with the tables (first pass: s_rot is complete)
+        if (tid >= 2 * kTile && tid < 2 * kTile + 3) s_rx[tid - 2 * kTile] = d_rx[3 * irx + tid - 2 * kTile];
         if (tid < 2 * kTile) {
             const int which = tid >> 4, l = tid & (kTile - 1);  // 0: theta, 1: phi
             const int idx = which == 0 ? tx * kTile + l : (int)p.row_begin + ty * kTile + l;
             const int ic = idx < p.n_scan ? idx : p.n_scan - 1;
             const double a = linspace_at(p.lin_start, p.lin_stop, p.lin_step, p.n_scan, ic);
             double sn, cs;
-            sincos(a, &sn, &cs);
+            if (use_rot) {
+                const double2 ra = s_rot[ic & 15], rb = s_rot[16 + ((ic >> 4) & 63)],
+                              rc = s_rot[80 + (ic >> 10)];
+                const double s1 = fma(rc.x, rb.y, rc.y * rb.x), c1 = fma(rc.y, rb.y, -(rc.x * rb.x));
+                sn = fma(s1, ra.y, c1 * ra.x);
+                cs = fma(c1, ra.y, -(s1 * ra.x));
+            } else {
+                sincos(a, &sn, &cs);
+            }
             s_sin[which][l] = sn;
             s_cos[which][l] = cs;
             const double ang = a - kHalfPi;  // -de_ho (theta) / de_ve (phi), ray_trace.py:1529-1532
@@ -231,15 +263,15 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
         const int ith = tx * kTile + lth;
         const int iph = ty * kTile + lph;  // relative to row_begin
         const bool live = ith < p.n_scan && iph < p.n_rows;
-        const double *rx = d_rx + 3 * irx;
+        const double *rx = s_rx;  // feed position [mm], staged with the tables
         RayResult r;
         {
             // lanes past the edge of the launch grid trace the clamped (edge) ray so that whole
             // warps stay converged; their result is dropped
             const double sth = s_sin[0][lth], cth = s_cos[0][lth];
             const double sph = s_sin[1][lph], cph = s_cos[1][lph];
-            trace_ray_newton<N32, N64, GENERIC>(g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph,
-                                                cth, r);
+            trace_ray_newton<N32, N64, GeoBuild<GEO>::generic, GeoBuild<GEO>::mask>(
+                g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph, cth, r);
         }
         if (r.valid && (r.flags & RAY_FLAGGED)) {
             // rare (< 0.15 % of rays): the reference's bracketed solve.  The launch direction is
@@ -439,6 +471,7 @@ extern "C" int sosat_set_geometry(const sosat_geom_t *h, void *stream) {
     GeomC g;
     memset(&g, 0, sizeof g);
     bool generic = false;
+    int refine_mask = 0;
     for (int i = 0; i < SOSAT_NUM_SURFACES; ++i) {
         const sosat_surface_t &s = h->surf[i];
         SOSAT_REQUIRE(s.n_in > 0 && s.n_out > 0, "surface %d: refractive index <= 0", i);
@@ -460,6 +493,7 @@ extern "C" int sosat_set_geometry(const sosat_geom_t *h, void *stream) {
         c.omm2 = 1.0 - c.mu2;
         c.cK = c.Kp != 0.0 ? c.cp / c.Kp : 0.0;
         c.refine = fabs(c.cK) > 300.0;
+        refine_mask |= c.refine << i;
         if (c.Kp == 0.0 ? c.cp != 0.0 : !(fabs(c.cK) <= 1e6)) generic = true;
         SurfF &f = g.f[i];
         f.Kp = (float)c.Kp; f.cp = (float)c.cp; f.a1p = (float)c.a1p; f.a2p = (float)c.a2p;
@@ -478,20 +512,23 @@ extern "C" int sosat_set_geometry(const sosat_geom_t *h, void *stream) {
     SOSAT_CUDA_OK(cudaStreamSynchronize((cudaStream_t)stream));
     g_host_geom[dev] = *h;
     g_geom_set[dev] = true;
-    const char *force = getenv("SOSAT_TRACE_GENERIC");  // testing hook: exercise the generic kernels
-    g_geom_generic[dev] = generic || (force && atoi(force) != 0);
+    const char *force = getenv("SOSAT_TRACE_GEO");  // testing hook: force build 1 or 2
+    int build = generic ? 2 : (refine_mask == 0x04 ? 0 : 1);
+    if (force && atoi(force) > build) build = atoi(force) > 2 ? 2 : atoi(force);
+    g_geom_build[dev] = build;
     return SOSAT_OK;
 }
 
 template <int N32, int N64>
-static void launch_rows(bool generic, const RowsParams &p, double *out, double *stats,
+static void launch_rows(int geo, const RowsParams &p, double *out, double *stats,
                         cudaStream_t st) {
     const int threads = 256;
-    const long long blocks = (p.n + threads - 1) / threads;
-    if (generic)
-        trace_rows_kernel<N32, N64, true><<<(unsigned)blocks, threads, 0, st>>>(p, out, stats);
-    else
-        trace_rows_kernel<N32, N64, false><<<(unsigned)blocks, threads, 0, st>>>(p, out, stats);
+    const unsigned blocks = (unsigned)((p.n + threads - 1) / threads);
+    switch (geo) {
+        case 0: trace_rows_kernel<N32, N64, 0><<<blocks, threads, 0, st>>>(p, out, stats); break;
+        case 1: trace_rows_kernel<N32, N64, 1><<<blocks, threads, 0, st>>>(p, out, stats); break;
+        default: trace_rows_kernel<N32, N64, 2><<<blocks, threads, 0, st>>>(p, out, stats); break;
+    }
 }
 
 extern "C" int sosat_trace_rays(const double *h_rx, const sosat_freq_t *h_freq, int n_scan,
@@ -518,12 +555,11 @@ extern "C" int sosat_trace_rays(const double *h_rx, const sosat_freq_t *h_freq, 
     if (p.n == 0) return SOSAT_OK;
     SOSAT_REQUIRE((p.n + 255) / 256 < 2147483647LL, "too many rays for one launch");
     cudaStream_t st = (cudaStream_t)stream;
-    const bool generic = g_geom_generic[dev];
+    const int geo = g_geom_build[dev];
     switch (trace_variant()) {
-        case 0: launch_rows<0, 5>(generic, p, d_out, d_stats, st); break;
-        case 2: launch_rows<3, 2>(generic, p, d_out, d_stats, st); break;
-        case 5: launch_rows<0, 4>(generic, p, d_out, d_stats, st); break;
-        default: launch_rows<2, 2>(generic, p, d_out, d_stats, st); break;
+        case 0: launch_rows<0, 5>(geo, p, d_out, d_stats, st); break;
+        case 2: launch_rows<3, 2>(geo, p, d_out, d_stats, st); break;
+        default: launch_rows<2, 2>(geo, p, d_out, d_stats, st); break;
     }
     SOSAT_CUDA_OK(cudaGetLastError());
     return SOSAT_OK;
@@ -562,24 +598,25 @@ extern "C" int sosat_rx_to_lyot_host(const sosat_geom_t *h_geom, const double *h
 }
 
 // Launch the persistent binning kernel with grid = SMs x resident CTAs per SM.
-template <int N32, int N64, int MINB, bool GENERIC>
+template <int N32, int N64, int MINB, int GEO>
 static void launch_bin(const BinParams &p, const double *rx, float *re, float *im, float *cnt,
                        double *stats, cudaStream_t st) {
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &occ, trace_bin_kernel<N32, N64, MINB, GENERIC>, 256, 0);
+        &occ, trace_bin_kernel<N32, N64, MINB, GEO>, 256, 0);
     const long long want = (long long)num_sms() * (occ > 0 ? occ : 1);
     const int blocks = (int)(p.n_tiles < want ? p.n_tiles : want);
-    trace_bin_kernel<N32, N64, MINB, GENERIC><<<blocks, 256, 0, st>>>(p, rx, re, im, cnt, stats);
+    trace_bin_kernel<N32, N64, MINB, GEO><<<blocks, 256, 0, st>>>(p, rx, re, im, cnt, stats);
 }
 
 template <int N32, int N64>
-static void launch_bin_minb(bool generic, int minb, const BinParams &p, const double *rx,
+static void launch_bin_minb(int geo, int minb, const BinParams &p, const double *rx,
                             float *re, float *im, float *cnt, double *stats, cudaStream_t st) {
-    if (generic) return launch_bin<N32, N64, 4, true>(p, rx, re, im, cnt, stats, st);
+    if (geo == 2) return launch_bin<N32, N64, 4, 2>(p, rx, re, im, cnt, stats, st);
+    if (geo == 1) return launch_bin<N32, N64, 4, 1>(p, rx, re, im, cnt, stats, st);
     switch (minb) {
-        case 3: launch_bin<N32, N64, 3, false>(p, rx, re, im, cnt, stats, st); break;
-        default: launch_bin<N32, N64, 4, false>(p, rx, re, im, cnt, stats, st); break;
+        case 3: launch_bin<N32, N64, 3, 0>(p, rx, re, im, cnt, stats, st); break;
+        default: launch_bin<N32, N64, 4, 0>(p, rx, re, im, cnt, stats, st); break;
     }
 }
 
@@ -638,12 +675,11 @@ extern "C" int sosat_trace_bin(const double *d_rx, int n_rx, const sosat_freq_t 
     SOSAT_REQUIRE(p.n_tiles < 2147483647LL, "too many ray tiles for one launch (%lld): split the "
                   "receiver list or the row range", p.n_tiles);
     const int minb = trace_minb();
-    const bool generic = g_geom_generic[dev];
+    const int geo = g_geom_build[dev];
     switch (trace_variant()) {
-        case 0: launch_bin_minb<0, 5>(generic, minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
-        case 2: launch_bin_minb<3, 2>(generic, minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
-        case 5: launch_bin_minb<0, 4>(generic, minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
-        default: launch_bin_minb<2, 2>(generic, minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
+        case 0: launch_bin_minb<0, 5>(geo, minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
+        case 2: launch_bin_minb<3, 2>(geo, minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
+        default: launch_bin_minb<2, 2>(geo, minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
     }
     SOSAT_CUDA_OK(cudaGetLastError());
     // bf lives on this stack frame: the async symbol copy from pageable memory is staged

@@ -153,7 +153,7 @@ __device__ __forceinline__ float rsqrt_f32(float x) {
 // f = [y0PyK - d_y t - u poly] + (cK w) rs, i.e. one DFMA after the rsqrt chain ends, with the
 // bracket and cK w evaluated while the MUFU seed is in flight.
 template <bool GENERIC>
-__device__ __forceinline__ void surf_eval(const SurfC &S, double Px, double Pz, double dx,
+__device__ __forceinline__ void surf_eval(const SurfC &S, const bool refine, double Px, double Pz, double dx,
                                           double dy, double dz, double y0PyK, double t,
                                           double &f, double &fp, double &X, double &Z,
                                           double &G, double &w) {
@@ -169,7 +169,7 @@ __device__ __forceinline__ void surf_eval(const SurfC &S, double Px, double Pz, 
         f = fma(-u, S.cp * rcp_full(1.0 + s), base);
     } else {
         const double B = S.cK * w;
-        if (S.refine) {  // warp-uniform (constant bank): one more Newton-Raphson step on rs
+        if (refine) {  // |cK| > 300 mm (folds to a constant in the unrolled surface loop)
             const double a = w * rs;
             rs = fma(0.5 * rs, fma(-a, rs, 1.0), rs);
         }
@@ -261,7 +261,12 @@ __device__ __forceinline__ void finish_ray(const GeomC &g, double Px, double Py,
 #endif
 
 // Fast path.  N32 Newton steps in fp32 from the vertex-plane guess, then N64 in fp64.
-template <int N32, int N64, bool GENERIC>
+// REFINE_MASK: bit si set = surface si uses the fully refined rsqrt / the division form of the
+// fp32 pre-iterations (|c'/K'| > 300 mm).  Compile-time so that the unrolled surface loop holds
+// one straight-line variant per surface (the instruction cache is a measured limiter of K1):
+// the host launches the 0x04 build when exactly lens 2b needs it (the SAT prescription) and
+// the 0x3f build -- refined everywhere, a few per cent slower -- for any other geometry.
+template <int N32, int N64, bool GENERIC, int REFINE_MASK>
 __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, double Py,
                                                  double Pz, double dx, double dy, double dz,
                                                  RayResult &r) {
@@ -278,7 +283,7 @@ __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, doub
             const float fPx = (float)Px, fPz = (float)Pz, fdx = (float)dx, fdy = (float)dy,
                         fdz = (float)dz, fy0 = (float)y0Py;
             float tf = fy0 * rcp_f32(fdy);  // vertex-plane guess
-            if (!GENERIC && !S.refine) {  // warp-uniform
+            if (!GENERIC && !((REFINE_MASK >> si) & 1)) {
                 const float fy0K = fy0 - F.cK;
 #pragma unroll
                 for (int it = 0; it < N32; ++it) {
@@ -303,7 +308,7 @@ __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, doub
 #pragma unroll
         for (int it = 0; it < N64; ++it) {
             double f, fp;
-            surf_eval<GENERIC>(S, Px, Pz, dx, dy, dz, y0PyK, t, f, fp, X, Z, G, w);
+            surf_eval<GENERIC>(S, ((REFINE_MASK >> si) & 1) != 0, Px, Pz, dx, dy, dz, y0PyK, t, f, fp, X, Z, G, w);
             step = f * rcp_seed(fp);
             t -= step;
         }
@@ -313,7 +318,7 @@ __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, doub
         for (int extra = 0; extra < SOSAT_NEWTON_EXTRA &&
                             __any_sync(0xffffffffu, fabs(step) > SOSAT_NEWTON_REFINE); ++extra) {
             double f, fp;
-            surf_eval<GENERIC>(S, Px, Pz, dx, dy, dz, y0PyK, t, f, fp, X, Z, G, w);
+            surf_eval<GENERIC>(S, ((REFINE_MASK >> si) & 1) != 0, Px, Pz, dx, dy, dz, y0PyK, t, f, fp, X, Z, G, w);
             step = f * rcp_seed(fp);
             t -= step;
         }
@@ -428,7 +433,7 @@ __device__ __noinline__ void trace_ray_bracketed(const GeomC &g, double Px, doub
         const double y0Py = S.y0 - Py;
         const double t = brent_solve(S, Px, Pz, dx, dy, dz, y0Py, flags);
         double f, fp, X, Z, G, w;
-        surf_eval<true>(S, Px, Pz, dx, dy, dz, y0Py, t, f, fp, X, Z, G, w);  // slope at the hit
+        surf_eval<true>(S, false, Px, Pz, dx, dy, dz, y0Py, t, f, fp, X, Z, G, w);  // slope at the hit
         Px = fma(dx, t, Px);
         Py = fma(dy, t, Py);
         Pz = fma(dz, t, Pz);
@@ -448,11 +453,11 @@ __device__ __noinline__ void trace_ray_bracketed(const GeomC &g, double Px, doub
 
 // Fast path, then the slow path for rays that came out valid but were flagged.  Must be called
 // by all 32 lanes of a warp (the fast path votes with __any_sync).
-template <int N32, int N64, bool GENERIC>
+template <int N32, int N64, bool GENERIC, int REFINE_MASK>
 __device__ __forceinline__ void trace_ray(const GeomC &g, double Px, double Py, double Pz,
                                           double dx, double dy, double dz, RayResult &r,
                                           unsigned &n_slow) {
-    trace_ray_newton<N32, N64, GENERIC>(g, Px, Py, Pz, dx, dy, dz, r);
+    trace_ray_newton<N32, N64, GENERIC, REFINE_MASK>(g, Px, Py, Pz, dx, dy, dz, r);
     if (r.valid && (r.flags & RAY_FLAGGED)) {
         trace_ray_bracketed(g, Px, Py, Pz, dx, dy, dz, r);
         r.flags |= RAY_FLAGGED;
