@@ -71,7 +71,8 @@ struct RowsParams {
 // geometry); 2 = the u c'/(1+s) form (near-parabolic surfaces).
 template <int GEO> struct GeoBuild {
     static constexpr bool generic = GEO == 2;
-    static constexpr int mask = GEO == 0 ? 0x04 : 0x3f;
+    static constexpr int mask = GEO == 0 ? 0x04 : 0x3f;  // surfaces with |c'/K'| > 300 mm
+    static constexpr int edge = GEO == 0 ? 0x10 : 0x3f;  // surfaces with K' > 0
 };
 
 template <int N32, int N64, int GEO>
@@ -93,7 +94,7 @@ trace_rows_kernel(RowsParams p, double *__restrict__ out, double *__restrict__ s
         const double d0x = sth * cph, d0y = sth * sph, d0z = cth;
         RayResult r;
         unsigned n_slow = 0;
-        trace_ray<N32, N64, GeoBuild<GEO>::generic, GeoBuild<GEO>::mask>(g_geom, p.rx[0], p.rx[1], p.rx[2], d0x, d0y, d0z, r, n_slow);
+        trace_ray<N32, N64, GeoBuild<GEO>::generic, GeoBuild<GEO>::mask, GeoBuild<GEO>::edge>(g_geom, p.rx[0], p.rx[1], p.rx[2], d0x, d0y, d0z, r, n_slow);
         double row[11];
         if (r.flags & RAY_CLIPPED_L3) {
 #pragma unroll
@@ -270,23 +271,37 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
             // warps stay converged; their result is dropped
             const double sth = s_sin[0][lth], cth = s_cos[0][lth];
             const double sph = s_sin[1][lph], cph = s_cos[1][lph];
-            trace_ray_newton<N32, N64, GeoBuild<GEO>::generic, GeoBuild<GEO>::mask>(
-                g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph, cth, r);
+            trace_ray_newton<N32, N64, GeoBuild<GEO>::generic, GeoBuild<GEO>::mask, GeoBuild<GEO>::edge,
+                             false>(g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph, cth, r);
         }
-        if (r.valid && (r.flags & RAY_FLAGGED)) {
-            // rare (< 0.15 % of rays): the reference's bracketed solve.  The launch direction is
-            // re-read here (volatile) instead of being kept live across the fast path, and the
-            // result goes through a local copy so that r itself stays in registers.
+        if (r.flags & (RAY_UNCONVERGED | RAY_FLAGGED)) {
+            // rare: the launch direction is re-read here (volatile) instead of being kept live
+            // across the fast path, and results go through a local copy so that r itself stays
+            // in registers.
             const double sth = *(volatile double *)&s_sin[0][lth], cth = *(volatile double *)&s_cos[0][lth];
             const double sph = *(volatile double *)&s_sin[1][lph], cph = *(volatile double *)&s_cos[1][lph];
             RayResult rs;
-            trace_ray_bracketed(g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph, cth, rs);
-            r.ax = rs.ax; r.az = rs.az; r.opl = rs.opl;
-            r.dx = rs.dx; r.dy = rs.dy; r.dz = rs.dz;
-            r.valid = rs.valid;
-            if (live) {
-                atomicAdd(&s_rare[0], 1u);
-                if (rs.flags & RAY_BRACKET_FAIL) atomicAdd(&s_rare[1], 1u);
+            rs.valid = r.valid;
+            rs.flags = r.flags;
+            bool redone = false;
+            if (r.flags & RAY_UNCONVERGED) {  // adaptive Newton refinement, out of line
+                trace_ray_adaptive<GeoBuild<GEO>::generic, GeoBuild<GEO>::mask, GeoBuild<GEO>::edge>(
+                    g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph, cth, rs);
+                redone = true;
+            }
+            if (rs.valid && (rs.flags & RAY_FLAGGED)) {
+                // < 0.15 % of rays: the reference's bracketed solve
+                trace_ray_bracketed(g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph, cth, rs);
+                redone = true;
+                if (live) {
+                    atomicAdd(&s_rare[0], 1u);
+                    if (rs.flags & RAY_BRACKET_FAIL) atomicAdd(&s_rare[1], 1u);
+                }
+            }
+            if (redone) {
+                r.ax = rs.ax; r.az = rs.az; r.opl = rs.opl;
+                r.dx = rs.dx; r.dy = rs.dy; r.dz = rs.dz;
+                r.valid = rs.valid;
             }
         }
         const bool valid = live && r.valid;
@@ -471,7 +486,7 @@ extern "C" int sosat_set_geometry(const sosat_geom_t *h, void *stream) {
     GeomC g;
     memset(&g, 0, sizeof g);
     bool generic = false;
-    int refine_mask = 0;
+    int refine_mask = 0, edge_mask = 0;
     for (int i = 0; i < SOSAT_NUM_SURFACES; ++i) {
         const sosat_surface_t &s = h->surf[i];
         SOSAT_REQUIRE(s.n_in > 0 && s.n_out > 0, "surface %d: refractive index <= 0", i);
@@ -494,6 +509,7 @@ extern "C" int sosat_set_geometry(const sosat_geom_t *h, void *stream) {
         c.cK = c.Kp != 0.0 ? c.cp / c.Kp : 0.0;
         c.refine = fabs(c.cK) > 300.0;
         refine_mask |= c.refine << i;
+        edge_mask |= (c.Kp > 0.0) << i;
         if (c.Kp == 0.0 ? c.cp != 0.0 : !(fabs(c.cK) <= 1e6)) generic = true;
         SurfF &f = g.f[i];
         f.Kp = (float)c.Kp; f.cp = (float)c.cp; f.a1p = (float)c.a1p; f.a2p = (float)c.a2p;
@@ -513,7 +529,7 @@ extern "C" int sosat_set_geometry(const sosat_geom_t *h, void *stream) {
     g_host_geom[dev] = *h;
     g_geom_set[dev] = true;
     const char *force = getenv("SOSAT_TRACE_GEO");  // testing hook: force build 1 or 2
-    int build = generic ? 2 : (refine_mask == 0x04 ? 0 : 1);
+    int build = generic ? 2 : (refine_mask == 0x04 && edge_mask == 0x10 ? 0 : 1);
     if (force && atoi(force) > build) build = atoi(force) > 2 ? 2 : atoi(force);
     g_geom_build[dev] = build;
     return SOSAT_OK;

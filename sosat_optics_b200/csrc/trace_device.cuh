@@ -59,12 +59,12 @@ struct GeomC {
 
 // Newton acceptance.  The surface normal is taken at the iterate before the last step, so the
 // last step bounds the normal error (curvature ~1e-2/mm, up to ~1e2/mm for wild rays near the
-// lens-1b conic edge).  After the fixed schedule a ray whose last step exceeds REFINE gets up
-// to SOSAT_NEWTON_EXTRA more fp64 steps (rare, warp-divergent); one still above TOL (or NaN)
-// is marked for the bracketed slow path.
+// lens-1b conic edge).  After the fixed schedule a ray whose last step exceeds REFINE is
+// re-traced by the adaptive path (up to SOSAT_NEWTON_EXTRA more fp64 steps per surface, rare,
+// lane-divergent); one still above TOL (or NaN) is marked for the bracketed slow path.
 #define SOSAT_NEWTON_REFINE 1.0e-9
 #define SOSAT_NEWTON_TOL 1.0e-8
-#define SOSAT_NEWTON_EXTRA 3
+#define SOSAT_NEWTON_EXTRA 6
 // lens 1b is the only surface with a bounded conic domain (k > -1): hits
 // with w = 1 - K'u below this are within ~8 mm of the domain edge r = 300.4 mm, where the
 // reference's brentq converges onto the sag discontinuity instead of a root.
@@ -73,7 +73,8 @@ struct GeomC {
 enum : unsigned {
     RAY_CLIPPED_L3 = 1u,  // ray_trace.py:1138-1140: whole output column stays zero
     RAY_FLAGGED = 2u,     // Newton not clearly converged / conic edge: needs the slow path
-    RAY_BRACKET_FAIL = 4u // slow path: f(lo), f(hi) same sign (reference raises ValueError)
+    RAY_BRACKET_FAIL = 4u,  // slow path: f(lo), f(hi) same sign (reference raises ValueError)
+    RAY_UNCONVERGED = 8u    // fast path: last fixed Newton step above REFINE, needs the adaptive path
 };
 
 struct RayResult {
@@ -260,13 +261,20 @@ __device__ __forceinline__ void finish_ray(const GeomC &g, double Px, double Py,
 #define SOSAT_SURFACE_LOOP_PRAGMA _Pragma("unroll 1")
 #endif
 
-// Fast path.  N32 Newton steps in fp32 from the vertex-plane guess, then N64 in fp64.
+// Newton path.  N32 Newton steps in fp32 from the vertex-plane guess, then N64 in fp64.
 // REFINE_MASK: bit si set = surface si uses the fully refined rsqrt / the division form of the
-// fp32 pre-iterations (|c'/K'| > 300 mm).  Compile-time so that the unrolled surface loop holds
-// one straight-line variant per surface (the instruction cache is a measured limiter of K1):
-// the host launches the 0x04 build when exactly lens 2b needs it (the SAT prescription) and
-// the 0x3f build -- refined everywhere, a few per cent slower -- for any other geometry.
-template <int N32, int N64, bool GENERIC, int REFINE_MASK>
+// fp32 pre-iterations (|c'/K'| > 300 mm).  EDGE_MASK: bit si set = surface si may have a
+// bounded conic domain (K' > 0) and gets the conic-edge test.  Both are compile-time so that
+// the unrolled surface loop holds one straight-line variant per surface (the instruction
+// cache is a measured limiter of K1): the host launches the (0x04, 0x10) build when exactly
+// lens 2b / lens 1b need them (the SAT prescription) and the (0x3f, 0x3f) build -- a few per
+// cent slower -- for any other geometry.
+// ADAPTIVE = false (fast path): a fixed schedule and nothing else; a lane whose last step is
+// still above REFINE raises RAY_UNCONVERGED and the caller re-traces it with ADAPTIVE = true
+// (out of line: essentially never taken for the boresight bundle, so the refinement loops
+// stay out of the hot instruction stream).  ADAPTIVE = true: up to SOSAT_NEWTON_EXTRA more
+// fp64 steps per surface; a lane still above TOL (or NaN) is marked for the bracketed solve.
+template <int N32, int N64, bool GENERIC, int REFINE_MASK, int EDGE_MASK, bool ADAPTIVE>
 __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, double Py,
                                                  double Pz, double dx, double dy, double dz,
                                                  RayResult &r) {
@@ -312,18 +320,21 @@ __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, doub
             step = f * rcp_seed(fp);
             t -= step;
         }
-        // warp-uniform refinement: every lane repeats the step while any lane still moves by
-        // more than REFINE (a converged lane just re-evaluates at its root); NaN lanes never ask
+        if (ADAPTIVE) {
 #pragma unroll 1
-        for (int extra = 0; extra < SOSAT_NEWTON_EXTRA &&
-                            __any_sync(0xffffffffu, fabs(step) > SOSAT_NEWTON_REFINE); ++extra) {
-            double f, fp;
-            surf_eval<GENERIC>(S, ((REFINE_MASK >> si) & 1) != 0, Px, Pz, dx, dy, dz, y0PyK, t, f, fp, X, Z, G, w);
-            step = f * rcp_seed(fp);
-            t -= step;
+            for (int extra = 0; extra < SOSAT_NEWTON_EXTRA && fabs(step) > SOSAT_NEWTON_REFINE;
+                 ++extra) {
+                double f, fp;
+                surf_eval<GENERIC>(S, ((REFINE_MASK >> si) & 1) != 0, Px, Pz, dx, dy, dz, y0PyK, t, f, fp, X, Z, G, w);
+                step = f * rcp_seed(fp);
+                t -= step;
+            }
+            if (!(fabs(step) <= SOSAT_NEWTON_TOL)) flags |= RAY_FLAGGED;
+        } else {
+            if (fabs(step) > SOSAT_NEWTON_REFINE) flags |= RAY_UNCONVERGED;  // false for NaN
         }
-        if (!(fabs(step) <= SOSAT_NEWTON_TOL)) flags |= RAY_FLAGGED;
-        if (S.Kp > 0.0 && !(w >= SOSAT_EDGE_W)) flags |= RAY_FLAGGED;
+        if (((EDGE_MASK >> si) & 1) && (EDGE_MASK == 0x10 || S.Kp > 0.0) && !(w >= SOSAT_EDGE_W))
+            flags |= RAY_FLAGGED;
         // hit point (ray_trace.py:1133-1136 and equivalents)
         Px = fma(dx, t, Px);
         Py = fma(dy, t, Py);
@@ -451,13 +462,22 @@ __device__ __noinline__ void trace_ray_bracketed(const GeomC &g, double Px, doub
     finish_ray(g, Px, Py, Pz, dx, dy, dz, opl, r2a_sq, r);
 }
 
-// Fast path, then the slow path for rays that came out valid but were flagged.  Must be called
-// by all 32 lanes of a warp (the fast path votes with __any_sync).
-template <int N32, int N64, bool GENERIC, int REFINE_MASK>
+// Out-of-line adaptive Newton path (pure fp64 start, 4 fixed steps + refinement).
+template <bool GENERIC, int REFINE_MASK, int EDGE_MASK>
+__device__ __noinline__ void trace_ray_adaptive(const GeomC &g, double Px, double Py, double Pz,
+                                                double dx, double dy, double dz, RayResult &r) {
+    trace_ray_newton<0, 4, GENERIC, REFINE_MASK, EDGE_MASK, true>(g, Px, Py, Pz, dx, dy, dz, r);
+}
+
+// Fast path; the adaptive path for lanes the fixed schedule left unconverged; the bracketed
+// slow path for rays that came out valid but were flagged.
+template <int N32, int N64, bool GENERIC, int REFINE_MASK, int EDGE_MASK>
 __device__ __forceinline__ void trace_ray(const GeomC &g, double Px, double Py, double Pz,
                                           double dx, double dy, double dz, RayResult &r,
                                           unsigned &n_slow) {
-    trace_ray_newton<N32, N64, GENERIC, REFINE_MASK>(g, Px, Py, Pz, dx, dy, dz, r);
+    trace_ray_newton<N32, N64, GENERIC, REFINE_MASK, EDGE_MASK, false>(g, Px, Py, Pz, dx, dy, dz, r);
+    if (r.flags & RAY_UNCONVERGED)
+        trace_ray_adaptive<GENERIC, REFINE_MASK, EDGE_MASK>(g, Px, Py, Pz, dx, dy, dz, r);
     if (r.valid && (r.flags & RAY_FLAGGED)) {
         trace_ray_bracketed(g, Px, Py, Pz, dx, dy, dz, r);
         r.flags |= RAY_FLAGGED;
