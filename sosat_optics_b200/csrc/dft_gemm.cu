@@ -7,13 +7,23 @@
 // (SURVEY section 7), so every operand is split x = hi + lo (two bf16) and each k-block issues
 // the three products hi*hi + hi*lo + lo*hi into the same accumulator ("bf16x3").
 //
-//   pass 1:  D1[(l,c), m] = sum_n  Wc[(l,c), (n,c')] * b[m, (n,c')]        (column transform)
-//   pass 2:  D2[(k,c), l] = sum_m  Wr[(k,c), (c',m)] * D1[l, (c',m)]       (row transform)
+//   prep:    X[m, (n,c')] = b[n, m]                 (transpose + bf16 hi/lo split, zero padded)
+//   pass 1:  D1[(l,c), m] = sum_n  W[(l,c), (n,c')] * X[m, (n,c')]     = (W b)[l, m]
+//   pass 2:  B[l, (k,c)]  = sum_m  D1[l, (c',m)]    * W[(k,c), (c',m)] = (W b W^T)[l, k]
 //
 // (.,c) = real/imag component.  The complex structure is folded into the twiddle operand:
 // row (l,re) = [Wr, -Wi], row (l,im) = [Wi, Wr] along K, so the data operand is just the
 // complex array viewed as reals.  Both passes are "TN" GEMMs with K-major operands; pass 1
-// writes its result already split into bf16 hi/lo in exactly the layout pass 2 reads.
+// writes its result already split into bf16 hi/lo in exactly the layout pass 2 reads, and pass 2
+// (twiddle on the N side) leaves the accumulator rows as rows of B with interleaved re/im
+// columns, so its epilogue stores the complex64 result directly -- no finishing pass.
+//
+// The mainloop of a 128 x 128 tile needs 64 KB of operands per 12 UMMAs (768 tensor-pipe
+// cycles): 85 B/clk/SM, more than L2 can feed 128-148 SMs at once (the first cut was
+// L2->SM bandwidth bound: 25 us per 1024^2 pass against 12.5 us of UMMA time).  CTAs are
+// therefore launched as CX x CY clusters: the CX CTAs of a cluster row share the A tile and
+// the CY CTAs of a column share the B tile; each CTA TMA-loads a 1/CX (1/CY) slice and
+// multicasts it, which divides the L2 traffic per CTA by 2 for 2 x 2 clusters.
 #include <cuda.h>
 #include <cuda_bf16.h>
 
@@ -62,6 +72,29 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap *map
         ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1)
         : "memory");
 }
+__device__ __forceinline__ void tma_load_2d_mc(uint32_t dst, const CUtensorMap *map, uint32_t bar,
+                                               int c0, int c1, uint16_t cta_mask) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes"
+        ".multicast::cluster [%0], [%1, {%3, %4}], [%2], %5;"
+        ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "h"(cta_mask)
+        : "memory");
+}
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+    uint32_t r;
+    asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+    return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+    asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+    asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// programmatic dependent launch: wait for the prerequisite grid (and its memory), and let the
+// dependent grid start its prologue
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() {
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");
+}
 __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
                                           uint32_t idesc, uint32_t accumulate) {
     asm volatile(
@@ -74,6 +107,12 @@ __device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint6
 __device__ __forceinline__ void umma_commit(uint32_t bar) {
     asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];"
                  ::"r"(bar) : "memory");
+}
+// commit that arrives on the barrier at the same offset in every CTA of cta_mask
+__device__ __forceinline__ void umma_commit_mc(uint32_t bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64"
+        " [%0], %1;" ::"r"(bar), "h"(cta_mask) : "memory");
 }
 __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile(
@@ -102,17 +141,21 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
            ((uint32_t)(m >> 4) << 24);
 }
 
-enum { EPI_F32 = 0, EPI_SPLIT_BF16 = 1 };
+enum { EPI_C64 = 0, EPI_SPLIT_BF16 = 1 };
 
-// D[M][N] (+)= A_hi B_hi^T + A_hi B_lo^T + A_lo B_hi^T ; one 128 x 128 tile per CTA.
+// D[M][N] (+)= A_hi B_hi^T + A_hi B_lo^T + A_lo B_hi^T ; one 128 x 128 tile per CTA, CTAs in
+// CX x CY clusters (cluster x = blockIdx.x = N tiles, y = M tiles).
 // warp 0 lane 0: TMA producer.  warp 1 lane 0: MMA issuer.  all 4 warps: epilogue.
-template <int EPI>
+//   EPI_SPLIT_BF16: D -> bf16 hi/lo planes d_hi/d_lo [M][ldd]                       (pass 1)
+//   EPI_C64:        D * scale -> d_c64 [n_valid][2 n_valid] floats = complex64 [n][n] (pass 2)
+template <int EPI, int CX, int CY>
 __global__ void __launch_bounds__(128, 1)
 gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                    const __grid_constant__ CUtensorMap map_a_lo,
                    const __grid_constant__ CUtensorMap map_b_hi,
-                   const __grid_constant__ CUtensorMap map_b_lo, int num_kb, float *__restrict__ d_f32,
-                   __nv_bfloat16 *__restrict__ d_hi, __nv_bfloat16 *__restrict__ d_lo, int ldd) {
+                   const __grid_constant__ CUtensorMap map_b_lo, int num_kb, float *__restrict__ d_c64,
+                   __nv_bfloat16 *__restrict__ d_hi, __nv_bfloat16 *__restrict__ d_lo, int ldd,
+                   int n_valid, float scale) {
     extern __shared__ uint8_t smem_raw[];
     uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
     uint64_t *bars = (uint64_t *)(smem + kStages * kStageBytes);
@@ -121,11 +164,20 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                    accum_bar = smem_u32(bars + 2 * kStages);
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int n0 = blockIdx.x * BN, m0 = blockIdx.y * BM;
+    constexpr bool kCluster = CX * CY > 1;
+    constexpr int kSharers = CX + CY - 1;  // CTAs whose smem one CTA's loads (and commits) reach
+    const uint32_t rank = kCluster ? cluster_ctarank() : 0u;
+    const int cx = (int)rank % CX, cy = (int)rank / CX;
+    uint16_t mask_a = 0, mask_b = 0;  // cluster row-mates share A, column-mates share B
+#pragma unroll
+    for (int x = 0; x < CX; ++x) mask_a |= (uint16_t)(1u << (x + cy * CX));
+#pragma unroll
+    for (int y = 0; y < CY; ++y) mask_b |= (uint16_t)(1u << (cx + y * CX));
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages; ++s) {
             mbar_init(full0 + 8 * s, 1);
-            mbar_init(empty0 + 8 * s, 1);
+            mbar_init(empty0 + 8 * s, kSharers);  // every CTA that reads this stage's data
         }
         mbar_init(accum_bar, 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -141,20 +193,35 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
     const uint32_t tmem_base = *tmem_slot;
+    if (kCluster) cluster_sync_all();  // peers' barriers are initialised before anything is multicast
+    pdl_wait();                        // operands come from the previous kernel in the stream
+    pdl_launch_dependents();
 
     if (warp == 0 && lane == 0) {
-        // ---- TMA producer ----
+        // ---- TMA producer: this CTA's slice of A (rows cx*128/CX ..) and of B, multicast ----
+        constexpr int kRowsA = BM / CX, kRowsB = BN / CY;
         for (int kb = 0; kb < num_kb; ++kb) {
             const int s = kb % kStages;
             const uint32_t ph = (uint32_t)(kb / kStages) & 1u;
             mbar_wait(empty0 + 8 * s, ph ^ 1u);
             const uint32_t full = full0 + 8 * s;
             const uint32_t base = smem_u32(smem + s * kStageBytes);
-            mbar_expect_tx(full, kStageBytes);
-            tma_load_2d(base + 0 * kTileBytes, &map_a_hi, full, kb * BK, m0);
-            tma_load_2d(base + 1 * kTileBytes, &map_a_lo, full, kb * BK, m0);
-            tma_load_2d(base + 2 * kTileBytes, &map_b_hi, full, kb * BK, n0);
-            tma_load_2d(base + 3 * kTileBytes, &map_b_lo, full, kb * BK, n0);
+            mbar_expect_tx(full, kStageBytes);  // own slices + the peers' multicasts
+            const uint32_t da = base + (uint32_t)(cx * kRowsA * 128), db = base + (uint32_t)(cy * kRowsB * 128);
+            if (CX > 1) {
+                tma_load_2d_mc(da + 0 * kTileBytes, &map_a_hi, full, kb * BK, m0 + cx * kRowsA, mask_a);
+                tma_load_2d_mc(da + 1 * kTileBytes, &map_a_lo, full, kb * BK, m0 + cx * kRowsA, mask_a);
+            } else {
+                tma_load_2d(da + 0 * kTileBytes, &map_a_hi, full, kb * BK, m0);
+                tma_load_2d(da + 1 * kTileBytes, &map_a_lo, full, kb * BK, m0);
+            }
+            if (CY > 1) {
+                tma_load_2d_mc(db + 2 * kTileBytes, &map_b_hi, full, kb * BK, n0 + cy * kRowsB, mask_b);
+                tma_load_2d_mc(db + 3 * kTileBytes, &map_b_lo, full, kb * BK, n0 + cy * kRowsB, mask_b);
+            } else {
+                tma_load_2d(db + 2 * kTileBytes, &map_b_hi, full, kb * BK, n0);
+                tma_load_2d(db + 3 * kTileBytes, &map_b_lo, full, kb * BK, n0);
+            }
         }
     } else if (warp == 1 && lane == 0) {
         // ---- MMA issuer (single thread) ----
@@ -176,7 +243,9 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                 umma_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
                 umma_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, 1u);
             }
-            umma_commit(empty0 + 8 * s);  // stage reusable once these MMAs retire
+            // stage reusable once these MMAs retire: tell every CTA that loads into this one
+            if (kCluster) umma_commit_mc(empty0 + 8 * s, (uint16_t)(mask_a | mask_b));
+            else umma_commit(empty0 + 8 * s);
         }
         umma_commit(accum_bar);
     }
@@ -190,14 +259,28 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     for (int c = 0; c < BN / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
-        const size_t off = (size_t)row * ldd + n0 + c * 32;
-        if (EPI == EPI_F32) {
-            float4 *dst = (float4 *)(d_f32 + off);
+        if (EPI == EPI_C64) {
+            // row = l, columns = (k, re|im) interleaved: the complex64 row of B, n_valid wide
+            const int j0 = n0 + c * 32;
+            if (row < n_valid && j0 < 2 * n_valid) {
+                float *dst = d_c64 + (size_t)row * (2 * (size_t)n_valid) + j0;
+                if ((n_valid & 1) == 0 && j0 + 32 <= 2 * n_valid) {
 #pragma unroll
-            for (int q = 0; q < 8; ++q)
-                dst[q] = make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
-                                     __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
+                    for (int q = 0; q < 8; ++q)
+                        ((float4 *)dst)[q] = make_float4(scale * __uint_as_float(v[4 * q]),
+                                                         scale * __uint_as_float(v[4 * q + 1]),
+                                                         scale * __uint_as_float(v[4 * q + 2]),
+                                                         scale * __uint_as_float(v[4 * q + 3]));
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q)
+                        if (j0 + 2 * q + 1 < 2 * n_valid)
+                            ((float2 *)dst)[q] = make_float2(scale * __uint_as_float(v[2 * q]),
+                                                             scale * __uint_as_float(v[2 * q + 1]));
+                }
+            }
         } else {
+            const size_t off = (size_t)row * ldd + n0 + c * 32;
             uint32_t hi[16], lo[16];
 #pragma unroll
             for (int q = 0; q < 16; ++q) {
@@ -221,6 +304,8 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     if (warp == 0)
         asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
                      "r"(kTmemCols) : "memory");
+    // no CTA may exit while a peer can still multicast into its shared memory or barriers
+    if (kCluster) cluster_sync_all();
 }
 
 // ---- operand preparation (HBM-bound elementwise kernels) -----------------------------------
@@ -261,60 +346,73 @@ __global__ void twiddle_kernel(int n, int np, int so, int si, int sign, __nv_bfl
         }
 }
 
-// data operand of pass 1 from interleaved complex64: b1[m][2n+c'] (zero padded to np)
-__global__ void prep_b_c64_kernel(const float2 *__restrict__ b, int n, int np,
-                                  __nv_bfloat16 *b_hi, __nv_bfloat16 *b_lo) {
-    const int col = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
-    if (col >= np) return;
-    float2 v = make_float2(0.f, 0.f);
-    if (row < n && col < n) v = b[(size_t)row * n + col];
-    __nv_bfloat16 h0, l0, h1, l1;
-    split_bf16(v.x, h0, l0);
-    split_bf16(v.y, h1, l1);
-    const size_t i = (size_t)row * 2 * np + 2 * col;
-    *(__nv_bfloat162 *)(b_hi + i) = __nv_bfloat162(h0, h1);
-    *(__nv_bfloat162 *)(b_lo + i) = __nv_bfloat162(l0, l1);
-}
-
-// a2b input: |A| exp(i phi pi/180), opt_analyze.py:224 (amplitude and degrees, float64)
-__global__ void prep_b_a2b_kernel(const double *__restrict__ amp, const double *__restrict__ phi,
-                                  int n, int np, __nv_bfloat16 *b_hi, __nv_bfloat16 *b_lo) {
-    const int col = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
-    if (col >= np) return;
-    float2 v = make_float2(0.f, 0.f);
-    if (row < n && col < n) {
-        const size_t i = (size_t)row * n + col;
-        double s, c;
-        sincos(phi[i] * 3.141592653589793 / 180.0, &s, &c);
-        const double a = fabs(amp[i]);
-        v = make_float2((float)(a * c), (float)(a * s));
+// Data operand of pass 1: X[m][2n+c'] = component c' of b[n][m] (the transpose, zero padded to
+// np), split into bf16 hi/lo.  32 x 32 tiles through shared memory: coalesced 8-byte reads along
+// the rows of b, coalesced 4-byte (bf16x2) writes along the rows of X.  LOAD(row, col) returns
+// the complex sample b[row][col].
+template <class Load>
+__device__ __forceinline__ void prep_transposed(Load load, int n, int np, __nv_bfloat16 *b_hi,
+                                                __nv_bfloat16 *b_lo) {
+    __shared__ float2 tile[32][33];
+    const int tx = threadIdx.x, ty = threadIdx.y;  // 32 x 8
+    const int r0 = blockIdx.y * 32, c0 = blockIdx.x * 32;  // rows / columns of b
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int r = r0 + ty + 8 * q, c = c0 + tx;
+        tile[ty + 8 * q][tx] = (r < n && c < n) ? load(r, c) : make_float2(0.f, 0.f);
     }
-    __nv_bfloat16 h0, l0, h1, l1;
-    split_bf16(v.x, h0, l0);
-    split_bf16(v.y, h1, l1);
-    const size_t i = (size_t)row * 2 * np + 2 * col;
-    *(__nv_bfloat162 *)(b_hi + i) = __nv_bfloat162(h0, h1);
-    *(__nv_bfloat162 *)(b_lo + i) = __nv_bfloat162(l0, l1);
+    __syncthreads();
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const int m = c0 + ty + 8 * q, nn = r0 + tx;  // X row (column of b), X complex column
+        const float2 v = tile[tx][ty + 8 * q];
+        __nv_bfloat16 h0, l0, h1, l1;
+        split_bf16(v.x, h0, l0);
+        split_bf16(v.y, h1, l1);
+        const size_t i = (size_t)m * 2 * np + 2 * nn;
+        *(__nv_bfloat162 *)(b_hi + i) = __nv_bfloat162(h0, h1);
+        *(__nv_bfloat162 *)(b_lo + i) = __nv_bfloat162(l0, l1);
+    }
 }
 
-// d2 planar fp32 [2 np][np] (row 2k+c, column l) -> interleaved complex64 [n][n]
-__global__ void finish_c64_kernel(const float *__restrict__ d2, int n, int np, float scale,
-                                  float2 *__restrict__ out) {
-    const int col = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
-    if (col >= n) return;
-    out[(size_t)row * n + col] = make_float2(scale * d2[(size_t)(2 * row) * np + col],
-                                             scale * d2[(size_t)(2 * row + 1) * np + col]);
+__global__ void __launch_bounds__(256)
+prep_b_c64_kernel(const float2 *__restrict__ b, int n, int np, __nv_bfloat16 *b_hi,
+                  __nv_bfloat16 *b_lo) {
+    pdl_wait();
+    pdl_launch_dependents();
+    prep_transposed([&](int r, int c) { return b[(size_t)r * n + c]; }, n, np, b_hi, b_lo);
 }
 
-// a2b outputs: complex128 beam and phase = arctan2(imag, real), opt_analyze.py:228-229
-__global__ void finish_a2b_kernel(const float *__restrict__ d2, int n, int np, double scale,
+// a2b / b2a input: |A| exp(i phi pi/180), opt_analyze.py:211, 224 (amplitude and degrees, float64)
+__global__ void __launch_bounds__(256)
+prep_b_a2b_kernel(const double *__restrict__ amp, const double *__restrict__ phi, int n, int np,
+                  __nv_bfloat16 *b_hi, __nv_bfloat16 *b_lo) {
+    pdl_wait();
+    pdl_launch_dependents();
+    prep_transposed(
+        [&](int r, int c) {
+            const size_t i = (size_t)r * n + c;
+            double sn, cs;
+            sincos(phi[i] * 3.141592653589793 / 180.0, &sn, &cs);
+            const double a = fabs(amp[i]);
+            return make_float2((float)(a * cs), (float)(a * sn));
+        },
+        n, np, b_hi, b_lo);
+}
+
+// a2b / b2a outputs from the complex64 transform: complex128 field and phase =
+// arctan2(imag, real), opt_analyze.py:215-216, 228-229
+__global__ void finish_a2b_kernel(const float2 *__restrict__ c64, long long n2,
                                   double2 *__restrict__ beam, double *__restrict__ phase) {
-    const int col = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
-    if (col >= n) return;
-    const double re = scale * d2[(size_t)(2 * row) * np + col];
-    const double im = scale * d2[(size_t)(2 * row + 1) * np + col];
-    beam[(size_t)row * n + col] = make_double2(re, im);
-    phase[(size_t)row * n + col] = atan2(im, re);
+    pdl_wait();
+    pdl_launch_dependents();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float2 v = c64[i];
+        const double re = v.x, im = v.y;
+        beam[i] = make_double2(re, im);
+        phase[i] = atan2(im, re);
+    }
 }
 
 // ---- host side -------------------------------------------------------------------------------
@@ -322,7 +420,7 @@ struct DftWorkspace {
     uint8_t *base;
     int n, np;
     __nv_bfloat16 *a1_hi, *a1_lo, *a2_hi, *a2_lo, *b1_hi, *b1_lo, *d1_hi, *d1_lo;
-    float *d2;
+    float *c64;  // complex64 [n][n] staging for the float64 entry points (8 np^2 bytes)
 };
 static inline int pad128(int n) { return (n + 127) / 128 * 128; }
 
@@ -346,7 +444,7 @@ static DftWorkspace carve(void *ws, int n) {
     w.b1_lo = (__nv_bfloat16 *)p; p += 4 * np2;
     w.d1_hi = (__nv_bfloat16 *)p; p += 4 * np2;
     w.d1_lo = (__nv_bfloat16 *)p; p += 4 * np2;
-    w.d2 = (float *)p;
+    w.c64 = (float *)p;
     return w;
 }
 
@@ -367,13 +465,13 @@ static EncodeTiledFn encode_fn() {
     return fn;
 }
 
-// 2-D bf16 row-major [rows][cols] with 128B-swizzled {BK x 128} boxes
-static int make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols) {
+// 2-D bf16 row-major [rows][cols] with 128B-swizzled {BK x box_rows} boxes
+static int make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t cols, int box_rows) {
     EncodeTiledFn fn = encode_fn();
     if (!fn) return set_error(SOSAT_ERR_CUDA, "cuTensorMapEncodeTiled entry point unavailable");
     const cuuint64_t dims[2] = {cols, rows};
     const cuuint64_t strides[1] = {cols * 2};
-    const cuuint32_t box[2] = {BK, 128};
+    const cuuint32_t box[2] = {BK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)ptr, dims, strides, box, estr,
                     CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
@@ -382,14 +480,16 @@ static int make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t col
     return 0;
 }
 
-// Twiddle operands depend only on n; they are generated once per (device, workspace, n) and
-// remembered in a small host-side registry so that repeat transforms launch no extra work.
-// A caller that frees a planned workspace must call sosat_dft2_forget(ptr) before the address
-// can be reused for another workspace.
+// Twiddle operands and TMA descriptors depend only on (workspace, n, kind); they are built once
+// per (device, workspace, n, kind) and remembered in a small host-side registry so that repeat
+// transforms launch no extra work.  A caller that frees a planned workspace must call
+// sosat_dft2_forget(ptr) before the address can be reused for another workspace.
 struct PlanEntry {
     int device;
     const void *ws;
     int n, kind;
+    bool wide;             // np % 256 == 0: both passes run as 2 x 2 clusters
+    CUtensorMap maps[8];   // pass 1: A hi/lo, B hi/lo; pass 2: A hi/lo, B hi/lo
 };
 static PlanEntry g_plans[64];
 static int g_num_plans = 0;
@@ -408,15 +508,37 @@ static int dft_kind_params(int kind, int n, int &so, int &si, int &sign, double 
     return set_error(SOSAT_ERR_INVALID_ARG, "unknown transform kind %d", kind);
 }
 
-static int ensure_twiddles(const DftWorkspace &w, int kind, cudaStream_t st) {
+// Cluster shapes: pass 1 has grid (np/128, 2np/128), pass 2 (2np/128, np/128); the doubled
+// dimension is always even, the other one only when np is a multiple of 256.
+static int ensure_plan(const DftWorkspace &w, int kind, cudaStream_t st, const PlanEntry **out) {
     int dev = 0, so, si, sign;
     double scale;
     SOSAT_CUDA_OK(cudaGetDevice(&dev));
     if (int rc = dft_kind_params(kind, w.n, so, si, sign, scale)) return rc;
     for (int i = 0; i < g_num_plans; ++i)
         if (g_plans[i].device == dev && g_plans[i].ws == w.base && g_plans[i].n == w.n &&
-            g_plans[i].kind == kind)
+            g_plans[i].kind == kind) {
+            *out = &g_plans[i];
             return 0;
+        }
+    PlanEntry e;
+    e.device = dev; e.ws = w.base; e.n = w.n; e.kind = kind;
+    e.wide = (w.np % 256) == 0;
+    const uint64_t np = w.np;
+    const int half = 64, full = 128;
+    int rc = 0;
+    // pass 1: A = twiddle a1 rows (l,c) (cluster y = M: always 2 -> B slices), B = X rows m
+    //   A is shared along cluster x (CX = wide ? 2 : 1), B along cluster y (CY = 2)
+    if ((rc = make_map(&e.maps[0], w.a1_hi, 2 * np, 2 * np, e.wide ? half : full))) return rc;
+    if ((rc = make_map(&e.maps[1], w.a1_lo, 2 * np, 2 * np, e.wide ? half : full))) return rc;
+    if ((rc = make_map(&e.maps[2], w.b1_hi, np, 2 * np, half))) return rc;
+    if ((rc = make_map(&e.maps[3], w.b1_lo, np, 2 * np, half))) return rc;
+    // pass 2: A = pass-1 output [2 np][np] viewed as [np][2 np] rows l, B = twiddle a2 rows (k,c)
+    //   CX = 2 always (A slices), CY = wide ? 2 : 1
+    if ((rc = make_map(&e.maps[4], w.d1_hi, np, 2 * np, half))) return rc;
+    if ((rc = make_map(&e.maps[5], w.d1_lo, np, 2 * np, half))) return rc;
+    if ((rc = make_map(&e.maps[6], w.a2_hi, 2 * np, 2 * np, e.wide ? half : full))) return rc;
+    if ((rc = make_map(&e.maps[7], w.a2_lo, 2 * np, 2 * np, e.wide ? half : full))) return rc;
     dim3 grid((w.np + 127) / 128, w.np);
     twiddle_kernel<<<grid, 128, 0, st>>>(w.n, w.np, so, si, sign, w.a1_hi, w.a1_lo, w.a2_hi, w.a2_lo);
     SOSAT_CUDA_OK(cudaGetLastError());
@@ -424,40 +546,71 @@ static int ensure_twiddles(const DftWorkspace &w, int kind, cudaStream_t st) {
     for (int i = 0; i < g_num_plans; ++i)
         if (g_plans[i].device == dev && g_plans[i].ws == w.base) slot = i;  // same buffer, re-planned
     if (slot < 0) slot = g_num_plans < 64 ? g_num_plans++ : 0;
-    g_plans[slot] = PlanEntry{dev, w.base, w.n, kind};
+    g_plans[slot] = e;
+    *out = &g_plans[slot];
     return 0;
 }
 
-// the two GEMM passes; b1 must already hold the split data operand
-static int run_passes(const DftWorkspace &w, cudaStream_t st) {
-    static bool attr_set = false;
-    if (!attr_set) {
-        SOSAT_CUDA_OK(cudaFuncSetAttribute(gemm_bf16x3_kernel<EPI_F32>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
-        SOSAT_CUDA_OK(cudaFuncSetAttribute(gemm_bf16x3_kernel<EPI_SPLIT_BF16>,
-                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
-        attr_set = true;
+// launch with programmatic stream serialization (the kernels call griddepcontrol.wait before
+// touching global memory) and, for the GEMM passes, the cluster shape
+template <class... KArgs, class... Args>
+static int launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st,
+                      int cx, int cy, Args... args) {
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = grid;
+    cfg.blockDim = block;
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = st;
+    cudaLaunchAttribute attrs[2];
+    int na = 0;
+    attrs[na].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attrs[na].val.programmaticStreamSerializationAllowed = 1;
+    ++na;
+    if (cx * cy > 1) {
+        attrs[na].id = cudaLaunchAttributeClusterDimension;
+        attrs[na].val.clusterDim.x = cx;
+        attrs[na].val.clusterDim.y = cy;
+        attrs[na].val.clusterDim.z = 1;
+        ++na;
     }
-    const uint64_t np = w.np;
-    CUtensorMap a1h, a1l, a2h, a2l, b1h, b1l, b2h, b2l;
-    int rc = 0;
-    if ((rc = make_map(&a1h, w.a1_hi, 2 * np, 2 * np))) return rc;
-    if ((rc = make_map(&a1l, w.a1_lo, 2 * np, 2 * np))) return rc;
-    if ((rc = make_map(&a2h, w.a2_hi, 2 * np, 2 * np))) return rc;
-    if ((rc = make_map(&a2l, w.a2_lo, 2 * np, 2 * np))) return rc;
-    if ((rc = make_map(&b1h, w.b1_hi, np, 2 * np))) return rc;
-    if ((rc = make_map(&b1l, w.b1_lo, np, 2 * np))) return rc;
-    // pass-2 data operand = pass-1 output [2 np][np] viewed as [np][2 np]
-    if ((rc = make_map(&b2h, w.d1_hi, np, 2 * np))) return rc;
-    if ((rc = make_map(&b2l, w.d1_lo, np, 2 * np))) return rc;
-    const dim3 grid(w.np / BN, 2 * w.np / BM);
-    const int num_kb = 2 * w.np / BK;
-    gemm_bf16x3_kernel<EPI_SPLIT_BF16><<<grid, 128, kGemmSmem, st>>>(
-        a1h, a1l, b1h, b1l, num_kb, nullptr, w.d1_hi, w.d1_lo, w.np);
-    gemm_bf16x3_kernel<EPI_F32><<<grid, 128, kGemmSmem, st>>>(a2h, a2l, b2h, b2l, num_kb, w.d2,
-                                                              nullptr, nullptr, w.np);
-    SOSAT_CUDA_OK(cudaGetLastError());
+    cfg.attrs = attrs;
+    cfg.numAttrs = na;
+    SOSAT_CUDA_OK(cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...));
     return 0;
+}
+
+template <int EPI, int CX, int CY>
+static int launch_gemm(dim3 grid, cudaStream_t st, const CUtensorMap *m, int num_kb, float *c64,
+                       __nv_bfloat16 *d_hi, __nv_bfloat16 *d_lo, int ldd, int n_valid, float scale) {
+    static bool attr_set[64] = {false};  // per device: the attribute is per (function, context)
+    int dev = 0;
+    SOSAT_CUDA_OK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        SOSAT_CUDA_OK(cudaFuncSetAttribute(gemm_bf16x3_kernel<EPI, CX, CY>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, kGemmSmem));
+        attr_set[dev] = true;
+    }
+    return launch_pdl(gemm_bf16x3_kernel<EPI, CX, CY>, grid, dim3(128), kGemmSmem, st, CX, CY, m[0],
+                      m[1], m[2], m[3], num_kb, c64, d_hi, d_lo, ldd, n_valid, scale);
+}
+
+// the two GEMM passes; b1 must already hold the split, transposed data operand.  The complex64
+// result (times scale) is written to d_c64 [n][n].
+static int run_passes(const DftWorkspace &w, const PlanEntry &pl, float scale, float *d_c64,
+                      cudaStream_t st) {
+    const int num_kb = 2 * w.np / BK;
+    const dim3 g1(w.np / BN, 2 * w.np / BM), g2(2 * w.np / BN, w.np / BM);
+    int rc;
+    if (pl.wide) {
+        if ((rc = launch_gemm<EPI_SPLIT_BF16, 2, 2>(g1, st, pl.maps, num_kb, nullptr, w.d1_hi,
+                                                    w.d1_lo, w.np, 0, 1.f))) return rc;
+        return launch_gemm<EPI_C64, 2, 2>(g2, st, pl.maps + 4, num_kb, d_c64, nullptr, nullptr, 0,
+                                          w.n, scale);
+    }
+    if ((rc = launch_gemm<EPI_SPLIT_BF16, 1, 2>(g1, st, pl.maps, num_kb, nullptr, w.d1_hi, w.d1_lo,
+                                                w.np, 0, 1.f))) return rc;
+    return launch_gemm<EPI_C64, 2, 1>(g2, st, pl.maps + 4, num_kb, d_c64, nullptr, nullptr, 0, w.n,
+                                      scale);
 }
 
 static int check_ws(const void *ws, size_t bytes, int n) {
@@ -490,14 +643,12 @@ extern "C" int sosat_dft2_gemm_kind(const float *d_b, int n, float *d_B, int kin
     if (int rc = dft_kind_params(kind, n, so, si, sign, scale)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     DftWorkspace w = carve(d_workspace, n);
-    if (int rc = ensure_twiddles(w, kind, st)) return rc;
-    dim3 grid((w.np + 127) / 128, w.np);
-    prep_b_c64_kernel<<<grid, 128, 0, st>>>((const float2 *)d_b, n, w.np, w.b1_hi, w.b1_lo);
-    if (int rc = run_passes(w, st)) return rc;
-    dim3 g2((n + 127) / 128, n);
-    finish_c64_kernel<<<g2, 128, 0, st>>>(w.d2, n, w.np, (float)scale, (float2 *)d_B);
-    SOSAT_CUDA_OK(cudaGetLastError());
-    return SOSAT_OK;
+    const PlanEntry *pl = nullptr;
+    if (int rc = ensure_plan(w, kind, st, &pl)) return rc;
+    const dim3 grid(w.np / 32, w.np / 32);
+    if (int rc = launch_pdl(prep_b_c64_kernel, grid, dim3(32, 8), 0, st, 1, 1, (const float2 *)d_b, n,
+                            w.np, w.b1_hi, w.b1_lo)) return rc;
+    return run_passes(w, *pl, (float)scale, d_B, st);
 }
 
 extern "C" int sosat_dft2_gemm(const float *d_b, int n, float *d_B, void *d_workspace,
@@ -516,14 +667,17 @@ static int amp_phase_transform(const double *d_amp, const double *d_phi_deg, int
     if (int rc = dft_kind_params(kind, n, so, si, sign, scale)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     DftWorkspace w = carve(d_workspace, n);
-    if (int rc = ensure_twiddles(w, kind, st)) return rc;
-    dim3 grid((w.np + 127) / 128, w.np);
-    prep_b_a2b_kernel<<<grid, 128, 0, st>>>(d_amp, d_phi_deg, n, w.np, w.b1_hi, w.b1_lo);
-    if (int rc = run_passes(w, st)) return rc;
-    dim3 g2((n + 127) / 128, n);
-    finish_a2b_kernel<<<g2, 128, 0, st>>>(w.d2, n, w.np, scale, (double2 *)d_out, d_phase);
-    SOSAT_CUDA_OK(cudaGetLastError());
-    return SOSAT_OK;
+    const PlanEntry *pl = nullptr;
+    if (int rc = ensure_plan(w, kind, st, &pl)) return rc;
+    const dim3 grid(w.np / 32, w.np / 32);
+    if (int rc = launch_pdl(prep_b_a2b_kernel, grid, dim3(32, 8), 0, st, 1, 1, d_amp, d_phi_deg, n,
+                            w.np, w.b1_hi, w.b1_lo)) return rc;
+    if (int rc = run_passes(w, *pl, (float)scale, w.c64, st)) return rc;  // complex64 [n][n]
+    const long long n2 = (long long)n * n;
+    long long blocks = (n2 + 255) / 256;
+    if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+    return launch_pdl(finish_a2b_kernel, dim3((unsigned)blocks), dim3(256), 0, st, 1, 1,
+                      (const float2 *)w.c64, n2, (double2 *)d_out, d_phase);
 }
 
 extern "C" int sosat_a2b(const double *d_apert, const double *d_phi_deg, int n, double *d_beam,

@@ -132,7 +132,16 @@ trace_rows_kernel(RowsParams p, double *__restrict__ out, double *__restrict__ s
 }
 
 // ---- K1b: fused trace + binning ------------------------------------------------------------
-constexpr int kTile = 16;  // rays per tile edge: a CTA traces a 16 x 16 patch of the launch grid
+constexpr int kTile = 16;  // rays per tile edge in theta
+// A CTA of kBinWarps warps traces a 16 (theta) x kTileH (phi) patch of the launch grid, one 8 x 4
+// sub-patch per warp.  Fewer warps per CTA = less skew to wait for at the per-tile barrier.
+#ifndef SOSAT_BIN_WARPS
+#define SOSAT_BIN_WARPS 8
+#endif
+constexpr int kBinWarps = SOSAT_BIN_WARPS;
+constexpr int kBinThreads = 32 * kBinWarps;
+constexpr int kTileH = 2 * kBinWarps;
+constexpr int kTileMax = kTileH > kTile ? kTileH : kTile;
 
 struct BinFreq {
     float neg_c_fx[SOSAT_MAX_FREQS];  // -4 ln2 / fwhp_x^2
@@ -159,21 +168,21 @@ struct BinParams {
 // (configs[4]), one per row of 8 at 15 rays/bin.  Any key sequence is handled correctly --
 // equal bins that are not adjacent in lane order simply become separate atomics.
 template <int N32, int N64, int MINB, int GEO>
-__global__ void __launch_bounds__(256, MINB)
+__global__ void __launch_bounds__(kBinThreads, MINB * 8 / kBinWarps)
 trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict__ re,
                  float *__restrict__ im, float *__restrict__ cnt, double *__restrict__ stats) {
-    __shared__ double s_sin[2][kTile], s_cos[2][kTile], s_rx[4];
+    __shared__ double s_sin[2][kTileMax], s_cos[2][kTileMax], s_rx[4];
     // Launch-angle tables, filled once per CTA: sin/cos of  l step (l < 16),  16 j step (j < 64)
     // and  start + 1024 k step (k < 64).  The angle of grid index i = l + 16 j + 1024 k is
     // start + i step (numpy.linspace, ray_trace.py:1086-1087); its sine and cosine follow from
     // two angle additions (8 DFMA/DMUL, ~3e-16 relative) instead of an fp64 sincos per tile
     // edge on the critical path in front of the tile barrier.
     __shared__ double2 s_rot[16 + 64 + 64];
-    __shared__ float s_amp[SOSAT_MAX_FREQS][2][kTile];  // [freq][theta|phi][index in tile]
+    __shared__ float s_amp[SOSAT_MAX_FREQS][2][kTileMax];  // [freq][theta|phi][index in tile]
     // Running statistics.  fp64 sums: one shared-memory slot per thread (no conflicts, no
     // registers held across the tracer).  Counters: warp ballots added by lane 0 to packed
     // 64-bit shared counters; the rare slow-path events use plain shared atomics.
-    __shared__ double s_sum[4][256];
+    __shared__ double s_sum[4][kBinThreads];
     __shared__ unsigned long long s_valid_binned;  // n_valid | n_binned << 32
     __shared__ unsigned s_rare[2];                 // n_slow, n_bracket_fail
 
@@ -188,13 +197,15 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
         s_rare[0] = s_rare[1] = 0u;
     }
     const bool use_rot = p.n_scan <= 65536;
-    if (use_rot && tid < 16 + 64 + 64) {
-        const double a = tid < 16 ? (double)tid * p.lin_step
-                         : tid < 80 ? (double)(16 * (tid - 16)) * p.lin_step
-                                    : fma((double)(1024 * (tid - 80)), p.lin_step, p.lin_start);
-        double sn, cs;
-        sincos(a, &sn, &cs);
-        s_rot[tid] = make_double2(sn, cs);
+    if (use_rot) {
+        for (int e = tid; e < 16 + 64 + 64; e += kBinThreads) {
+            const double a = e < 16 ? (double)e * p.lin_step
+                             : e < 80 ? (double)(16 * (e - 16)) * p.lin_step
+                                      : fma((double)(1024 * (e - 80)), p.lin_step, p.lin_start);
+            double sn, cs;
+            sincos(a, &sn, &cs);
+            s_rot[e] = make_double2(sn, cs);
+        }
     }
     int acc_rx = -1;
     // tile bookkeeping in 32 bits (the host checks n_tiles < 2^31): 64-bit divisions cost
@@ -235,10 +246,11 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
             acc_rx = irx;
         }
         __syncthreads();  // previous tile done with the tables (first pass: s_rot is complete)
-        if (tid >= 2 * kTile && tid < 2 * kTile + 3) s_rx[tid - 2 * kTile] = d_rx[3 * irx + tid - 2 * kTile];
-        if (tid < 2 * kTile) {
-            const int which = tid >> 4, l = tid & (kTile - 1);  // 0: theta, 1: phi
-            const int idx = which == 0 ? tx * kTile + l : (int)p.row_begin + ty * kTile + l;
+        constexpr int kEntries = kTile + kTileH;
+        if (tid >= kEntries && tid < kEntries + 3) s_rx[tid - kEntries] = d_rx[3 * irx + tid - kEntries];
+        if (tid < kEntries) {
+            const int which = tid >= kTile, l = which ? tid - kTile : tid;  // 0: theta, 1: phi
+            const int idx = which == 0 ? tx * kTile + l : (int)p.row_begin + ty * kTileH + l;
             const int ic = idx < p.n_scan ? idx : p.n_scan - 1;
             const double a = linspace_at(p.lin_start, p.lin_stop, p.lin_step, p.n_scan, ic);
             double sn, cs;
@@ -262,7 +274,7 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
         __syncthreads();
 
         const int ith = tx * kTile + lth;
-        const int iph = ty * kTile + lph;  // relative to row_begin
+        const int iph = ty * kTileH + lph;  // relative to row_begin
         const bool live = ith < p.n_scan && iph < p.n_rows;
         const double *rx = s_rx;  // feed position [mm], staged with the tables
         RayResult r;
@@ -619,10 +631,10 @@ static void launch_bin(const BinParams &p, const double *rx, float *re, float *i
                        double *stats, cudaStream_t st) {
     int occ = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &occ, trace_bin_kernel<N32, N64, MINB, GEO>, 256, 0);
+        &occ, trace_bin_kernel<N32, N64, MINB, GEO>, kBinThreads, 0);
     const long long want = (long long)num_sms() * (occ > 0 ? occ : 1);
     const int blocks = (int)(p.n_tiles < want ? p.n_tiles : want);
-    trace_bin_kernel<N32, N64, MINB, GEO><<<blocks, 256, 0, st>>>(p, rx, re, im, cnt, stats);
+    trace_bin_kernel<N32, N64, MINB, GEO><<<blocks, kBinThreads, 0, st>>>(p, rx, re, im, cnt, stats);
 }
 
 template <int N32, int N64>
@@ -686,7 +698,7 @@ extern "C" int sosat_trace_bin(const double *d_rx, int n_rx, const sosat_freq_t 
     p.n_freq = n_freq;
     p.grid_n = binning ? grid_n : 0;
     p.tiles_x = (n_scan + kTile - 1) / kTile;
-    p.tiles_y = (p.n_rows + kTile - 1) / kTile;
+    p.tiles_y = (p.n_rows + kTileH - 1) / kTileH;
     p.n_tiles = (long long)p.tiles_x * p.tiles_y * n_rx;
     SOSAT_REQUIRE(p.n_tiles < 2147483647LL, "too many ray tiles for one launch (%lld): split the "
                   "receiver list or the row range", p.n_tiles);
