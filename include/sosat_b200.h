@@ -195,6 +195,25 @@ int sosat_a2b_host(const double *h_apert, const double *h_phi_deg, int n, double
 int sosat_nudft_direct(const float *d_xyb, int64_t n_pts, const float *d_th, int64_t n_ang,
                        double inv_lambda, float *d_B, void *stream);
 
+/* ---- on-device reductions for sweeps -------------------------- */
+/* get_beam_cent / get_fwhm / tan_og of getNearField (ray_trace.py:1604-1614, 1652-1666) from the
+ * ray table d_out ([17][n], rays ray_begin .. ray_begin+n of the n_scan^2 launch grid), for
+ * n_freq feed patterns at once (the ray geometry is frequency independent; the amplitude of
+ * ray (itheta, iphi) follows from its launch angles).  d_result (6 + 2*SOSAT_MAX_FREQS doubles):
+ *   [0] n_valid  [1] mean x_sim [cm]  [2] mean y_sim [cm]  [3..5] tan_og
+ *   [6+2f] fwhm_nf_x(f) = max|y_sim - cy|, [7+2f] fwhm_nf_y(f) = max|x_sim - cx| over rays with
+ *   a_f^2 > max(a_f^2)/2 (the reference's swapped naming kept).
+ * d_work: 8 + SOSAT_MAX_FREQS doubles of scratch. */
+int sosat_near_field_metrics(const double *d_out, int64_t n, int n_scan, int64_t ray_begin,
+                             double cone, const sosat_freq_t *h_freq, int n_freq,
+                             double *d_result, double *d_work, void *stream);
+/* The searches of ff_fwhm_est (ray_trace.py:1757-1779) on a complex64 far field d_B [n][n]:
+ * d_idx[6] = {peak row, peak column (first maximum of |B|^2, row-major), first / last column
+ * above half power in the peak row, first / last row above half power in the peak column};
+ * d_val[0] = peak |B|^2.  d_work: 8 bytes of scratch. */
+int sosat_ff_fwhm_indices(const float *d_B, int n, int *d_idx, float *d_val, void *d_work,
+                          void *stream);
+
 /* ---- measurement helpers --------------------------------------------------------------- */
 /* Dependent-free FP64 FMA throughput microkernel: returns achieved FLOP/s (2 per FMA) in
  * *flops_per_s; used by bench.py as the roofline denominator of the ray tracer because

@@ -71,6 +71,9 @@ SIGNATURES = {
                                POINTER(c_double)]),
     "sosat_nudft_direct": (c_int, [c_void_p, c_int64, c_void_p, c_int64, c_double, c_void_p,
                                    c_void_p]),
+    "sosat_near_field_metrics": (c_int, [c_void_p, c_int64, c_int, c_int64, c_double, POINTER(Freq),
+                                         c_int, c_void_p, c_void_p, c_void_p]),
+    "sosat_ff_fwhm_indices": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sosat_measure_fp64_peak": (c_int, [POINTER(c_double), POINTER(c_double)]),
 }
 

@@ -10,8 +10,14 @@ function                reference                   device code
 ``rx_to_lyot``          ray_trace.py:1070-1591      ``sosat_trace_rays``  (trace_rows_kernel)
 ``getNearField``        ray_trace.py:1594-1614      ``sosat_near_field_arrays``
 ``near_field_binned``   -- (north_star, row a7)     ``sosat_trace_bin``   (trace_bin_kernel)
-``get_fwhm`` etc.       ray_trace.py:1648-1672,     host numpy helpers (cheap reductions over the
-``ff_fwhm_est``         1757-1779                   returned arrays; out of scope for kernels)
+``get_fwhm`` etc.       ray_trace.py:1648-1672,     host numpy helpers over returned arrays (the
+``ff_fwhm_est``         1757-1779                   reference's signatures) ...
+``near_field_metrics``  same reductions, on device  ``sosat_near_field_metrics`` (reduce.cu): one
+                        for a whole frequency sweep trace, scalars per frequency come back
+``ff_fwhm_device``      ff_fwhm_est on a CUDA field ``sosat_ff_fwhm_indices`` (reduce.cu)
+``sim2d``, ``sim_data`` ray_trace.py:1675-1754      host glue (scipy), kept so the notebooks'
+                                                    scattered->grid route still runs end to end;
+                                                    the device route is near_field_binned
 ======================  ==========================  ==========================================
 
 ``plot`` / ``col`` arguments are accepted and ignored (plotting is out of scope).
@@ -27,6 +33,7 @@ from . import _lib, geometry
 
 __all__ = ["rx_to_lyot", "getNearField", "get_sim", "get_beam_cent", "get_fwhm",
            "get_angle_out", "ff_fwhm_est", "near_field_binned", "trace_stats",
+           "near_field_metrics", "ff_fwhm_device", "sim2d", "sim_data",
            "SimOutput", "BinnedField"]
 
 
@@ -166,6 +173,123 @@ def ff_fwhm_est(beam_fft, x_ang, y_ang):
     y = abs(a)[:, indx[1][0]] / np.max(abs(a))
     fwhm2 = abs(x[np.where(y > 0.5)][0] - x[np.where(y > 0.5)][-1])
     return (fwhm1 + fwhm2) / 2
+
+
+# --- on-device reductions for sweeps -------------------------------
+def near_field_metrics(tele_geo, rx, freqs: Optional[Sequence] = None):
+    """``get_beam_cent`` / ``get_fwhm`` / ``get_angle_out`` of ``getNearField(tele_geo, rx)``
+    evaluated on the device for a whole list of frequencies with ONE trace (the ray geometry is
+    frequency independent): the reference's sat_reqs sweep re-traces every frequency.
+
+    ``freqs``: ``None`` -> the frequency set on ``tele_geo``; else a sequence of
+    ``(k, th_fwhp_x, th_fwhp_y)``.  Returns a dict: ``n_valid``, ``beam_cent`` [cm] (2),
+    ``tan_og`` (3), ``angle_out`` [deg] (2), ``fwhm`` [cm] ``[F, 2]`` in the order
+    ``get_fwhm`` returns (its swapped x/y naming kept)."""
+    lib = _lib.require_gpu()
+    torch = _torch()
+    out, _ = _trace_device(rx, tele_geo)
+    specs = list(freqs) if freqs is not None else [
+        (tele_geo.k, tele_geo.th_fwhp_x, tele_geo.th_fwhp_y)]
+    n_scan = int(tele_geo.n_scan)
+    res_all = []
+    head = None
+    for f0 in range(0, len(specs), _lib.MAX_FREQS):
+        chunk = geometry.make_freqs(specs[f0:f0 + _lib.MAX_FREQS])
+        result = torch.empty(6 + 2 * _lib.MAX_FREQS, dtype=torch.float64, device="cuda")
+        work = torch.empty(8 + _lib.MAX_FREQS, dtype=torch.float64, device="cuda")
+        _lib.check(lib.sosat_near_field_metrics(
+            ctypes.c_void_p(out.data_ptr()), out.shape[1], n_scan, 0, geometry.ot_geo.CONE_HALF_ANGLE,
+            chunk, len(chunk), ctypes.c_void_p(result.data_ptr()), ctypes.c_void_p(work.data_ptr()),
+            _stream(torch)))
+        h = result.cpu().numpy()
+        head = h[:6]
+        res_all.append(h[6:6 + 2 * len(chunk)].reshape(-1, 2))
+    tan_og = head[3:6].copy()
+    sb = SimOutput(None, None, None, None, tan_og)
+    return {"n_valid": int(head[0]), "beam_cent": head[1:3].copy(), "tan_og": tan_og,
+            "angle_out": np.array(get_angle_out(sb)), "fwhm": np.concatenate(res_all, axis=0)}
+
+
+def ff_fwhm_device(beam_fft, x_ang, y_ang):
+    """``ff_fwhm_est`` (ray_trace.py:1757-1779) for a far field that lives on the GPU
+    (``far_field(..., device=True)``): the peak and half-power searches run on the device and
+    only six indices come back.  ``x_ang`` / ``y_ang``: the label grids of
+    ``coords_spat_to_ang`` (host arrays)."""
+    lib = _lib.require_gpu()
+    torch = _torch()
+    B = beam_fft if not isinstance(beam_fft, np.ndarray) else torch.from_numpy(
+        np.ascontiguousarray(beam_fft.astype(np.complex64))).to("cuda")
+    B = B.to(device="cuda", dtype=torch.complex64).contiguous()
+    n = B.shape[0]
+    idx = torch.empty(6, dtype=torch.int32, device="cuda")
+    val = torch.empty(1, dtype=torch.float32, device="cuda")
+    work = torch.empty(1, dtype=torch.int64, device="cuda")
+    _lib.check(lib.sosat_ff_fwhm_indices(ctypes.c_void_p(B.data_ptr()), n,
+                                         ctypes.c_void_p(idx.data_ptr()),
+                                         ctypes.c_void_p(val.data_ptr()),
+                                         ctypes.c_void_p(work.data_ptr()), _stream(torch)))
+    pr, pc, c0, c1, r0, r1 = (int(v) for v in idx.cpu().numpy())
+    x_out, y_out = y_ang, x_ang  # the reference's swap, ray_trace.py:1759-1760
+    scale = 60 * 180 / np.pi
+    fwhm1 = abs(y_out[pr, c0] * scale - y_out[pr, c1] * scale)
+    fwhm2 = abs(x_out[r0, pc] * scale - x_out[r1, pc] * scale)
+    return (fwhm1 + fwhm2) / 2
+
+
+# --- the notebooks' scattered -> grid glue (SURVEY section 8 row f1), host side -----------------
+class _Grid2d:
+    def __init__(self, x_sim, y_sim, a_sim, p_sim):
+        self.a_sim, self.p_sim, self.x_sim, self.y_sim = a_sim, p_sim, x_sim, y_sim
+
+
+def sim2d(sb):
+    """Cubic ``griddata`` of amplitude and phase on a 100 x 100 grid spanning the valid rays within
+    21 cm of the beam centre, zero beyond 20 cm (ray_trace.py:1675-1717).  Host glue exactly as
+    in the reference (scipy); on the device the same role is played by ``near_field_binned``."""
+    from scipy.interpolate import griddata
+    x_sim, y_sim = sb.x_sim, sb.y_sim
+    beam_cent = get_beam_cent(sb)
+    indx_xy = np.where((np.isnan(x_sim) == False) & (np.isnan(y_sim) == False)  # noqa: E712
+                       & ((x_sim - beam_cent[0]) ** 2 + (y_sim - beam_cent[1]) ** 2 <= 21.0 ** 2))
+    grid_x, grid_y = np.mgrid[np.min(x_sim[indx_xy]):np.max(x_sim[indx_xy]):100j,
+                              np.min(y_sim[indx_xy]):np.max(y_sim[indx_xy]):100j]
+    points = np.array([x_sim[indx_xy], y_sim[indx_xy]]).T
+    outside = (grid_x - beam_cent[0]) ** 2 + (grid_y - beam_cent[1]) ** 2 >= 20 ** 2
+
+    def grid(values):
+        g = griddata(points, np.array(values[indx_xy]).T, (grid_x, grid_y), method="cubic")
+        g = np.where(outside, 0, g)
+        return np.where(np.isnan(g), 0, g)
+
+    return _Grid2d(grid_x, grid_y, grid(sb.a_sim), grid(sb.p_sim))
+
+
+class _StageData:
+    def __init__(self, x_data, y_data, a_data, p_data):
+        self.a_data, self.p_data, self.x_data, self.y_data = a_data, p_data, x_data, y_data
+
+
+def sim_data(sb_in, STAGE_RANGE, STEP):
+    """Resample the ``sim2d`` grid onto the holography stage grid (ray_trace.py:1720-1754).
+    The reference calls ``scipy.interpolate.interp2d(kind='cubic')``, removed in SciPy 1.14;
+    ``RectBivariateSpline(kx=ky=3, s=0)`` is the same interpolating bicubic spline."""
+    from scipy.interpolate import RectBivariateSpline
+    beam_final = sb_in.a_sim.T * np.exp(complex(0, 1) * sb_in.p_sim.T)
+    x_interp = sb_in.x_sim[:, 0]
+    y_interp = sb_in.y_sim[0, :]
+
+    def interp2d(z):
+        spl = RectBivariateSpline(x_interp, y_interp, np.asarray(z).T, kx=3, ky=3, s=0)
+        return lambda xn, yn: spl(xn, yn).T
+
+    func_beam = interp2d(np.abs(beam_final) / np.max(np.abs(beam_final)))
+    func_phase = interp2d(np.arctan2(np.imag(beam_final), np.real(beam_final)))
+    x_data = np.arange(-STAGE_RANGE / 2, STAGE_RANGE / 2, STEP)
+    y_data = np.arange(-STAGE_RANGE / 2, STAGE_RANGE / 2, STEP)
+    beam_data = func_beam(x_data, y_data)
+    phase_data = func_phase(x_data, y_data)
+    x_data, y_data = np.meshgrid(x_data, y_data)
+    return _StageData(x_data, y_data, beam_data / np.max(beam_data), phase_data)
 
 
 # --- fused trace + binning (north_star) -------------------------------------------------------

@@ -265,3 +265,26 @@ def test_transform_kind_argument_errors(mods):
         mods["oa"].beam_convolve(np.zeros((4, 4)), np.zeros((4, 4)), np.zeros((4, 5)), 1, 2, 0)
     with pytest.raises(ValueError):
         mods["oa"].b2a(np.zeros((4, 5)), np.zeros((4, 5)))
+
+
+def test_ff_fwhm_device_matches_host_estimator(mods):
+    """Row f2: the peak / half-power searches of ff_fwhm_est on the device, on the reference's
+    240^2 and 1000^2-style fields and on a field with an off-centre peak."""
+    oa, rt, torch = mods["oa"], mods["rt"], mods["torch"]
+    g = golden("farfield_cfg2_240.npz")
+    n = g["beam_fft"].shape[0]
+    x_ang, y_ang = np.meshgrid(g["x_ang_row"], g["y_ang_col"])
+    want = rt.ff_fwhm_est(g["beam_fft"], x_ang, y_ang)
+    assert abs(rt.ff_fwhm_device(g["beam_fft"], x_ang, y_ang) - want) < 1e-9
+    assert "%.2f" % want == "21.50"
+    # device-resident field straight from far_field(..., device=True), peak away from the centre
+    m = 300
+    x = (np.arange(m) - m // 2) * 0.3
+    X, Y = np.meshgrid(x, x)
+    b = np.exp(-(X ** 2 + Y ** 2) / (2 * 6.0 ** 2)) * np.exp(1j * (0.35 * X - 0.2 * Y))
+    B = oa.far_field(b, device=True)
+    xa, ya = oa.coords_spat_to_ang(X / 1e2, Y / 1e2, 90.0)
+    Bh = B.cpu().numpy()
+    pk = np.unravel_index(np.argmax(np.abs(Bh)), Bh.shape)
+    assert pk != (m // 2, m // 2)
+    assert abs(rt.ff_fwhm_device(B, xa, ya) - rt.ff_fwhm_est(Bh, xa, ya)) < 1e-9

@@ -123,9 +123,38 @@ def test_reqs_frequency_sweep_known_answers(mods, feed_table):
 def test_all_newton_schedules_agree(mods, monkeypatch):
     g = golden("trace_cfg1_n40_90ghz.npz")
     t = tele_geo_from_golden(g)
-    for var in (0, 2, 5, 6):
+    for var in (0, 2, 6):  # 0 + 5, 3 + 2, 2 + 2 (default) fp32 + fp64 Newton steps
         monkeypatch.setenv("SOSAT_TRACE_VARIANT", str(var))
         _check_rows(mods["rt"].rx_to_lyot([0, 0, 0], t), g["out"], float(g["k"]))
+
+
+@pytest.mark.parametrize("geo", [1, 2])
+def test_other_geometry_builds_agree(mods, monkeypatch, geo):
+    """The kernels are built three times (trace_device.cuh): 0 = SAT prescription (division-free
+    conic sag, only lens 2b refined), 1 = any geometry (every surface refined, conic-edge test
+    everywhere), 2 = near-parabolic surfaces (u c'/(1+s) form).  SOSAT_TRACE_GEO forces builds 1
+    and 2 on the SAT geometry: same goldens, rows and fused binning."""
+    rt, oracle = mods["rt"], mods["oracle"]
+    monkeypatch.setenv("SOSAT_TRACE_GEO", str(geo))
+    rt._geom_cache.clear()  # the build is chosen when the geometry is uploaded
+    try:
+        g = golden("trace_cfg1_n60_106ghz.npz")
+        t = tele_geo_from_golden(g)
+        _check_rows(rt.rx_to_lyot([0, 0, 0], t), g["out"], float(g["k"]))
+        g4 = golden("trace_cfg4_offaxis_n32_90ghz.npz")
+        t4 = tele_geo_from_golden(g4)
+        for i in (1, 3):
+            _check_rows(rt.rx_to_lyot(list(g4["rx"][i]), t4), g4["out"][i], float(g4["k"]))
+        t.n_scan = 300
+        ref = oracle.rx_to_lyot([30, 0, -40], t)
+        re, im, cnt, sums = oracle.bin_near_field(ref, float(g["k"]), 48, 420.0, 0.0)
+        bf = rt.near_field_binned(t, [30, 0, -40], grid_n=48, extent_cm=42.0, keep_sums=True)
+        assert np.abs(bf.count[0] - cnt).sum() <= 2
+        assert np.abs(bf.re[0, 0] - re).max() < 2e-3 * np.abs(re).max()
+        assert int(bf.stats[0][0]) == sums["n_valid"]
+    finally:
+        monkeypatch.delenv("SOSAT_TRACE_GEO")
+        rt._geom_cache.clear()
 
 
 @pytest.mark.parametrize("rx", [[0, 0, 0], [150, 0, 0], [-120, 0, 80], [0, 0, 170], [60, 0, -90]])
@@ -376,3 +405,66 @@ def test_cfg4_focal_plane_receiver_sweep(mods):
         assert (~ok).sum() <= 2
         s = np.abs(re + 1j * im).max()
         assert np.abs(bf.re[i, 0] - re)[ok].max() < 1e-5 * s
+
+
+def test_near_field_metrics_one_trace_for_the_whole_sweep(mods, feed_table):
+    """Row f2: sat_reqs.ipynb's FWHM-vs-frequency table (reference golden, one trace per
+    frequency there) from ONE trace and on-device reductions."""
+    g = golden("reqs_cfg3_n150.npz")
+    rt, ot_geo, geometry = mods["rt"], mods["ot_geo"], mods["geometry"]
+    t = ot_geo.SatGeo()
+    t.n_scan = 150
+    t.y_source = ot_geo.y_lyot + 200
+    specs = geometry.freq_specs_from_table([float(f) for f in g["freqs"]], feed_table)
+    t.k, t.th_fwhp_x, t.th_fwhp_y = specs[0]
+    m = rt.near_field_metrics(t, [0, 0, 0], specs)
+    assert m["n_valid"] == 15312 and (g["n_valid"] == 15312).all()
+    assert m["fwhm"].shape == (len(specs), 2)
+    assert np.allclose(m["fwhm"], g["fwhm"], atol=1e-6)
+    assert np.allclose(m["beam_cent"], g["beam_cent"][0], atol=1e-7)
+    # and against the host helpers on the arrays of the drop-in getNearField, off axis
+    t.n_scan = 64
+    sb = rt.getNearField(t, [60, 0, -90])
+    m = rt.near_field_metrics(t, [60, 0, -90])
+    assert m["n_valid"] == len(sb.a_sim)
+    assert np.allclose(m["fwhm"][0], rt.get_fwhm(sb), atol=1e-9)
+    assert np.allclose(m["beam_cent"], rt.get_beam_cent(sb), atol=1e-9)
+    assert np.allclose(m["angle_out"], rt.get_angle_out(sb), atol=1e-9)
+    assert np.allclose(m["tan_og"], sb.tan_og, atol=1e-12)
+
+
+def test_notebook_scattered_grid_route_end_to_end(mods):
+    """Row f1: sat_farfield.ipynb cells 1-6 with the GPU tracer and the GPU a2b around the
+    reference's host glue (sim2d / sim_data): the 100 x 100 grid the reference produced, its 240^2
+    far field, and 'Estimated FWHM: 21.50 arcmin'.
+
+    The glue itself is ill-conditioned: scipy's cubic griddata triangulates the nearly regular
+    ray positions, and perturbing them by 1e-9 cm (CPU experiment with the oracle's rays, four
+    seeds) moves the interpolated amplitude grid by 3e-5, the wrapped-phase grid by 5e-3 rad and
+    the far field by 0.6-1.1e-4 of peak, while the FWHM stays 21.5039.  The bounds below are that
+    conditioning, not the kernels' accuracy (rays: 1e-8 mm, a2b: 5e-6 of peak)."""
+    g = golden("farfield_cfg2_240.npz")
+    rt, oa, ot_geo = mods["rt"], mods["oa"], mods["ot_geo"]
+    table = golden("feedhorn_fwhm.npz")["table"]
+    t = ot_geo.SatGeo()
+    t.n_scan = 100
+    t.y_source = ot_geo.y_lyot + 300
+    t.lambda_ = float(g["lambda_"])
+    t.k = 2 * np.pi / t.lambda_
+    row = int(g["table_row"])
+    t.th_fwhp_x = np.deg2rad(table[np.where(table[:, 0] == row), 1])
+    t.th_fwhp_y = np.deg2rad(table[np.where(table[:, 0] == row), 2])
+    sb = rt.getNearField(t, [0, 0, 0], plot=False)
+    sb2 = rt.sim2d(sb)
+    assert np.abs(sb2.x_sim - g["sb2_x"]).max() < 1e-6 and np.abs(sb2.y_sim - g["sb2_y"]).max() < 1e-6
+    assert np.abs(sb2.a_sim - g["sb2_a"]).max() < 1e-3
+    d = rt.sim_data(sb2, 80, 2)
+    assert np.abs(d.a_data - g["a_data"]).max() < 1e-4
+    x_new, y_new, beam_data = oa.zero_pad(d.x_data, d.y_data, d.a_data, 100)
+    x_data, y_data, phase_data = oa.zero_pad(d.x_data, d.y_data, d.p_data, 100)
+    beam_fft, phase_fft = oa.a2b(beam_data, np.rad2deg(phase_data))
+    assert np.abs(beam_fft - g["beam_fft"]).max() < 1e-3 * np.abs(g["beam_fft"]).max()
+    x_ang, y_ang = oa.coords_spat_to_ang(x_data / 1e2, y_data / 1e2, oa.m_to_ghz(t.lambda_))
+    assert abs(rt.ff_fwhm_est(beam_fft, x_ang, y_ang) - float(g["fwhm"])) < 1e-3
+    assert "%.2f" % rt.ff_fwhm_est(beam_fft, x_ang, y_ang) == "21.50"
+    assert "%.2f" % rt.ff_fwhm_device(beam_fft, x_ang, y_ang) == "21.50"

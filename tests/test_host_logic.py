@@ -149,3 +149,16 @@ def test_ray_sharded_near_field_world2_gloo():
         assert np.allclose(s[:, [0, 7]], stats.numpy()[:, [0, 7]])
         assert np.allclose(s[:, 1], stats.numpy()[:, 1], rtol=1e-12)
         assert sweep == [(0, 0), (1, 1), (2, 0), (3, 1), (4, 0)]
+
+
+def test_sim_data_glue_matches_reference_golden():
+    """Row f1 host glue: sim_data on the 100 x 100 grid the reference's sim2d produced gives the
+    reference's stage-grid arrays (RectBivariateSpline stands in for the removed interp2d)."""
+    from types import SimpleNamespace
+    g = golden("farfield_cfg2_240.npz")
+    sb2 = SimpleNamespace(a_sim=g["sb2_a"], p_sim=g["sb2_p"], x_sim=g["sb2_x"], y_sim=g["sb2_y"])
+    d = ray_trace.sim_data(sb2, 80, 2)
+    assert d.a_data.shape == g["a_data"].shape
+    assert np.abs(d.a_data - g["a_data"]).max() < 1e-12
+    assert np.abs(d.p_data - g["p_data"]).max() < 1e-12
+    assert np.array_equal(d.x_data, g["x_data"]) and np.array_equal(d.y_data, g["y_data"])
