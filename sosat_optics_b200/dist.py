@@ -50,20 +50,37 @@ def world_info(group=None) -> Tuple[int, int]:
     return 0, 1
 
 
-def reduce_bins(re, im, cnt, stats, group=None):
-    """All-reduce(sum) of the near-field accumulators in place.  The three float32 planes are
-    packed into one flat buffer so that the exchange is a single collective (50 MB at 2048^2);
-    the fp64 statistics follow in a second, tiny one."""
+def alloc_planes(n_rx: int, n_freq: int, grid_n: int, device="cuda"):
+    """Accumulator planes ``(re, im, cnt)`` as views of ONE flat float32 buffer (returned last),
+    so that :func:`reduce_bins` can all-reduce them in place with a single collective."""
+    import torch
+    n_ri = n_rx * n_freq * grid_n * grid_n
+    n_c = n_rx * grid_n * grid_n
+    flat = torch.zeros(2 * n_ri + n_c, dtype=torch.float32, device=device)
+    re = flat[:n_ri].view(n_rx, n_freq, grid_n, grid_n)
+    im = flat[n_ri:2 * n_ri].view(n_rx, n_freq, grid_n, grid_n)
+    cnt = flat[2 * n_ri:].view(n_rx, grid_n, grid_n)
+    return re, im, cnt, flat
+
+
+def reduce_bins(re, im, cnt, stats, group=None, flat=None):
+    """All-reduce(sum) of the near-field accumulators in place: one collective over the three
+    float32 planes (50 MB at 2048^2) and a second, tiny one over the fp64 statistics.  Pass the
+    ``flat`` buffer of :func:`alloc_planes` to reduce the planes where they lie; otherwise they
+    are packed into a temporary and copied back."""
     dist = _dist()
     if not (dist.is_available() and dist.is_initialized()) or dist.get_world_size(group) == 1:
         return re, im, cnt, stats
     import torch
-    flat = torch.cat([re.reshape(-1), im.reshape(-1), cnt.reshape(-1)])
-    dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
-    n_re, n_im = re.numel(), im.numel()
-    re.copy_(flat[:n_re].view_as(re))
-    im.copy_(flat[n_re:n_re + n_im].view_as(im))
-    cnt.copy_(flat[n_re + n_im:].view_as(cnt))
+    if flat is not None:
+        dist.all_reduce(flat, op=dist.ReduceOp.SUM, group=group)
+    else:
+        packed = torch.cat([re.reshape(-1), im.reshape(-1), cnt.reshape(-1)])
+        dist.all_reduce(packed, op=dist.ReduceOp.SUM, group=group)
+        n_re, n_im = re.numel(), im.numel()
+        re.copy_(packed[:n_re].view_as(re))
+        im.copy_(packed[n_re:n_re + n_im].view_as(im))
+        cnt.copy_(packed[n_re + n_im:].view_as(cnt))
     dist.all_reduce(stats, op=dist.ReduceOp.SUM, group=group)
     return re, im, cnt, stats
 
