@@ -84,20 +84,23 @@ class ClockSampler(threading.Thread):
         except Exception:
             pass
 
+    def sample(self):
+        try:
+            self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
+            try:
+                r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
+            except Exception:
+                r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
+            for bit, name in self.REASONS.items():
+                if r & bit:
+                    self.reasons.add(name)
+        except Exception:
+            pass
+
     def run(self):
         while self.ok and not self._stop_evt.is_set():
-            try:
-                self.samples.append(self.nv.nvmlDeviceGetClockInfo(self.h, self.nv.NVML_CLOCK_SM))
-                try:
-                    r = self.nv.nvmlDeviceGetCurrentClocksEventReasons(self.h)
-                except Exception:
-                    r = self.nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h)
-                for bit, name in self.REASONS.items():
-                    if r & bit:
-                        self.reasons.add(name)
-            except Exception:
-                pass
-            time.sleep(0.05)
+            self.sample()
+            time.sleep(0.005)  # short timed regions (8 GPUs: 40 ms) still get several samples
 
     def result(self):
         self._stop_evt.set()
@@ -193,6 +196,7 @@ def other_configs(torch, ot_geo, opt_analyze, ray_trace, table):
     out = {}
     # cfg 0: sat_nearfield notebook default through the drop-in call (host arrays in and out)
     t = _tele_geo(ot_geo, opt_analyze, table, 60)
+    ray_trace.getNearField(t, [0, 0, 0])  # module load / first-launch cost stays outside
     t0 = time.perf_counter()
     for _ in range(5):
         ray_trace.getNearField(t, [0, 0, 0])
