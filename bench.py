@@ -402,6 +402,40 @@ def run_ours(args):
         "note": "16 N^3 algorithmic flop; the bf16x3 split executes 3x that on the tensor pipe",
     }
 
+    # ---- K3: direct-sum far field on irregular samples (SFU bound: 2 MUFU per point-angle pair) ----
+    if world == 1:
+        import ctypes
+        n_pts, n_ang = 100_000, 256 * 256
+        gen = torch.Generator(device="cuda").manual_seed(3)
+        pts = torch.rand((n_pts, 4), device="cuda", generator=gen) - 0.5
+        th = (torch.rand((n_ang, 2), device="cuda", generator=gen) - 0.5) * 0.05
+        outB = torch.empty((n_ang, 2), dtype=torch.float32, device="cuda")
+        st = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+        def nudft():
+            _lib.check(lib.sosat_nudft_direct(ctypes.c_void_p(pts.data_ptr()), n_pts,
+                                              ctypes.c_void_p(th.data_ptr()), n_ang, 1.0 / 3.33e-3,
+                                              ctypes.c_void_p(outB.data_ptr()), st))
+        nudft()
+        torch.cuda.synchronize()
+        ts = []
+        for _ in range(5):
+            a, b_ = ev(), ev()
+            a.record()
+            nudft()
+            b_.record()
+            torch.cuda.synchronize()
+            ts.append(a.elapsed_time(b_))
+        pairs = n_pts * n_ang / (min(ts) * 1e-3)
+        sm_count = torch.cuda.get_device_properties(local).multi_processor_count
+        mufu_peak = 16.0 * sm_count * (clocks.get("sm_mhz") or 1965.0) * 1e6  # MUFU lanes/clk/SM
+        farfield["nudft_direct"] = {
+            "points": n_pts, "angles": n_ang, "ms_best": min(ts), "pairs_per_s": pairs,
+            "bound": "sfu", "achieved_mufu_per_s": 2 * pairs, "peak_mufu_per_s": mufu_peak,
+            "frac": 2 * pairs / mufu_peak,
+            "note": "2 MUFU (sin, cos) + ~10 FP32 per pair; 16 MUFU lanes/clk/SM (measured: "
+                    "8 cycles per warp instruction and SMSP, scripts/dp_latency.cu)"}
+
     # ---- the other BASELINE.json configs, one line each (N = 1 only; not the headline) ----
     configs = None
     if world == 1:

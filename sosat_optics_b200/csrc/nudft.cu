@@ -40,7 +40,9 @@ nudft_kernel(const float4 *__restrict__ xyb, long long n_pts, const float2 *__re
 #pragma unroll
             for (int q = 0; q < kNuPerThread; ++q) {
                 float cyc = fmaf(pt.x, tx[q], pt.y * ty[q]);
-                cyc -= rintf(cyc);
+                // cyc -= rint(cyc) with the 1.5 * 2^23 trick: two FADDs on the FMA pipe instead
+                // of an FRND on the XU pipe that the two MUFUs already saturate (|cyc| < 2^22)
+                cyc -= __fadd_rn(__fadd_rn(cyc, 12582912.f), -12582912.f);
                 const float ang = cyc * 6.2831853071795865f;
                 const float sn = __sinf(ang), cs = __cosf(ang);
                 ar[q] = fmaf(pt.z, cs, fmaf(-pt.w, sn, ar[q]));

@@ -353,7 +353,9 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
             if (bin >= 0) {
                 const float a = s_amp[f][0][lth] * s_amp[f][1][lph];
                 double cyc = dopl * g_freq.kk[f];
-                cyc -= rint(cyc);  // phase reduced to [-1/2, 1/2] cycles in fp64
+                // phase reduced to [-1/2, 1/2] cycles in fp64: cyc - rint(cyc) with the 1.5 * 2^52
+                // trick (two DADDs; an FRND.F64 would go through the XU pipe)
+                cyc -= __dadd_rn(__dadd_rn(cyc, 6755399441055744.0), -6755399441055744.0);
                 float sn, cs;
                 __sincosf(6.2831853071795865f * (float)cyc, &sn, &cs);  // SFU, |err| < 1e-6
                 vre = a * cs;
