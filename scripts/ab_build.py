@@ -1,5 +1,6 @@
 """Build experimental variants of libsosat_b200.so with extra nvcc flags into bin_tmp/ for A/B
 timing on the GPU box:   python scripts/ab_build.py name "-DFOO=1 -DBAR=2" [name2 "flags2" ...]
+(AB_SOURCES=dft_gemm.cu,trace.cu selects which sources are recompiled with the flags; default trace.cu)
 Run with SOSAT_LIB=bin_tmp/lib_<name>.so python scripts/prof_trace.py"""
 import os
 import subprocess
@@ -17,7 +18,7 @@ for name, flags in zip(args[0::2], args[1::2]):
     objs = []
     for src in B.SOURCES:
         o = os.path.join(out_dir, f"{name}_{src.replace('.cu', '.o')}")
-        if src != "trace.cu" and os.path.exists(os.path.join(B.CSRC, "_obj", src.replace(".cu", ".o"))):
+        if src not in os.environ.get("AB_SOURCES", "trace.cu").split(",") and os.path.exists(os.path.join(B.CSRC, "_obj", src.replace(".cu", ".o"))):
             objs.append(os.path.join(B.CSRC, "_obj", src.replace(".cu", ".o")))
             continue
         objs.append(o)

@@ -33,9 +33,17 @@
 
 namespace sosat {
 
-constexpr int BM = 128, BN = 128, BK = 64;  // CTA tile; BK * 2 B = one 128 B swizzle row
+// CTA tile 128 x 128; a k-block is one swizzle row: BK = 64 (128 B swizzle, 3 stages of 64 KB) or
+// BK = 32 (64 B swizzle, 6 stages of 32 KB: the same 192 KB in flight in finer units, so that a
+// freed stage leaves 5/6 instead of 2/3 of the ring to cover the refill latency).
+#ifndef SOSAT_GEMM_BK
+#define SOSAT_GEMM_BK 64
+#endif
+constexpr int BM = 128, BN = 128, BK = SOSAT_GEMM_BK;
+static_assert(BK == 64 || BK == 32, "BK must be one 128 B or 64 B swizzle row of bf16");
 constexpr int UMMA_K = 16;
-constexpr int kStages = 3;
+constexpr int kStages = BK == 64 ? 3 : 6;
+constexpr int kRowBytes = BK * 2;                    // one K-major row of a tile
 constexpr int kTileBytes = BM * BK * 2;              // 16 KiB per operand tile
 constexpr int kStageBytes = 4 * kTileBytes;          // A_hi, A_lo, B_hi, B_lo
 constexpr int kGemmSmem = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
@@ -129,11 +137,13 @@ __device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&v)[32]) {
     asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// K-major, 128B-swizzled operand tile: rows of 128 B, 8-row swizzle atoms 1024 B apart
-// (SBO = 1024 B; LBO unused for swizzled K-major layouts and set to 1), descriptor version 1.
+// K-major, swizzled operand tile: rows of kRowBytes (128 B or 64 B = the swizzle span), 8-row
+// swizzle atoms 8 * kRowBytes apart (SBO; LBO unused for swizzled K-major layouts and set to 1),
+// descriptor version 1, layout type 2 = SWIZZLE_128B / 4 = SWIZZLE_64B.
 __device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
-    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) | ((uint64_t)(1024 >> 4) << 32) |
-           (1ull << 46) | (2ull << 61);
+    return (uint64_t)((smem_addr >> 4) & 0x3FFF) | (1ull << 16) |
+           ((uint64_t)((8 * kRowBytes) >> 4) << 32) | (1ull << 46) |
+           ((uint64_t)(BK == 64 ? 2 : 4) << 61);
 }
 // kind::f16 instruction descriptor: D = f32, A = B = bf16, both K-major, M x N tile.
 __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
@@ -207,7 +217,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
             const uint32_t full = full0 + 8 * s;
             const uint32_t base = smem_u32(smem + s * kStageBytes);
             mbar_expect_tx(full, kStageBytes);  // own slices + the peers' multicasts
-            const uint32_t da = base + (uint32_t)(cx * kRowsA * 128), db = base + (uint32_t)(cy * kRowsB * 128);
+            const uint32_t da = base + (uint32_t)(cx * kRowsA * kRowBytes), db = base + (uint32_t)(cy * kRowsB * kRowBytes);
             if (CX > 1) {
                 tma_load_2d_mc(da + 0 * kTileBytes, &map_a_hi, full, kb * BK, m0 + cx * kRowsA, mask_a);
                 tma_load_2d_mc(da + 1 * kTileBytes, &map_a_lo, full, kb * BK, m0 + cx * kRowsA, mask_a);
@@ -474,7 +484,8 @@ static int make_map(CUtensorMap *m, const void *ptr, uint64_t rows, uint64_t col
     const cuuint32_t box[2] = {BK, (cuuint32_t)box_rows};
     const cuuint32_t estr[2] = {1, 1};
     CUresult r = fn(m, CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, (void *)ptr, dims, strides, box, estr,
-                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE,
+                    BK == 64 ? CU_TENSOR_MAP_SWIZZLE_128B : CU_TENSOR_MAP_SWIZZLE_64B,
                     CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
     if (r != CUDA_SUCCESS) return set_error(SOSAT_ERR_CUDA, "cuTensorMapEncodeTiled failed (%d)", (int)r);
     return 0;
