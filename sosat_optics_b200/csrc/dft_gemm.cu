@@ -27,6 +27,7 @@
 #include <cuda.h>
 #include <cuda_bf16.h>
 
+#include <cstdlib>
 #include <cstring>
 
 #include "common.cuh"
@@ -153,6 +154,62 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
 
 enum { EPI_C64 = 0, EPI_SPLIT_BF16 = 1 };
 
+// TMEM accumulator tile (128 lanes x 128 fp32 columns) -> registers -> global.
+//   EPI_SPLIT_BF16: bf16 hi/lo planes d_hi/d_lo [M][ldd]
+//   EPI_C64:        times scale -> d_c64 [n_valid][2 n_valid] floats = complex64 [n][n]
+template <int EPI, int NCOLS = BN>
+__device__ __forceinline__ void gemm_epilogue(uint32_t tmem_base, int m0, int n0, int warp, int lane,
+                                              float *__restrict__ d_c64,
+                                              __nv_bfloat16 *__restrict__ d_hi,
+                                              __nv_bfloat16 *__restrict__ d_lo, int ldd, int n_valid,
+                                              float scale) {
+    const int row = m0 + warp * 32 + lane;  // TMEM lane == accumulator row
+#pragma unroll 1
+    for (int c = 0; c < NCOLS / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
+        if (EPI == EPI_C64) {
+            // row = l, columns = (k, re|im) interleaved: the complex64 row of B, n_valid wide
+            const int j0 = n0 + c * 32;
+            if (row < n_valid && j0 < 2 * n_valid) {
+                float *dst = d_c64 + (size_t)row * (2 * (size_t)n_valid) + j0;
+                if ((n_valid & 1) == 0 && j0 + 32 <= 2 * n_valid) {
+#pragma unroll
+                    for (int q = 0; q < 8; ++q)
+                        ((float4 *)dst)[q] = make_float4(scale * __uint_as_float(v[4 * q]),
+                                                         scale * __uint_as_float(v[4 * q + 1]),
+                                                         scale * __uint_as_float(v[4 * q + 2]),
+                                                         scale * __uint_as_float(v[4 * q + 3]));
+                } else {
+#pragma unroll
+                    for (int q = 0; q < 16; ++q)
+                        if (j0 + 2 * q + 1 < 2 * n_valid)
+                            ((float2 *)dst)[q] = make_float2(scale * __uint_as_float(v[2 * q]),
+                                                             scale * __uint_as_float(v[2 * q + 1]));
+                }
+            }
+        } else {
+            const size_t off = (size_t)row * ldd + n0 + c * 32;
+            uint32_t hi[16], lo[16];
+#pragma unroll
+            for (int q = 0; q < 16; ++q) {
+                const float x0 = __uint_as_float(v[2 * q]), x1 = __uint_as_float(v[2 * q + 1]);
+                const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
+                const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
+                const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
+                hi[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
+                lo[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
+            }
+            uint4 *dh = (uint4 *)(d_hi + off), *dl = (uint4 *)(d_lo + off);
+#pragma unroll
+            for (int q = 0; q < 4; ++q) {
+                dh[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
+                dl[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
+            }
+        }
+    }
+}
+
 // D[M][N] (+)= A_hi B_hi^T + A_hi B_lo^T + A_lo B_hi^T ; one 128 x 128 tile per CTA, CTAs in
 // CX x CY clusters (cluster x = blockIdx.x = N tiles, y = M tiles).
 // warp 0 lane 0: TMA producer.  warp 1 lane 0: MMA issuer.  all 4 warps: epilogue.
@@ -264,51 +321,7 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     // ---- epilogue: TMEM -> registers -> global ----
     mbar_wait(accum_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    const int row = m0 + warp * 32 + lane;  // TMEM lane == accumulator row
-#pragma unroll 1
-    for (int c = 0; c < BN / 32; ++c) {
-        uint32_t v[32];
-        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
-        if (EPI == EPI_C64) {
-            // row = l, columns = (k, re|im) interleaved: the complex64 row of B, n_valid wide
-            const int j0 = n0 + c * 32;
-            if (row < n_valid && j0 < 2 * n_valid) {
-                float *dst = d_c64 + (size_t)row * (2 * (size_t)n_valid) + j0;
-                if ((n_valid & 1) == 0 && j0 + 32 <= 2 * n_valid) {
-#pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        ((float4 *)dst)[q] = make_float4(scale * __uint_as_float(v[4 * q]),
-                                                         scale * __uint_as_float(v[4 * q + 1]),
-                                                         scale * __uint_as_float(v[4 * q + 2]),
-                                                         scale * __uint_as_float(v[4 * q + 3]));
-                } else {
-#pragma unroll
-                    for (int q = 0; q < 16; ++q)
-                        if (j0 + 2 * q + 1 < 2 * n_valid)
-                            ((float2 *)dst)[q] = make_float2(scale * __uint_as_float(v[2 * q]),
-                                                             scale * __uint_as_float(v[2 * q + 1]));
-                }
-            }
-        } else {
-            const size_t off = (size_t)row * ldd + n0 + c * 32;
-            uint32_t hi[16], lo[16];
-#pragma unroll
-            for (int q = 0; q < 16; ++q) {
-                const float x0 = __uint_as_float(v[2 * q]), x1 = __uint_as_float(v[2 * q + 1]);
-                const __nv_bfloat16 h0 = __float2bfloat16_rn(x0), h1 = __float2bfloat16_rn(x1);
-                const __nv_bfloat16 l0 = __float2bfloat16_rn(x0 - __bfloat162float(h0));
-                const __nv_bfloat16 l1 = __float2bfloat16_rn(x1 - __bfloat162float(h1));
-                hi[q] = (uint32_t)__bfloat16_as_ushort(h0) | ((uint32_t)__bfloat16_as_ushort(h1) << 16);
-                lo[q] = (uint32_t)__bfloat16_as_ushort(l0) | ((uint32_t)__bfloat16_as_ushort(l1) << 16);
-            }
-            uint4 *dh = (uint4 *)(d_hi + off), *dl = (uint4 *)(d_lo + off);
-#pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                dh[q] = make_uint4(hi[4 * q], hi[4 * q + 1], hi[4 * q + 2], hi[4 * q + 3]);
-                dl[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
-            }
-        }
-    }
+    gemm_epilogue<EPI>(tmem_base, m0, n0, warp, lane, d_c64, d_hi, d_lo, ldd, n_valid, scale);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
     if (warp == 0)
@@ -316,6 +329,163 @@ gemm_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                      "r"(kTmemCols) : "memory");
     // no CTA may exit while a peer can still multicast into its shared memory or barriers
     if (kCluster) cluster_sync_all();
+}
+
+// ---- CTA-pair variant: tcgen05.mma.cta_group::2 on a 256 x 128 pair tile ---------------------
+// Two CTAs of a (2, 1, 1) cluster (adjacent M tiles = blockIdx.x, same N tile = blockIdx.y; the
+// pair must be the cluster's x dimension) execute ONE UMMA of M = 256:
+// each CTA holds its own 128 rows of A and HALF of the B tile (64 of the 128 rows); the tensor
+// cores of the two SMs exchange the B halves, so a CTA's shared memory sees 3 x (4 KB A + 2 KB B)
+// of operand reads per 192 tensor cycles (96 B/clk instead of 128) and 48 KB instead of 64 KB of
+// TMA fill per k-block (62 B/clk instead of 85) -- and the ring is 4 stages deep in the same
+// 192 KB.  Roles: both CTAs run a TMA producer (their A rows, their B half; the bytes are
+// accounted on the LEADER's full barrier through the .cta_group::2 TMA form), only the leader
+// (cluster rank 0) issues the UMMAs, and its tcgen05.commit is multicast to the stage-free and
+// accumulator-ready barriers of both CTAs.  Each CTA drains its own 128 TMEM lanes.
+// BN2 = N of the pair tile: 128 (4 stages of 48 KB) or 256 (3 stages of 64 KB, 256 TMEM columns).
+template <int BN2> struct PairCfg {
+    static constexpr int kHalfBytes = (BN2 / 2) * BK * 2;              // half of a B tile
+    static constexpr int kStageBytes = 2 * kTileBytes + 2 * kHalfBytes;  // per CTA and stage
+    static constexpr int kStages = BN2 == 128 ? 4 : 3;
+    static constexpr int kSmem = kStages * kStageBytes + 1024 + 256;
+    static constexpr int kTmem = BN2;
+};
+
+__device__ __forceinline__ uint32_t map_to_cta(uint32_t smem_addr, uint32_t cta) {
+    uint32_t r;
+    asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(smem_addr), "r"(cta));
+    return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_bar) {
+    asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(cluster_bar)
+                 : "memory");
+}
+// TMA load whose completion bytes are signalled on a barrier of the pair's leader CTA
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap *map,
+                                                 uint32_t cluster_bar, int c0, int c1) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes"
+        " [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(dst), "l"(map), "r"(cluster_bar), "r"(c0), "r"(c1)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc,
+                                           uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void umma2_commit_mc(uint32_t bar, uint16_t cta_mask) {
+    asm volatile(
+        "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64"
+        " [%0], %1;" ::"r"(bar), "h"(cta_mask) : "memory");
+}
+
+template <int EPI, int BN2>
+__global__ void __launch_bounds__(128, 1)
+gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
+                    const __grid_constant__ CUtensorMap map_a_lo,
+                    const __grid_constant__ CUtensorMap map_b_hi,
+                    const __grid_constant__ CUtensorMap map_b_lo, int num_kb, float *__restrict__ d_c64,
+                    __nv_bfloat16 *__restrict__ d_hi, __nv_bfloat16 *__restrict__ d_lo, int ldd,
+                    int n_valid, float scale) {
+    using Cfg = PairCfg<BN2>;
+    constexpr int kStages2 = Cfg::kStages, kStageBytes2 = Cfg::kStageBytes,
+                  kHalfTileBytes = Cfg::kHalfBytes;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = (uint64_t *)(smem + kStages2 * kStageBytes2);
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * kStages2 + 1);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages2),
+                   accum_bar = smem_u32(bars + 2 * kStages2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();  // 0: leader (even M tile), 1: peer
+    // Rasterisation: the pair must lie along grid x, but consecutive pairs should sweep the N
+    // tiles of one pair of A row-tiles (as the single-CTA kernel does) -- with M fastest a wave
+    // touches the whole twiddle matrix and DRAM traffic doubles (measured 280 vs 126 MB at 2048^2).
+    const unsigned pair_id = (blockIdx.x >> 1) + (gridDim.x >> 1) * blockIdx.y;
+    const int n0 = (int)(pair_id % gridDim.y) * BN2;
+    const int m0 = (int)(2 * (pair_id / gridDim.y) + rank) * BM;  // this CTA's own 128 rows of D
+    const bool leader = rank == 0;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages2; ++s) {
+            mbar_init(full0 + 8 * s, 2);   // leader: its own arrive.expect_tx + the peer's arrive
+            mbar_init(empty0 + 8 * s, 1);  // the leader's multicast commit
+        }
+        mbar_init(accum_bar, 1);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"(Cfg::kTmem) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    cluster_sync_all();  // both CTAs' barriers and TMEM are set up
+    pdl_wait();
+    pdl_launch_dependents();
+
+    if (warp == 0 && lane == 0) {
+        // ---- TMA producer (both CTAs): own A rows, own half of B; bytes land on the leader ----
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % kStages2;
+            const uint32_t ph = (uint32_t)(kb / kStages2) & 1u;
+            mbar_wait(empty0 + 8 * s, ph ^ 1u);
+            const uint32_t lead_full = map_to_cta(full0 + 8 * s, 0);
+            const uint32_t base = smem_u32(smem + s * kStageBytes2);
+            if (leader) mbar_expect_tx(full0 + 8 * s, 2 * kStageBytes2);
+            else mbar_arrive_cluster(lead_full);
+            tma_load_2d_pair(base, &map_a_hi, lead_full, kb * BK, m0);
+            tma_load_2d_pair(base + kTileBytes, &map_a_lo, lead_full, kb * BK, m0);
+            tma_load_2d_pair(base + 2 * kTileBytes, &map_b_hi, lead_full, kb * BK,
+                             n0 + (int)rank * (BN2 / 2));
+            tma_load_2d_pair(base + 2 * kTileBytes + kHalfTileBytes, &map_b_lo, lead_full, kb * BK,
+                             n0 + (int)rank * (BN2 / 2));
+        }
+    } else if (warp == 1 && lane == 0 && leader) {
+        // ---- MMA issuer: one thread of the leader CTA drives both SMs' tensor cores ----
+        constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN2);
+        for (int kb = 0; kb < num_kb; ++kb) {
+            const int s = kb % kStages2;
+            const uint32_t ph = (uint32_t)(kb / kStages2) & 1u;
+            mbar_wait(full0 + 8 * s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t base = smem_u32(smem + s * kStageBytes2);
+            const uint64_t a_hi = umma_desc_sw128(base);
+            const uint64_t a_lo = umma_desc_sw128(base + kTileBytes);
+            const uint64_t b_hi = umma_desc_sw128(base + 2 * kTileBytes);
+            const uint64_t b_lo = umma_desc_sw128(base + 2 * kTileBytes + kHalfTileBytes);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+                const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+                umma2_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+                umma2_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
+                umma2_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, 1u);
+            }
+            umma2_commit_mc(empty0 + 8 * s, (uint16_t)0x3);  // frees the stage in both CTAs
+        }
+        umma2_commit_mc(accum_bar, (uint16_t)0x3);
+    }
+    __syncwarp();
+
+    // ---- epilogue (both CTAs): own 128 TMEM lanes -> global ----
+    mbar_wait(accum_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    gemm_epilogue<EPI, BN2>(tmem_base, m0, n0, warp, lane, d_c64, d_hi, d_lo, ldd, n_valid, scale);
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();  // both CTAs are done with TMEM and with each other's barriers
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"(Cfg::kTmem) : "memory");
 }
 
 // ---- operand preparation (HBM-bound elementwise kernels) -----------------------------------
@@ -501,6 +671,8 @@ struct PlanEntry {
     int n, kind;
     bool wide;             // np % 256 == 0: both passes run as 2 x 2 clusters
     CUtensorMap maps[8];   // pass 1: A hi/lo, B hi/lo; pass 2: A hi/lo, B hi/lo
+    CUtensorMap pair[8];   // the same operands with the boxes of the CTA-pair kernel (256 x 128)
+    CUtensorMap pair256[8];  // ... and of its 256 x 256 form (128-row halves of the B tile)
 };
 static PlanEntry g_plans[64];
 static int g_num_plans = 0;
@@ -550,6 +722,20 @@ static int ensure_plan(const DftWorkspace &w, int kind, cudaStream_t st, const P
     if ((rc = make_map(&e.maps[5], w.d1_lo, np, 2 * np, half))) return rc;
     if ((rc = make_map(&e.maps[6], w.a2_hi, 2 * np, 2 * np, e.wide ? half : full))) return rc;
     if ((rc = make_map(&e.maps[7], w.a2_lo, 2 * np, 2 * np, e.wide ? half : full))) return rc;
+    // CTA-pair kernel: whole 128-row A boxes, 64-row halves of the B tile
+    if ((rc = make_map(&e.pair[0], w.a1_hi, 2 * np, 2 * np, full))) return rc;
+    if ((rc = make_map(&e.pair[1], w.a1_lo, 2 * np, 2 * np, full))) return rc;
+    if ((rc = make_map(&e.pair[2], w.b1_hi, np, 2 * np, half))) return rc;
+    if ((rc = make_map(&e.pair[3], w.b1_lo, np, 2 * np, half))) return rc;
+    if ((rc = make_map(&e.pair[4], w.d1_hi, np, 2 * np, full))) return rc;
+    if ((rc = make_map(&e.pair[5], w.d1_lo, np, 2 * np, full))) return rc;
+    if ((rc = make_map(&e.pair[6], w.a2_hi, 2 * np, 2 * np, half))) return rc;
+    if ((rc = make_map(&e.pair[7], w.a2_lo, 2 * np, 2 * np, half))) return rc;
+    for (int q = 0; q < 8; ++q) e.pair256[q] = e.pair[q];
+    if ((rc = make_map(&e.pair256[2], w.b1_hi, np, 2 * np, full))) return rc;
+    if ((rc = make_map(&e.pair256[3], w.b1_lo, np, 2 * np, full))) return rc;
+    if ((rc = make_map(&e.pair256[6], w.a2_hi, 2 * np, 2 * np, full))) return rc;
+    if ((rc = make_map(&e.pair256[7], w.a2_lo, 2 * np, 2 * np, full))) return rc;
     dim3 grid((w.np + 127) / 128, w.np);
     twiddle_kernel<<<grid, 128, 0, st>>>(w.n, w.np, so, si, sign, w.a1_hi, w.a1_lo, w.a2_hi, w.a2_lo);
     SOSAT_CUDA_OK(cudaGetLastError());
@@ -605,6 +791,42 @@ static int launch_gemm(dim3 grid, cudaStream_t st, const CUtensorMap *m, int num
                       m[1], m[2], m[3], num_kb, c64, d_hi, d_lo, ldd, n_valid, scale);
 }
 
+// grid = (M tiles of 128, N tiles of BN2): the pair kernel indexes M tiles with blockIdx.x
+template <int EPI, int BN2>
+static int launch_gemm_pair(dim3 grid, cudaStream_t st, const CUtensorMap *m, int num_kb, float *c64,
+                            __nv_bfloat16 *d_hi, __nv_bfloat16 *d_lo, int ldd, int n_valid,
+                            float scale) {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    SOSAT_CUDA_OK(cudaGetDevice(&dev));
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        SOSAT_CUDA_OK(cudaFuncSetAttribute(gemm2_bf16x3_kernel<EPI, BN2>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                           PairCfg<BN2>::kSmem));
+        attr_set[dev] = true;
+    }
+    return launch_pdl(gemm2_bf16x3_kernel<EPI, BN2>, grid, dim3(128), PairCfg<BN2>::kSmem, st, 2, 1,
+                      m[0], m[1], m[2], m[3], num_kb, c64, d_hi, d_lo, ldd, n_valid, scale);
+}
+
+// Which UMMA kernel runs the passes.  Measured on B200 (1024^2 / 2048^2, ms per transform):
+//   single-CTA UMMA, 2 x 2 multicast clusters, 128 x 128 tiles   0.071 / 0.353
+//   CTA pair (cta_group::2), 256 x 128 pair tiles               0.089 / 0.527  (N = 128 UMMAs of a
+//                                                                pair run at half rate)
+//   CTA pair, 256 x 256 pair tiles                              0.098 / 0.324
+// The 256 x 256 pair tile is the only shape that is not shared-memory-pipe bound, but it needs
+// enough tiles to fill the machine: it is used when a pass has >= 120 CTAs (np >= 1536).
+// SOSAT_GEMM_PAIR = 0 / 128 / 256 overrides the choice for A/B runs.
+static int pair_kernel_width(int np) {
+    static int v = -2;
+    if (v == -2) {
+        const char *e = getenv("SOSAT_GEMM_PAIR");
+        v = e ? atoi(e) : -1;
+    }
+    if (v >= 0) return v;
+    return (np % 256 == 0 && (2 * np / BM) * (np / 256) >= 120) ? 256 : 0;
+}
+
 // the two GEMM passes; b1 must already hold the split, transposed data operand.  The complex64
 // result (times scale) is written to d_c64 [n][n].
 static int run_passes(const DftWorkspace &w, const PlanEntry &pl, float scale, float *d_c64,
@@ -612,6 +834,26 @@ static int run_passes(const DftWorkspace &w, const PlanEntry &pl, float scale, f
     const int num_kb = 2 * w.np / BK;
     const dim3 g1(w.np / BN, 2 * w.np / BM), g2(2 * w.np / BN, w.np / BM);
     int rc;
+    const int pw = BK == 64 ? pair_kernel_width(w.np) : 0;
+    const unsigned mt1 = 2 * w.np / BM, mt2 = w.np / BM;  // M tiles of pass 1 / pass 2
+    if (pw == 256 && pl.wide) {
+        if ((rc = launch_gemm_pair<EPI_SPLIT_BF16, 256>(dim3(mt1, w.np / 256), st, pl.pair256, num_kb,
+                                                        nullptr, w.d1_hi, w.d1_lo, w.np, 0, 1.f)))
+            return rc;
+        return launch_gemm_pair<EPI_C64, 256>(dim3(mt2, 2 * w.np / 256), st, pl.pair256 + 4, num_kb,
+                                              d_c64, nullptr, nullptr, 0, w.n, scale);
+    }
+    if (pw == 128) {
+        // pass 1 has an even number of M tiles for every size; pass 2 only when np % 256 == 0
+        if ((rc = launch_gemm_pair<EPI_SPLIT_BF16, 128>(dim3(mt1, w.np / BN), st, pl.pair, num_kb,
+                                                        nullptr, w.d1_hi, w.d1_lo, w.np, 0, 1.f)))
+            return rc;
+        if (pl.wide)
+            return launch_gemm_pair<EPI_C64, 128>(dim3(mt2, 2 * w.np / BN), st, pl.pair + 4, num_kb,
+                                                  d_c64, nullptr, nullptr, 0, w.n, scale);
+        return launch_gemm<EPI_C64, 2, 1>(g2, st, pl.maps + 4, num_kb, d_c64, nullptr, nullptr, 0,
+                                          w.n, scale);
+    }
     if (pl.wide) {
         if ((rc = launch_gemm<EPI_SPLIT_BF16, 2, 2>(g1, st, pl.maps, num_kb, nullptr, w.d1_hi,
                                                     w.d1_lo, w.np, 0, 1.f))) return rc;

@@ -288,3 +288,24 @@ def test_ff_fwhm_device_matches_host_estimator(mods):
     pk = np.unravel_index(np.argmax(np.abs(Bh)), Bh.shape)
     assert pk != (m // 2, m // 2)
     assert abs(rt.ff_fwhm_device(B, xa, ya) - rt.ff_fwhm_est(Bh, xa, ya)) < 1e-9
+
+
+@pytest.mark.parametrize("pair", ["0", "128", "256"])
+def test_all_umma_kernels_agree(mods, monkeypatch, pair):
+    """The three UMMA kernels behind the passes (single-CTA with 2 x 2 multicast clusters,
+    cta_group::2 pair tiles 256 x 128 and 256 x 256) on a size where all of them are legal and on
+    one that is not a multiple of 256 (the pair kernels then run pass 1 only / fall back)."""
+    import subprocess, sys, os
+    code = (
+        "import numpy as np, sys; sys.path.insert(0, %r)\n"
+        "from sosat_optics_b200 import opt_analyze as oa\n"
+        "rng = np.random.default_rng(4)\n"
+        "for n in (512, 384, 100):\n"
+        "    b = (rng.standard_normal((n, n)) + 1j * rng.standard_normal((n, n))).astype(np.complex64)\n"
+        "    ref = np.fft.fftshift(np.fft.fft2(np.fft.fftshift(b.astype(np.complex128))))\n"
+        "    err = np.abs(oa.far_field(b) - ref).max() / np.abs(ref).max()\n"
+        "    assert err < 1e-4, (n, err)\n"
+        "print('ok')\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    env = dict(os.environ, SOSAT_GEMM_PAIR=pair)  # read once per process: run in a fresh one
+    r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
+    assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
