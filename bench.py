@@ -394,7 +394,8 @@ def run_ours(args):
                              "frac_of_bf16_peak": tf / peaks["bf16_tflops"],
                              "executed_tflops": 3 * tf}
     farfield["roofline"] = {
-        "kernel": "prep_b_c64_kernel + gemm_bf16x3_kernel x2 (2x2-cluster TMA multicast, PDL)",
+        "kernel": "prep_b_c64_kernel + 2 UMMA passes: gemm2_bf16x3_kernel (cta_group::2, 256x256 pair "
+                  "tiles) at 2048^2, gemm_bf16x3_kernel (2x2-cluster TMA multicast) at 1024^2; PDL",
         "bound": "tensor",
         "achieved": farfield["n2048"]["algorithmic_tflops"], "peak": peaks["bf16_tflops"],
         "unit": "TFLOP/s", "frac": farfield["n2048"]["frac_of_bf16_peak"],

@@ -468,3 +468,24 @@ def test_notebook_scattered_grid_route_end_to_end(mods):
     assert abs(rt.ff_fwhm_est(beam_fft, x_ang, y_ang) - float(g["fwhm"])) < 1e-3
     assert "%.2f" % rt.ff_fwhm_est(beam_fft, x_ang, y_ang) == "21.50"
     assert "%.2f" % rt.ff_fwhm_device(beam_fft, x_ang, y_ang) == "21.50"
+
+
+@pytest.mark.parametrize("n_scan", [65536, 65537])
+def test_launch_angle_tables_and_direct_sincos_agree_with_the_oracle(mods, n_scan):
+    """The fused kernel forms sin/cos of the launch angles from rotation tables (angle addition)
+    up to n_scan = 65536 and by direct fp64 sincos beyond: both against the oracle on a block of
+    launch rows in the middle of a very dense bundle (1e6 rays of 4.3e9)."""
+    rt, oracle = mods["rt"], mods["oracle"]
+    t = _bundle(mods, n_scan)
+    spec = [(t.k, t.th_fwhp_x, t.th_fwhp_y)]
+    r0 = n_scan // 2 - 8
+    re, im, cnt, st = rt.trace_bin_device(t, [[20, 0, -30]], spec, 64, 420.0, row_begin=r0,
+                                          row_end=r0 + 16)
+    ref = oracle.rx_to_lyot([20, 0, -30], t, ray_begin=r0 * n_scan, ray_end=(r0 + 16) * n_scan)
+    rre, rim, rcnt, sums = oracle.bin_near_field(ref, float(t.k), 64, 420.0, 0.0)
+    st = st.cpu().numpy()[0]
+    assert int(st[0]) == sums["n_valid"] and int(st[7]) == sums["n_binned"]
+    assert st[1] == pytest.approx(sums["sum_opl"], rel=1e-12)
+    assert np.abs(cnt[0].cpu().numpy() - rcnt).sum() <= 4        # rays sitting on a cell edge
+    assert np.abs(re[0, 0].cpu().numpy() - rre).max() < 2e-3 * np.abs(rre).max()
+    assert np.abs(im[0, 0].cpu().numpy() - rim).max() < 2e-3 * np.abs(rre).max()
