@@ -169,6 +169,18 @@ enum { SOSAT_DFT_FORWARD = 0, SOSAT_DFT_INVERSE = 1, SOSAT_DFT_B2A = 2 };
 int sosat_dft2_gemm_kind(const float *d_b, int n, float *d_B, int kind, void *d_workspace,
                          size_t workspace_bytes, void *stream);
 
+/* Zoomed far field on caller-chosen angles (the matrix-DFT form's advantage over
+ * an FFT): for j, k < n_out
+ *   B[j][k] = sum_{m,n} b[m][n] exp(-2 pi i (y_m thy_j + x_n thx_k) * inv_lambda)
+ * with row coordinates h_y[n], column coordinates h_x[n] (any spacing, unit of 1/inv_lambda) and
+ * angles h_thy[n_out], h_thx[n_out] [rad] (host arrays, n_out <= n rounded up to 128).  Same two
+ * UMMA passes as sosat_dft2_gemm with twiddles generated for these angles on every call.
+ * d_B: [n_out][n_out][2] float32.  With x_n = (n - ceil(N/2)) dx, th_k = (k - floor(N/2))
+ * lambda / (N dx) it equals sosat_dft2_gemm. */
+int sosat_dft2_zoom(const float *d_b, int n, float *d_B, int n_out, const double *h_y,
+                    const double *h_x, const double *h_thy, const double *h_thx,
+                    double inv_lambda, void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* a2b with the reference's argument meaning: d_apert (amplitude, abs() is taken) and
  * d_phi_deg (phase in degrees) are [n][n] float64; outputs d_beam [n][n][2] float64
  * (complex128) and d_phase [n][n] float64 = arctan2(imag, real). */

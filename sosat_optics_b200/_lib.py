@@ -60,6 +60,9 @@ SIGNATURES = {
     "sosat_dft2_gemm": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
     "sosat_dft2_gemm_kind": (c_int, [c_void_p, c_int, c_void_p, c_int, c_void_p, c_size_t,
                                      c_void_p]),
+    "sosat_dft2_zoom": (c_int, [c_void_p, c_int, c_void_p, c_int, POINTER(c_double),
+                                POINTER(c_double), POINTER(c_double), POINTER(c_double), c_double,
+                                c_void_p, c_size_t, c_void_p]),
     "sosat_b2a": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_size_t,
                           c_void_p]),
     "sosat_horn_aperture": (c_int, [c_void_p, c_void_p, c_int64, c_double, c_double, c_void_p,

@@ -526,6 +526,45 @@ __global__ void twiddle_kernel(int n, int np, int so, int si, int sign, __nv_bfl
         }
 }
 
+// Twiddle operands of the zoomed ("matrix DFT") transform on caller-chosen angles:
+//   W1[l][n] = exp(-2 pi i y_n thy_l / lambda)   (pass 1, rows of b = y axis)
+//   W2[k][m] = exp(-2 pi i x_m thx_k / lambda)   (pass 2, columns of b = x axis)
+// coords: y[n], x[n] (n values each), angles: thy[n_out], thx[n_out]; the phase in cycles is
+// reduced in fp64 before sincospi.  Same [c][c'] folding and layouts as twiddle_kernel.
+__global__ void twiddle_zoom_kernel(int n, int n_out, int np, const double *__restrict__ y,
+                                    const double *__restrict__ thy, const double *__restrict__ x,
+                                    const double *__restrict__ thx, double inv_lambda,
+                                    __nv_bfloat16 *a1_hi, __nv_bfloat16 *a1_lo,
+                                    __nv_bfloat16 *a2_hi, __nv_bfloat16 *a2_lo) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
+    if (col >= np) return;
+    float w1r = 0.f, w1i = 0.f, w2r = 0.f, w2i = 0.f;
+    if (row < n_out && col < n) {
+        double p = y[col] * thy[row] * inv_lambda, sn, cs;
+        p -= rint(p);
+        sincospi(-2.0 * p, &sn, &cs);
+        w1r = (float)cs; w1i = (float)sn;
+        p = x[col] * thx[row] * inv_lambda;
+        p -= rint(p);
+        sincospi(-2.0 * p, &sn, &cs);
+        w2r = (float)cs; w2i = (float)sn;
+    }
+    const float v1[2][2] = {{w1r, -w1i}, {w1i, w1r}}, v2[2][2] = {{w2r, -w2i}, {w2i, w2r}};
+    const size_t ld = 2 * (size_t)np;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int cp = 0; cp < 2; ++cp) {
+            __nv_bfloat16 h, l;
+            const size_t i1 = (size_t)(2 * row + c) * ld + 2 * col + cp;
+            const size_t i2 = (size_t)(2 * row + c) * ld + (size_t)cp * np + col;
+            split_bf16(v1[c][cp], h, l);
+            a1_hi[i1] = h; a1_lo[i1] = l;
+            split_bf16(v2[c][cp], h, l);
+            a2_hi[i2] = h; a2_lo[i2] = l;
+        }
+}
+
 // Data operand of pass 1: X[m][2n+c'] = component c' of b[n][m] (the transpose, zero padded to
 // np), split into bf16 hi/lo.  32 x 32 tiles through shared memory: coalesced 8-byte reads along
 // the rows of b, coalesced 4-byte (bf16x2) writes along the rows of X.  LOAD(row, col) returns
@@ -693,14 +732,17 @@ static int dft_kind_params(int kind, int n, int &so, int &si, int &sign, double 
 
 // Cluster shapes: pass 1 has grid (np/128, 2np/128), pass 2 (2np/128, np/128); the doubled
 // dimension is always even, the other one only when np is a multiple of 256.
+constexpr int kKindZoom = 100;  // twiddles written by the caller (sosat_dft2_zoom): never cached
+
 static int ensure_plan(const DftWorkspace &w, int kind, cudaStream_t st, const PlanEntry **out) {
-    int dev = 0, so, si, sign;
+    int dev = 0, so = 0, si = 0, sign = 0;
     double scale;
     SOSAT_CUDA_OK(cudaGetDevice(&dev));
-    if (int rc = dft_kind_params(kind, w.n, so, si, sign, scale)) return rc;
+    if (kind != kKindZoom)
+        if (int rc = dft_kind_params(kind, w.n, so, si, sign, scale)) return rc;
     for (int i = 0; i < g_num_plans; ++i)
         if (g_plans[i].device == dev && g_plans[i].ws == w.base && g_plans[i].n == w.n &&
-            g_plans[i].kind == kind) {
+            g_plans[i].kind == kind && kind != kKindZoom) {
             *out = &g_plans[i];
             return 0;
         }
@@ -736,9 +778,12 @@ static int ensure_plan(const DftWorkspace &w, int kind, cudaStream_t st, const P
     if ((rc = make_map(&e.pair256[3], w.b1_lo, np, 2 * np, full))) return rc;
     if ((rc = make_map(&e.pair256[6], w.a2_hi, 2 * np, 2 * np, full))) return rc;
     if ((rc = make_map(&e.pair256[7], w.a2_lo, 2 * np, 2 * np, full))) return rc;
-    dim3 grid((w.np + 127) / 128, w.np);
-    twiddle_kernel<<<grid, 128, 0, st>>>(w.n, w.np, so, si, sign, w.a1_hi, w.a1_lo, w.a2_hi, w.a2_lo);
-    SOSAT_CUDA_OK(cudaGetLastError());
+    if (kind != kKindZoom) {
+        dim3 grid((w.np + 127) / 128, w.np);
+        twiddle_kernel<<<grid, 128, 0, st>>>(w.n, w.np, so, si, sign, w.a1_hi, w.a1_lo, w.a2_hi,
+                                             w.a2_lo);
+        SOSAT_CUDA_OK(cudaGetLastError());
+    }
     int slot = -1;
     for (int i = 0; i < g_num_plans; ++i)
         if (g_plans[i].device == dev && g_plans[i].ws == w.base) slot = i;  // same buffer, re-planned
@@ -830,7 +875,8 @@ static int pair_kernel_width(int np) {
 // the two GEMM passes; b1 must already hold the split, transposed data operand.  The complex64
 // result (times scale) is written to d_c64 [n][n].
 static int run_passes(const DftWorkspace &w, const PlanEntry &pl, float scale, float *d_c64,
-                      cudaStream_t st) {
+                      cudaStream_t st, int n_out = 0) {
+    if (n_out <= 0) n_out = w.n;  // output is n_out x n_out complex64
     const int num_kb = 2 * w.np / BK;
     const dim3 g1(w.np / BN, 2 * w.np / BM), g2(2 * w.np / BN, w.np / BM);
     int rc;
@@ -841,7 +887,7 @@ static int run_passes(const DftWorkspace &w, const PlanEntry &pl, float scale, f
                                                         nullptr, w.d1_hi, w.d1_lo, w.np, 0, 1.f)))
             return rc;
         return launch_gemm_pair<EPI_C64, 256>(dim3(mt2, 2 * w.np / 256), st, pl.pair256 + 4, num_kb,
-                                              d_c64, nullptr, nullptr, 0, w.n, scale);
+                                              d_c64, nullptr, nullptr, 0, n_out, scale);
     }
     if (pw == 128) {
         // pass 1 has an even number of M tiles for every size; pass 2 only when np % 256 == 0
@@ -850,19 +896,19 @@ static int run_passes(const DftWorkspace &w, const PlanEntry &pl, float scale, f
             return rc;
         if (pl.wide)
             return launch_gemm_pair<EPI_C64, 128>(dim3(mt2, 2 * w.np / BN), st, pl.pair + 4, num_kb,
-                                                  d_c64, nullptr, nullptr, 0, w.n, scale);
+                                                  d_c64, nullptr, nullptr, 0, n_out, scale);
         return launch_gemm<EPI_C64, 2, 1>(g2, st, pl.maps + 4, num_kb, d_c64, nullptr, nullptr, 0,
-                                          w.n, scale);
+                                          n_out, scale);
     }
     if (pl.wide) {
         if ((rc = launch_gemm<EPI_SPLIT_BF16, 2, 2>(g1, st, pl.maps, num_kb, nullptr, w.d1_hi,
                                                     w.d1_lo, w.np, 0, 1.f))) return rc;
         return launch_gemm<EPI_C64, 2, 2>(g2, st, pl.maps + 4, num_kb, d_c64, nullptr, nullptr, 0,
-                                          w.n, scale);
+                                          n_out, scale);
     }
     if ((rc = launch_gemm<EPI_SPLIT_BF16, 1, 2>(g1, st, pl.maps, num_kb, nullptr, w.d1_hi, w.d1_lo,
                                                 w.np, 0, 1.f))) return rc;
-    return launch_gemm<EPI_C64, 2, 1>(g2, st, pl.maps + 4, num_kb, d_c64, nullptr, nullptr, 0, w.n,
+    return launch_gemm<EPI_C64, 2, 1>(g2, st, pl.maps + 4, num_kb, d_c64, nullptr, nullptr, 0, n_out,
                                       scale);
 }
 
@@ -902,6 +948,34 @@ extern "C" int sosat_dft2_gemm_kind(const float *d_b, int n, float *d_B, int kin
     if (int rc = launch_pdl(prep_b_c64_kernel, grid, dim3(32, 8), 0, st, 1, 1, (const float2 *)d_b, n,
                             w.np, w.b1_hi, w.b1_lo)) return rc;
     return run_passes(w, *pl, (float)scale, d_B, st);
+}
+
+extern "C" int sosat_dft2_zoom(const float *d_b, int n, float *d_B, int n_out, const double *h_y,
+                               const double *h_x, const double *h_thy, const double *h_thx,
+                               double inv_lambda, void *d_workspace, size_t workspace_bytes_,
+                               void *stream) {
+    SOSAT_REQUIRE(d_b && d_B && h_y && h_x && h_thy && h_thx, "sosat_dft2_zoom: null pointer");
+    if (int rc = check_ws(d_workspace, workspace_bytes_, n)) return rc;
+    SOSAT_REQUIRE(n_out >= 1 && n_out <= pad128(n), "n_out=%d must be in [1, %d] for n=%d", n_out,
+                  pad128(n), n);
+    cudaStream_t st = (cudaStream_t)stream;
+    DftWorkspace w = carve(d_workspace, n);
+    const PlanEntry *pl = nullptr;
+    if (int rc = ensure_plan(w, kKindZoom, st, &pl)) return rc;
+    // coordinates and angles staged at the start of the (otherwise unused here) complex64 area
+    double *d_y = (double *)w.c64, *d_x = d_y + w.np, *d_thy = d_x + w.np, *d_thx = d_thy + w.np;
+    SOSAT_CUDA_OK(cudaMemcpyAsync(d_y, h_y, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    SOSAT_CUDA_OK(cudaMemcpyAsync(d_x, h_x, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+    SOSAT_CUDA_OK(cudaMemcpyAsync(d_thy, h_thy, sizeof(double) * n_out, cudaMemcpyHostToDevice, st));
+    SOSAT_CUDA_OK(cudaMemcpyAsync(d_thx, h_thx, sizeof(double) * n_out, cudaMemcpyHostToDevice, st));
+    const dim3 tg((w.np + 127) / 128, w.np);
+    twiddle_zoom_kernel<<<tg, 128, 0, st>>>(n, n_out, w.np, d_y, d_thy, d_x, d_thx, inv_lambda,
+                                            w.a1_hi, w.a1_lo, w.a2_hi, w.a2_lo);
+    SOSAT_CUDA_OK(cudaGetLastError());
+    const dim3 grid(w.np / 32, w.np / 32);
+    if (int rc = launch_pdl(prep_b_c64_kernel, grid, dim3(32, 8), 0, st, 1, 1, (const float2 *)d_b, n,
+                            w.np, w.b1_hi, w.b1_lo)) return rc;
+    return run_passes(w, *pl, 1.0f, d_B, st, n_out);
 }
 
 extern "C" int sosat_dft2_gemm(const float *d_b, int n, float *d_B, void *d_workspace,

@@ -212,11 +212,18 @@ def beam_convolve(x, y, beam, apert1, apert2, plots=0):
     return x, y, final.cpu().numpy().astype(np.complex128) * (scale * peak)
 
 
-def far_field(b, dx_cm=None, lam_m=None, *, device: bool = False):
-    """Centred 2-D DFT of a complex near field ``b`` [N, N] (numpy complex or CUDA complex64
-    tensor): ``B = fftshift(fft2(fftshift(b)))``.  With ``device=True`` a CUDA complex64 tensor
-    is returned (no host copies).  If the cell size ``dx_cm`` and the wavelength ``lam_m`` are
-    given, returns ``(B, theta)`` with ``theta`` the true FFT-bin angles [rad] of both axes."""
+def far_field(b, dx_cm=None, lam_m=None, theta_x=None, theta_y=None, *, device: bool = False):
+    """Far field of a complex near field ``b`` [N, N] (numpy complex or CUDA complex64 tensor).
+
+    Without angles: the centred 2-D DFT ``B = fftshift(fft2(fftshift(b)))``; if the cell size
+    ``dx_cm`` and the wavelength ``lam_m`` are given, returns ``(B, theta)`` with ``theta`` the
+    true FFT-bin angles [rad] of both axes.
+
+    With ``theta_x`` / ``theta_y`` (1-D arrays of M <= N angles [rad] each; needs ``dx_cm`` and
+    ``lam_m``): the zoomed matrix DFT ``B[j, k] = sum_mn b[m, n] exp(-2 pi i (y_m theta_y[j] +
+    x_n theta_x[k]) / lam)`` on exactly those angles, cell centres ``x_n = (n - ceil(N/2)) dx``
+    (the convention under which the FFT-bin angles reproduce the plain transform).  Returns the
+    ``[M, M]`` field.  ``device=True`` returns a CUDA complex64 tensor (no host copies)."""
     lib = _lib.require_gpu()
     torch = _torch()
     if isinstance(b, np.ndarray):
@@ -226,6 +233,24 @@ def far_field(b, dx_cm=None, lam_m=None, *, device: bool = False):
     if d_b.dim() != 2 or d_b.shape[0] != d_b.shape[1]:
         raise ValueError("far_field expects a square [N, N] field")
     n = d_b.shape[0]
+    if theta_x is not None or theta_y is not None:
+        if theta_x is None or theta_y is None or dx_cm is None or lam_m is None:
+            raise ValueError("zoomed far field needs theta_x, theta_y, dx_cm and lam_m")
+        tx = np.ascontiguousarray(np.asarray(theta_x, dtype=np.float64).ravel())
+        ty = np.ascontiguousarray(np.asarray(theta_y, dtype=np.float64).ravel())
+        if tx.size != ty.size or not 1 <= tx.size <= n:
+            raise ValueError("theta_x and theta_y must be 1-D arrays of the same length M, 1 <= M <= N")
+        m = tx.size
+        xs = np.ascontiguousarray((np.arange(n) - (n + 1) // 2) * (float(dx_cm) / 100.0))
+        dp = lambda a: a.ctypes.data_as(ctypes.POINTER(ctypes.c_double))  # noqa: E731
+        out = torch.empty((m, m), dtype=torch.complex64, device="cuda")
+        ws = _workspace(lib, torch, n, 100)  # own workspace: its twiddles are rewritten per call
+        _lib.check(lib.sosat_dft2_zoom(ctypes.c_void_p(d_b.data_ptr()), n,
+                                       ctypes.c_void_p(out.data_ptr()), m, dp(xs), dp(xs), dp(ty),
+                                       dp(tx), 1.0 / float(lam_m), ctypes.c_void_p(ws.data_ptr()),
+                                       ws.numel(), _stream(torch)))
+        torch.cuda.current_stream().synchronize()  # the host arrays above are read asynchronously
+        return out if device else out.cpu().numpy()
     out = torch.empty((n, n), dtype=torch.complex64, device="cuda")
     ws = _workspace(lib, torch, n)
     _lib.check(lib.sosat_dft2_gemm(ctypes.c_void_p(d_b.data_ptr()), n,

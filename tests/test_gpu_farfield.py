@@ -309,3 +309,42 @@ def test_all_umma_kernels_agree(mods, monkeypatch, pair):
     env = dict(os.environ, SOSAT_GEMM_PAIR=pair)  # read once per process: run in a fresh one
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
+
+
+def test_zoomed_far_field_on_chosen_angles(mods):
+    """Row f4, second half: the matrix DFT on caller-chosen angles.  (i) On the FFT-bin angles it
+    is the plain transform; (ii) on a 4x finer angle grid around the beam it equals the direct
+    sum (numpy, fp64) to 1e-4 of peak; (iii) M < N outputs and a non-multiple-of-128 size."""
+    oa = mods["oa"]
+    n, dx_cm, lam = 256, 0.25, 3.33e-3
+    x = (np.arange(n) - (n + 1) // 2) * dx_cm
+    X, Y = np.meshgrid(x, x)
+    R = np.hypot(X, Y)
+    b = (np.exp(-R ** 2 / (2 * 9.0 ** 2)) * (R < 20) *
+         np.exp(1j * (0.3 * np.cos(X / 3) + 0.05 * (R / 20) ** 4 + 0.2 * X))).astype(np.complex64)
+    B, theta = oa.far_field(b, dx_cm, lam)
+    Bz = oa.far_field(b, dx_cm, lam, theta_x=theta, theta_y=theta)
+    assert Bz.shape == (n, n)
+    assert _rel_peak(Bz, B) < FF_TOL
+
+    def direct(bb, xs_m, thy, thx):
+        wy = np.exp(-2j * np.pi * np.outer(thy, xs_m) / lam)   # [M, N] over rows of b (y)
+        wx = np.exp(-2j * np.pi * np.outer(thx, xs_m) / lam)   # [M, N] over columns of b (x)
+        return wy @ bb.astype(np.complex128) @ wx.T
+
+    fine = theta[n // 2 - 16:n // 2 + 16]
+    thx = np.linspace(fine[0], fine[-1], 128) - 0.2 * lam / (2 * np.pi * 1e-2)  # beam is tilted in x
+    thy = np.linspace(fine[0], fine[-1], 128)
+    Bz = oa.far_field(b, dx_cm, lam, theta_x=thx, theta_y=thy)
+    ref = direct(b, x / 100.0, thy, thx)
+    assert Bz.shape == (128, 128) and _rel_peak(Bz, ref) < FF_TOL
+    assert np.abs(ref).max() > 0.9 * np.abs(B).max()          # the zoom window holds the peak
+
+    n2 = 100
+    b2 = b[:n2, :n2].copy()
+    x2 = (np.arange(n2) - (n2 + 1) // 2) * dx_cm / 100.0
+    th = np.linspace(-0.02, 0.03, 37)
+    Bz = oa.far_field(b2, dx_cm, lam, theta_x=th, theta_y=0.5 * th)
+    assert _rel_peak(Bz, direct(b2, x2, 0.5 * th, th)) < FF_TOL
+    with pytest.raises(ValueError):
+        oa.far_field(b2, dx_cm, lam, theta_x=th)
