@@ -14,8 +14,8 @@ namespace sosat {
 
 __constant__ GeomC g_geom;
 static bool g_geom_set[64] = {false};
-// a near-parabolic surface on this device's geometry: use the kernels that keep the
-// u c'/(1+s) form of the conic sag (trace_device.cuh)
+// which build of the kernels this device's geometry needs (GeoBuild below): 0 = the SAT
+// prescription, 1 = any other geometry, 2 = near-parabolic surfaces (u c'/(1+s) form)
 static int g_geom_build[64] = {0};
 
 static constexpr double kHalfPi = 1.5707963267948966;
@@ -134,14 +134,24 @@ trace_rows_kernel(RowsParams p, double *__restrict__ out, double *__restrict__ s
 // ---- K1b: fused trace + binning ------------------------------------------------------------
 constexpr int kTile = 16;  // rays per tile edge in theta
 // A CTA of kBinWarps warps traces a 16 (theta) x kTileH (phi) patch of the launch grid, one 8 x 4
-// sub-patch per warp.  Fewer warps per CTA = less skew to wait for at the per-tile barrier.
+// sub-patch per warp.  Measured (1e9 rays): 8 warps 1.74e10 rays/s, 16 warps +0.3 %, 4 warps
+// -1.6 %, 2 warps -4 %, barrier-free per-warp patches -4 %: warps that run in step share
+// instruction-cache lines of the 21 KB straight-line hot path, which outweighs the barrier skew.
 #ifndef SOSAT_BIN_WARPS
 #define SOSAT_BIN_WARPS 8
 #endif
 constexpr int kBinWarps = SOSAT_BIN_WARPS;
 constexpr int kBinThreads = 32 * kBinWarps;
 constexpr int kTileH = 2 * kBinWarps;
-constexpr int kTileMax = kTileH > kTile ? kTileH : kTile;
+// Rays per thread: with kNR = 2 a thread traces two rays 16 launch columns apart in the same
+// straight-line block (tile = 32 x kTileH), so that ptxas can interleave the two independent
+// dependency chains; costs twice the registers (2 CTAs/SM instead of 4).
+#ifndef SOSAT_BIN_NR
+#define SOSAT_BIN_NR 1
+#endif
+constexpr int kNR = SOSAT_BIN_NR;
+constexpr int kTileW = kTile * kNR;
+constexpr int kTileMax = kTileH > kTileW ? kTileH : kTileW;
 
 struct BinFreq {
     float neg_c_fx[SOSAT_MAX_FREQS];  // -4 ln2 / fwhp_x^2
@@ -168,7 +178,7 @@ struct BinParams {
 // (configs[4]), one per row of 8 at 15 rays/bin.  Any key sequence is handled correctly --
 // equal bins that are not adjacent in lane order simply become separate atomics.
 template <int N32, int N64, int MINB, int GEO>
-__global__ void __launch_bounds__(kBinThreads, MINB * 8 / kBinWarps)
+__global__ void __launch_bounds__(kBinThreads, MINB * 8 / kBinWarps / kNR)
 trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict__ re,
                  float *__restrict__ im, float *__restrict__ cnt, double *__restrict__ stats) {
     __shared__ double s_sin[2][kTileMax], s_cos[2][kTileMax], s_rx[4];
@@ -246,11 +256,11 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
             acc_rx = irx;
         }
         __syncthreads();  // previous tile done with the tables (first pass: s_rot is complete)
-        constexpr int kEntries = kTile + kTileH;
+        constexpr int kEntries = kTileW + kTileH;
         if (tid >= kEntries && tid < kEntries + 3) s_rx[tid - kEntries] = d_rx[3 * irx + tid - kEntries];
         if (tid < kEntries) {
-            const int which = tid >= kTile, l = which ? tid - kTile : tid;  // 0: theta, 1: phi
-            const int idx = which == 0 ? tx * kTile + l : (int)p.row_begin + ty * kTileH + l;
+            const int which = tid >= kTileW, l = which ? tid - kTileW : tid;  // 0: theta, 1: phi
+            const int idx = which == 0 ? tx * kTileW + l : (int)p.row_begin + ty * kTileH + l;
             const int ic = idx < p.n_scan ? idx : p.n_scan - 1;
             const double a = linspace_at(p.lin_start, p.lin_stop, p.lin_step, p.n_scan, ic);
             double sn, cs;
@@ -273,106 +283,111 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
         }
         __syncthreads();
 
-        const int ith = tx * kTile + lth;
         const int iph = ty * kTileH + lph;  // relative to row_begin
-        const bool live = ith < p.n_scan && iph < p.n_rows;
         const double *rx = s_rx;  // feed position [mm], staged with the tables
-        RayResult r;
-        {
+        RayResult rr[kNR];
+#pragma unroll
+        for (int q = 0; q < kNR; ++q) {
             // lanes past the edge of the launch grid trace the clamped (edge) ray so that whole
             // warps stay converged; their result is dropped
-            const double sth = s_sin[0][lth], cth = s_cos[0][lth];
+            const double sth = s_sin[0][lth + kTile * q], cth = s_cos[0][lth + kTile * q];
             const double sph = s_sin[1][lph], cph = s_cos[1][lph];
             trace_ray_newton<N32, N64, GeoBuild<GEO>::generic, GeoBuild<GEO>::mask, GeoBuild<GEO>::edge,
-                             false>(g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph, cth, r);
+                             false>(g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph, cth, rr[q]);
         }
-        if (r.flags & (RAY_UNCONVERGED | RAY_FLAGGED)) {
-            // rare: the launch direction is re-read here (volatile) instead of being kept live
-            // across the fast path, and results go through a local copy so that r itself stays
-            // in registers.
-            const double sth = *(volatile double *)&s_sin[0][lth], cth = *(volatile double *)&s_cos[0][lth];
-            const double sph = *(volatile double *)&s_sin[1][lph], cph = *(volatile double *)&s_cos[1][lph];
-            RayResult rs;
-            rs.valid = r.valid;
-            rs.flags = r.flags;
-            bool redone = false;
-            if (r.flags & RAY_UNCONVERGED) {  // adaptive Newton refinement, out of line
-                trace_ray_adaptive<GeoBuild<GEO>::generic, GeoBuild<GEO>::mask, GeoBuild<GEO>::edge>(
-                    g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph, cth, rs);
-                redone = true;
-            }
-            if (rs.valid && (rs.flags & RAY_FLAGGED)) {
-                // < 0.15 % of rays: the reference's bracketed solve
-                trace_ray_bracketed(g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph, cth, rs);
-                redone = true;
-                if (live) {
-                    atomicAdd(&s_rare[0], 1u);
-                    if (rs.flags & RAY_BRACKET_FAIL) atomicAdd(&s_rare[1], 1u);
-                }
-            }
-            if (redone) {
-                r.ax = rs.ax; r.az = rs.az; r.opl = rs.opl;
-                r.dx = rs.dx; r.dy = rs.dy; r.dz = rs.dz;
-                r.valid = rs.valid;
-            }
-        }
-        const bool valid = live && r.valid;
-        int bin = -1;
-        if (valid) {
-            const int ix = __double2int_rd((r.ax + p.half_extent) * p.inv_cell);
-            const int iz = __double2int_rd((r.az + p.half_extent) * p.inv_cell);
-            if ((unsigned)ix < (unsigned)p.grid_n && (unsigned)iz < (unsigned)p.grid_n)
-                bin = iz * p.grid_n + ix;
-            s_sum[0][tid] += r.opl;
-            s_sum[1][tid] += r.dx;
-            s_sum[2][tid] += r.dy;
-            s_sum[3][tid] += r.dz;
-        }
-        const unsigned vmask = __ballot_sync(0xffffffffu, valid);
-        const unsigned bmask = __ballot_sync(0xffffffffu, bin >= 0);
-        if (lane == 0 && vmask)
-            atomicAdd(&s_valid_binned, (unsigned long long)__popc(vmask) |
-                                           ((unsigned long long)__popc(bmask) << 32));
-        if (re == nullptr || bmask == 0u) continue;
-
-        // ---- run-length aggregation along the lane order ------------------------------------
-        const int prev = __shfl_up_sync(0xffffffffu, bin, 1);
-        const bool head = lane == 0 || prev != bin;
-        const unsigned heads = __ballot_sync(0xffffffffu, head);
-        // bit q of m: lane + 1 + q starts a new run; a virtual head sits just past lane 31
-        const unsigned m = ((heads >> lane) >> 1) | (1u << (31 - lane));
-        const int rest = __ffs(m) - 1;  // lanes lane+1 .. lane+rest continue this lane's run
-        const bool flush = head && bin >= 0;
-        if (flush) atomicAdd(cnt + (long long)irx * plane + bin, (float)(rest + 1));
-
-        const double dopl = r.opl - p.opl_ref;
-        float *re_f = re + (long long)irx * p.n_freq * plane;
-        float *im_f = im + (long long)irx * p.n_freq * plane;
-        for (int f = 0; f < p.n_freq; ++f, re_f += plane, im_f += plane) {
-            float vre = 0.f, vim = 0.f;
-            if (bin >= 0) {
-                const float a = s_amp[f][0][lth] * s_amp[f][1][lph];
-                double cyc = dopl * g_freq.kk[f];
-                // phase reduced to [-1/2, 1/2] cycles in fp64: cyc - rint(cyc) with the 1.5 * 2^52
-                // trick (two DADDs; an FRND.F64 would go through the XU pipe)
-                cyc -= __dadd_rn(__dadd_rn(cyc, 6755399441055744.0), -6755399441055744.0);
-                float sn, cs;
-                __sincosf(6.2831853071795865f * (float)cyc, &sn, &cs);  // SFU, |err| < 1e-6
-                vre = a * cs;
-                vim = a * sn;
-            }
 #pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const float ore = __shfl_down_sync(0xffffffffu, vre, o);
-                const float oim = __shfl_down_sync(0xffffffffu, vim, o);
-                if (o <= rest) {
-                    vre += ore;
-                    vim += oim;
+        for (int q = 0; q < kNR; ++q) {
+            RayResult &r = rr[q];
+            const int lthq = lth + kTile * q;
+            const bool live = tx * kTileW + lthq < p.n_scan && iph < p.n_rows;
+            if (r.flags & (RAY_UNCONVERGED | RAY_FLAGGED)) {
+                // rare: the launch direction is re-read here (volatile) instead of being kept live
+                // across the fast path, and results go through a local copy so that r itself
+                // stays in registers.
+                const double sth = *(volatile double *)&s_sin[0][lthq], cth = *(volatile double *)&s_cos[0][lthq];
+                const double sph = *(volatile double *)&s_sin[1][lph], cph = *(volatile double *)&s_cos[1][lph];
+                RayResult rs;
+                rs.valid = r.valid;
+                rs.flags = r.flags;
+                bool redone = false;
+                if (r.flags & RAY_UNCONVERGED) {  // adaptive Newton refinement, out of line
+                    trace_ray_adaptive<GeoBuild<GEO>::generic, GeoBuild<GEO>::mask, GeoBuild<GEO>::edge>(
+                        g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph, cth, rs);
+                    redone = true;
+                }
+                if (rs.valid && (rs.flags & RAY_FLAGGED)) {
+                    // < 0.15 % of rays: the reference's bracketed solve
+                    trace_ray_bracketed(g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph, cth, rs);
+                    redone = true;
+                    if (live) {
+                        atomicAdd(&s_rare[0], 1u);
+                        if (rs.flags & RAY_BRACKET_FAIL) atomicAdd(&s_rare[1], 1u);
+                    }
+                }
+                if (redone) {
+                    r.ax = rs.ax; r.az = rs.az; r.opl = rs.opl;
+                    r.dx = rs.dx; r.dy = rs.dy; r.dz = rs.dz;
+                    r.valid = rs.valid;
                 }
             }
-            if (flush) {
-                atomicAdd(re_f + bin, vre);
-                atomicAdd(im_f + bin, vim);
+            const bool valid = live && r.valid;
+            int bin = -1;
+            if (valid) {
+                const int ix = __double2int_rd((r.ax + p.half_extent) * p.inv_cell);
+                const int iz = __double2int_rd((r.az + p.half_extent) * p.inv_cell);
+                if ((unsigned)ix < (unsigned)p.grid_n && (unsigned)iz < (unsigned)p.grid_n)
+                    bin = iz * p.grid_n + ix;
+                s_sum[0][tid] += r.opl;
+                s_sum[1][tid] += r.dx;
+                s_sum[2][tid] += r.dy;
+                s_sum[3][tid] += r.dz;
+            }
+            const unsigned vmask = __ballot_sync(0xffffffffu, valid);
+            const unsigned bmask = __ballot_sync(0xffffffffu, bin >= 0);
+            if (lane == 0 && vmask)
+                atomicAdd(&s_valid_binned, (unsigned long long)__popc(vmask) |
+                                               ((unsigned long long)__popc(bmask) << 32));
+            if (re == nullptr || bmask == 0u) continue;
+
+            // ---- run-length aggregation along the lane order --------------------------------
+            const int prev = __shfl_up_sync(0xffffffffu, bin, 1);
+            const bool head = lane == 0 || prev != bin;
+            const unsigned heads = __ballot_sync(0xffffffffu, head);
+            // bit b of m: lane + 1 + b starts a new run; a virtual head sits just past lane 31
+            const unsigned m = ((heads >> lane) >> 1) | (1u << (31 - lane));
+            const int rest = __ffs(m) - 1;  // lanes lane+1 .. lane+rest continue this lane's run
+            const bool flush = head && bin >= 0;
+            if (flush) atomicAdd(cnt + (long long)irx * plane + bin, (float)(rest + 1));
+
+            const double dopl = r.opl - p.opl_ref;
+            float *re_f = re + (long long)irx * p.n_freq * plane;
+            float *im_f = im + (long long)irx * p.n_freq * plane;
+            for (int f = 0; f < p.n_freq; ++f, re_f += plane, im_f += plane) {
+                float vre = 0.f, vim = 0.f;
+                if (bin >= 0) {
+                    const float a = s_amp[f][0][lthq] * s_amp[f][1][lph];
+                    double cyc = dopl * g_freq.kk[f];
+                    // phase reduced to [-1/2, 1/2] cycles in fp64: cyc - rint(cyc) with the
+                    // 1.5 * 2^52 trick (two DADDs; an FRND.F64 would go through the XU pipe)
+                    cyc -= __dadd_rn(__dadd_rn(cyc, 6755399441055744.0), -6755399441055744.0);
+                    float sn, cs;
+                    __sincosf(6.2831853071795865f * (float)cyc, &sn, &cs);  // SFU, |err| < 1e-6
+                    vre = a * cs;
+                    vim = a * sn;
+                }
+#pragma unroll
+                for (int o = 1; o < 32; o <<= 1) {
+                    const float ore = __shfl_down_sync(0xffffffffu, vre, o);
+                    const float oim = __shfl_down_sync(0xffffffffu, vim, o);
+                    if (o <= rest) {
+                        vre += ore;
+                        vim += oim;
+                    }
+                }
+                if (flush) {
+                    atomicAdd(re_f + bin, vre);
+                    atomicAdd(im_f + bin, vim);
+                }
             }
         }
     }
@@ -699,7 +714,7 @@ extern "C" int sosat_trace_bin(const double *d_rx, int n_rx, const sosat_freq_t 
     p.n_rx = n_rx;
     p.n_freq = n_freq;
     p.grid_n = binning ? grid_n : 0;
-    p.tiles_x = (n_scan + kTile - 1) / kTile;
+    p.tiles_x = (n_scan + kTileW - 1) / kTileW;
     p.tiles_y = (p.n_rows + kTileH - 1) / kTileH;
     p.n_tiles = (long long)p.tiles_x * p.tiles_y * n_rx;
     SOSAT_REQUIRE(p.n_tiles < 2147483647LL, "too many ray tiles for one launch (%lld): split the "
