@@ -123,6 +123,17 @@ def _worker(rank, world, port, q):
         b, cnt, stats = sdist.near_field_binned_distributed(
             t, [[0, 0, 0], [60, 0, -90]], 16, 42.0, trace_fn=_oracle_trace_fn, field_fn=_field_fn)
         sweep = sdist.sweep_distributed(list(range(5)), lambda p: (p, rank))
+        # the single-buffer form bench.py uses: planes are views of one flat tensor, one collective
+        re, im, c2, flat = sdist.alloc_planes(2, 1, 16, device="cpu")
+        st = torch.zeros((2, 8), dtype=torch.float64)
+        r0, r1 = sdist.partition_rows(40, world, rank)
+        a, bb, cc, ss = _oracle_trace_fn(t, np.array([[0., 0, 0], [60, 0, -90]]),
+                                         [(t.k, t.th_fwhp_x, t.th_fwhp_y)], 16, 420.0,
+                                         row_begin=r0, row_end=r1)
+        re.copy_(a); im.copy_(bb); c2.copy_(cc); st.copy_(ss)
+        sdist.reduce_bins(re, im, c2, st, flat=flat)
+        assert flat.data_ptr() == re.data_ptr() and torch.equal(c2, cnt)
+        assert (torch.complex(re, im) - b).abs().max().item() < 1e-6
         q.put((rank, b.numpy(), cnt.numpy(), stats, sweep))
     finally:
         dist.destroy_process_group()
