@@ -110,6 +110,15 @@ int sosat_trace_rays(const double *h_rx, const sosat_freq_t *h_freq, int n_scan,
                      int64_t ray_begin, int64_t ray_end, double *d_out, double *d_stats,
                      void *stream);
 
+/* Compact per-ray output of the same trace (SURVEY 8d "compact SoA mode", 16 B/ray): for every
+ * ray one float4 {x_sim [cm], y_sim [cm], a cos p, a sin p}, p = k_over_2e3 (OPL - opl_ref),
+ * all-zero for invalid rays -- the sample format sosat_nudft_direct consumes, so a near field on
+ * the scattered ray positions goes to the far field without gridding.  d_xyb: [n][4] float32,
+ * 16-byte aligned. */
+int sosat_trace_samples(const double *h_rx, const sosat_freq_t *h_freq, int n_scan,
+                        int64_t ray_begin, int64_t ray_end, double opl_ref, float *d_xyb,
+                        double *d_stats, void *stream);
+
 /* Host-buffer form of the same call: h_out is [17][n] float64 host memory.  Synchronous. */
 int sosat_rx_to_lyot_host(const sosat_geom_t *h_geom, const double *h_rx,
                           const sosat_freq_t *h_freq, int n_scan, int64_t ray_begin,

@@ -46,6 +46,8 @@ SIGNATURES = {
     "sosat_set_geometry": (c_int, [POINTER(Geom), c_void_p]),
     "sosat_trace_rays": (c_int, [POINTER(c_double), POINTER(Freq), c_int, c_int64, c_int64,
                                  c_void_p, c_void_p, c_void_p]),
+    "sosat_trace_samples": (c_int, [POINTER(c_double), POINTER(Freq), c_int, c_int64, c_int64,
+                                    c_double, c_void_p, c_void_p, c_void_p]),
     "sosat_rx_to_lyot_host": (c_int, [POINTER(Geom), POINTER(c_double), POINTER(Freq), c_int,
                                       c_int64, c_int64, POINTER(c_double), POINTER(c_double)]),
     "sosat_near_field_arrays": (c_int, [c_void_p, c_int64, c_double, c_void_p, c_void_p,

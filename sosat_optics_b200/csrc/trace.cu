@@ -61,6 +61,7 @@ struct RowsParams {
     double rx[3];
     double fwhp_x, fwhp_y;
     double lin_start, lin_stop, lin_step;
+    double opl_ref, kk;  // compact mode: phase = 2 pi frac(kk (OPL - opl_ref)), kk = k/2e3/(2 pi)
     int n_scan;
     long long ray_begin, n;
 };
@@ -75,9 +76,14 @@ template <int GEO> struct GeoBuild {
     static constexpr int edge = GEO == 0 ? 0x10 : 0x3f;  // surfaces with K' > 0
 };
 
-template <int N32, int N64, int GEO>
+// COMPACT = false: the reference's table out[17][n] (fp64 rows, coalesced 8-byte row stores).
+// COMPACT = true:  one float4 {x_sim [cm], y_sim [cm], a cos p, a sin p} per ray (16 B/ray, one
+//                  coalesced 16-byte store; invalid rays are all-zero samples) -- the input
+//                  format of the direct-sum far field (nudft.cu), SURVEY 8d "compact SoA mode".
+template <int N32, int N64, int GEO, bool COMPACT>
 __global__ void __launch_bounds__(256)
-trace_rows_kernel(RowsParams p, double *__restrict__ out, double *__restrict__ stats) {
+trace_rows_kernel(RowsParams p, double *__restrict__ out, float4 *__restrict__ samples,
+                  double *__restrict__ stats) {
     const long long j0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     const bool live_thread = j0 < p.n;
     const long long j = live_thread ? j0 : p.n - 1;  // idle lanes shadow the last ray: whole warps trace
@@ -121,7 +127,19 @@ trace_rows_kernel(RowsParams p, double *__restrict__ out, double *__restrict__ s
         }
         acc[SOSAT_STAT_N_SLOW] = live_thread ? (double)n_slow : 0.0;
         acc[SOSAT_STAT_N_BRACKET_FAIL] = (live_thread && (r.flags & RAY_BRACKET_FAIL)) ? 1.0 : 0.0;
-        if (live_thread) {
+        if (live_thread && COMPACT) {
+            float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+            if (row[4] != 0.0) {
+                double cyc = (row[3] - p.opl_ref) * p.kk;
+                cyc -= rint(cyc);  // phase reduced to [-1/2, 1/2] cycles in fp64
+                float sn, cs;
+                sincospif(2.0f * (float)cyc, &sn, &cs);
+                const float a = (float)row[4];
+                v = make_float4((float)(row[0] / 1e1), (float)(row[2] / 1e1), a * cs, a * sn);
+            }
+            samples[j] = v;
+        }
+        if (live_thread && !COMPACT) {
 #pragma unroll
             for (int q = 0; q < 11; ++q) out[(long long)q * p.n + j] = row[q];
 #pragma unroll
@@ -564,25 +582,25 @@ extern "C" int sosat_set_geometry(const sosat_geom_t *h, void *stream) {
     return SOSAT_OK;
 }
 
-template <int N32, int N64>
-static void launch_rows(int geo, const RowsParams &p, double *out, double *stats,
+template <int N32, int N64, bool COMPACT>
+static void launch_rows(int geo, const RowsParams &p, double *out, float4 *samples, double *stats,
                         cudaStream_t st) {
     const int threads = 256;
     const unsigned blocks = (unsigned)((p.n + threads - 1) / threads);
     switch (geo) {
-        case 0: trace_rows_kernel<N32, N64, 0><<<blocks, threads, 0, st>>>(p, out, stats); break;
-        case 1: trace_rows_kernel<N32, N64, 1><<<blocks, threads, 0, st>>>(p, out, stats); break;
-        default: trace_rows_kernel<N32, N64, 2><<<blocks, threads, 0, st>>>(p, out, stats); break;
+        case 0: trace_rows_kernel<N32, N64, 0, COMPACT><<<blocks, threads, 0, st>>>(p, out, samples, stats); break;
+        case 1: trace_rows_kernel<N32, N64, 1, COMPACT><<<blocks, threads, 0, st>>>(p, out, samples, stats); break;
+        default: trace_rows_kernel<N32, N64, 2, COMPACT><<<blocks, threads, 0, st>>>(p, out, samples, stats); break;
     }
 }
 
-extern "C" int sosat_trace_rays(const double *h_rx, const sosat_freq_t *h_freq, int n_scan,
-                                int64_t ray_begin, int64_t ray_end, double *d_out,
-                                double *d_stats, void *stream) {
+static int trace_rows_common(const double *h_rx, const sosat_freq_t *h_freq, int n_scan,
+                             int64_t ray_begin, int64_t ray_end, double opl_ref, double *d_out,
+                             float4 *d_samples, double *d_stats, void *stream) {
     int dev;
     if (int rc = current_device(&dev)) return rc;
     if (!g_geom_set[dev]) return set_error(SOSAT_ERR_NO_GEOMETRY, "call sosat_set_geometry first");
-    SOSAT_REQUIRE(h_rx && h_freq && d_out, "sosat_trace_rays: null pointer");
+    SOSAT_REQUIRE(h_rx && h_freq && (d_out || d_samples), "null pointer");
     SOSAT_REQUIRE(n_scan >= 1, "n_scan must be >= 1 (got %d)", n_scan);
     const int64_t total = (int64_t)n_scan * n_scan;
     SOSAT_REQUIRE(ray_begin >= 0 && ray_end >= ray_begin && ray_end <= total,
@@ -593,6 +611,8 @@ extern "C" int sosat_trace_rays(const double *h_rx, const sosat_freq_t *h_freq, 
     p.rx[0] = h_rx[0]; p.rx[1] = h_rx[1]; p.rx[2] = h_rx[2];
     p.fwhp_x = h_freq->fwhp_x;
     p.fwhp_y = h_freq->fwhp_y;
+    p.opl_ref = opl_ref;
+    p.kk = h_freq->k_over_2e3 / 6.283185307179586;
     fill_linspace(g_host_geom[dev].cone, n_scan, p.lin_start, p.lin_stop, p.lin_step);
     p.n_scan = n_scan;
     p.ray_begin = ray_begin;
@@ -601,13 +621,34 @@ extern "C" int sosat_trace_rays(const double *h_rx, const sosat_freq_t *h_freq, 
     SOSAT_REQUIRE((p.n + 255) / 256 < 2147483647LL, "too many rays for one launch");
     cudaStream_t st = (cudaStream_t)stream;
     const int geo = g_geom_build[dev];
-    switch (trace_variant()) {
-        case 0: launch_rows<0, 5>(geo, p, d_out, d_stats, st); break;
-        case 2: launch_rows<3, 2>(geo, p, d_out, d_stats, st); break;
-        default: launch_rows<2, 2>(geo, p, d_out, d_stats, st); break;
+    if (d_samples) {
+        launch_rows<2, 2, true>(geo, p, nullptr, d_samples, d_stats, st);
+    } else {
+        switch (trace_variant()) {
+            case 0: launch_rows<0, 5, false>(geo, p, d_out, nullptr, d_stats, st); break;
+            case 2: launch_rows<3, 2, false>(geo, p, d_out, nullptr, d_stats, st); break;
+            default: launch_rows<2, 2, false>(geo, p, d_out, nullptr, d_stats, st); break;
+        }
     }
     SOSAT_CUDA_OK(cudaGetLastError());
     return SOSAT_OK;
+}
+
+extern "C" int sosat_trace_rays(const double *h_rx, const sosat_freq_t *h_freq, int n_scan,
+                                int64_t ray_begin, int64_t ray_end, double *d_out,
+                                double *d_stats, void *stream) {
+    SOSAT_REQUIRE(d_out, "sosat_trace_rays: null pointer");
+    return trace_rows_common(h_rx, h_freq, n_scan, ray_begin, ray_end, 0.0, d_out, nullptr, d_stats,
+                             stream);
+}
+
+extern "C" int sosat_trace_samples(const double *h_rx, const sosat_freq_t *h_freq, int n_scan,
+                                   int64_t ray_begin, int64_t ray_end, double opl_ref,
+                                   float *d_xyb, double *d_stats, void *stream) {
+    SOSAT_REQUIRE(d_xyb, "sosat_trace_samples: null pointer");
+    SOSAT_REQUIRE(((uintptr_t)d_xyb & 15) == 0, "sosat_trace_samples: d_xyb must be 16-byte aligned");
+    return trace_rows_common(h_rx, h_freq, n_scan, ray_begin, ray_end, opl_ref, nullptr,
+                             (float4 *)d_xyb, d_stats, stream);
 }
 
 extern "C" int sosat_rx_to_lyot_host(const sosat_geom_t *h_geom, const double *h_rx,

@@ -272,26 +272,39 @@ def far_field_angles(n: int, dx_m: float, lam_m: float):
 def far_field_irregular(x, y, b, theta_x, theta_y, lam):
     """Direct-sum far field of irregular samples: ``B_j = sum_p b_p exp(-2 pi i (x_p thx_j +
     y_p thy_j) / lam)``; ``x, y, lam`` in the same length unit, angles in radians.  The sign
-    follows the reference's code path (numpy FFT), not README.md:24."""
+    follows the reference's code path (numpy FFT), not README.md:24.
+
+    ``x`` may instead be a CUDA float32 tensor ``[P, 4]`` of samples ``{x, y, Re b, Im b}`` as
+    returned by ``ray_trace.near_field_samples(..., device=True)`` (then ``y`` and ``b`` must be
+    ``None``): the samples stay on the device."""
     lib = _lib.require_gpu()
     torch = _torch()
-    x = np.asarray(x, dtype=np.float64).ravel()
-    y = np.asarray(y, dtype=np.float64).ravel()
-    b = np.asarray(b, dtype=np.complex128).ravel()
-    if not (x.size == y.size == b.size):
-        raise ValueError("x, y, b must have the same number of samples")
     tx = np.asarray(theta_x, dtype=np.float64)
     ty = np.asarray(theta_y, dtype=np.float64)
     if tx.shape != ty.shape:
         raise ValueError("theta_x and theta_y must have the same shape")
-    if x.size == 0 or tx.size == 0:
+    if not isinstance(x, np.ndarray) and hasattr(x, "is_cuda"):
+        if y is not None or b is not None:
+            raise ValueError("with a device sample tensor, y and b must be None")
+        d_pts = x.to(device="cuda", dtype=torch.float32).contiguous()
+        if d_pts.dim() != 2 or d_pts.shape[1] != 4:
+            raise ValueError("device samples must be [P, 4] float32 {x, y, Re b, Im b}")
+        n_pts = d_pts.shape[0]
+    else:
+        x = np.asarray(x, dtype=np.float64).ravel()
+        y = np.asarray(y, dtype=np.float64).ravel()
+        b = np.asarray(b, dtype=np.complex128).ravel()
+        if not (x.size == y.size == b.size):
+            raise ValueError("x, y, b must have the same number of samples")
+        n_pts = x.size
+        pts = np.stack([x, y, b.real, b.imag], axis=1).astype(np.float32)
+        d_pts = torch.from_numpy(np.ascontiguousarray(pts)).to("cuda") if n_pts else None
+    if n_pts == 0 or tx.size == 0:
         return np.zeros(tx.shape, dtype=np.complex128)
-    pts = np.stack([x, y, b.real, b.imag], axis=1).astype(np.float32)
     th = np.stack([tx.ravel(), ty.ravel()], axis=1).astype(np.float32)
-    d_pts = torch.from_numpy(np.ascontiguousarray(pts)).to("cuda")
     d_th = torch.from_numpy(np.ascontiguousarray(th)).to("cuda")
     out = torch.empty((th.shape[0], 2), dtype=torch.float32, device="cuda")
-    _lib.check(lib.sosat_nudft_direct(ctypes.c_void_p(d_pts.data_ptr()), pts.shape[0],
+    _lib.check(lib.sosat_nudft_direct(ctypes.c_void_p(d_pts.data_ptr()), n_pts,
                                       ctypes.c_void_p(d_th.data_ptr()), th.shape[0],
                                       1.0 / float(lam), ctypes.c_void_p(out.data_ptr()),
                                       _stream(torch)))

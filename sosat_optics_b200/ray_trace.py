@@ -12,6 +12,8 @@ function                reference                   device code
 ``near_field_binned``   -- (north_star, row a7)     ``sosat_trace_bin``   (trace_bin_kernel)
 ``get_fwhm`` etc.       ray_trace.py:1648-1672,     host numpy helpers over returned arrays (the
 ``ff_fwhm_est``         1757-1779                   reference's signatures) ...
+``near_field_samples``  -- (north_star, irregular)    ``sosat_trace_samples``: float4 {x, y, Re b, Im b}
+                        route)                      per ray, the input of the direct-sum far field
 ``near_field_metrics``  same reductions, on device  ``sosat_near_field_metrics`` (reduce.cu): one
                         for a whole frequency sweep trace, scalars per frequency come back
 ``ff_fwhm_device``      ff_fwhm_est on a CUDA field ``sosat_ff_fwhm_indices`` (reduce.cu)
@@ -33,7 +35,7 @@ from . import _lib, geometry
 
 __all__ = ["rx_to_lyot", "getNearField", "get_sim", "get_beam_cent", "get_fwhm",
            "get_angle_out", "ff_fwhm_est", "near_field_binned", "trace_stats",
-           "near_field_metrics", "ff_fwhm_device", "sim2d", "sim_data",
+           "near_field_metrics", "near_field_samples", "ff_fwhm_device", "sim2d", "sim_data",
            "SimOutput", "BinnedField"]
 
 
@@ -173,6 +175,38 @@ def ff_fwhm_est(beam_fft, x_ang, y_ang):
     y = abs(a)[:, indx[1][0]] / np.max(abs(a))
     fwhm2 = abs(x[np.where(y > 0.5)][0] - x[np.where(y > 0.5)][-1])
     return (fwhm1 + fwhm2) / 2
+
+
+# --- compact per-ray samples for the irregular-sample far field (north_star) -------------------
+def near_field_samples(tele_geo, rx, *, device: bool = False):
+    """Trace the bundle of one feed and return the near field ON THE RAY POSITIONS as samples
+    ``[n_scan**2, 4]`` float32 ``{x_sim [cm], y_sim [cm], Re b, Im b}`` with ``b = a exp(i p)``,
+    ``p = k (OPL - <OPL>)/1e3/2`` (invalid rays are all-zero rows, so they drop out of any sum),
+    plus the statistics row.  This is the input format of :func:`opt_analyze.far_field_irregular`
+    (pass the tensor with ``device=True`` to stay on the GPU): no gridding between the ray trace
+    and the far field.  One trace: the phase is first referred to OPL = 0 inside the kernel and
+    the global factor ``exp(-i k <OPL>/2e3)`` is applied afterwards."""
+    lib = _lib.require_gpu()
+    torch = _torch()
+    n_scan = int(tele_geo.n_scan)
+    n = n_scan * n_scan
+    _upload_geometry(lib, torch, tele_geo)
+    freq = geometry.make_freq(tele_geo)
+    rxa = _rx_array(rx)
+    xyb = torch.empty((n, 4), dtype=torch.float32, device="cuda")
+    stats = torch.zeros(_lib.NUM_STATS, dtype=torch.float64, device="cuda")
+    _lib.check(lib.sosat_trace_samples(
+        rxa.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.byref(freq), n_scan, 0, n, 0.0,
+        ctypes.c_void_p(xyb.data_ptr()), ctypes.c_void_p(stats.data_ptr()), _stream(torch)))
+    h_stats = stats.cpu().numpy()
+    if h_stats[_lib.STAT_N_BRACKET_FAIL] > 0:
+        raise ValueError("f(a) and f(b) must have different signs")
+    nv = h_stats[_lib.STAT_N_VALID]
+    mean_opl = h_stats[_lib.STAT_SUM_OPL] / nv if nv > 0 else 0.0
+    phi0 = float(np.mod(geometry.scalar(tele_geo.k) / 1e3 / 2 * mean_opl, 2 * np.pi))
+    b = torch.view_as_complex(xyb[:, 2:4].contiguous()) * complex(np.cos(phi0), -np.sin(phi0))
+    xyb[:, 2:4] = torch.view_as_real(b)
+    return (xyb if device else xyb.cpu().numpy()), h_stats
 
 
 # --- on-device reductions for sweeps (SURVEY section 8 row f2) -------------------------------

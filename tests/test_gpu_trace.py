@@ -489,3 +489,33 @@ def test_launch_angle_tables_and_direct_sincos_agree_with_the_oracle(mods, n_sca
     assert np.abs(cnt[0].cpu().numpy() - rcnt).sum() <= 4        # rays sitting on a cell edge
     assert np.abs(re[0, 0].cpu().numpy() - rre).max() < 2e-3 * np.abs(rre).max()
     assert np.abs(im[0, 0].cpu().numpy() - rim).max() < 2e-3 * np.abs(rre).max()
+
+
+def test_irregular_route_trace_samples_to_direct_sum_far_field(mods):
+    """north_star's irregular-sample route end to end on the device: compact float4 samples from
+    the tracer (16 B/ray) straight into the direct-sum far field, against the oracle's rays and
+    the numpy direct sum.  Also the sample rows themselves against getNearField."""
+    rt, oa, oracle = mods["rt"], mods["oa"], mods["oracle"]
+    t = _bundle(mods, 120)
+    t.th_fwhp_x = t.th_fwhp_y = np.deg2rad(28.0)
+    rx = [40, 0, -25]
+    xyb, st = rt.near_field_samples(t, rx)
+    assert xyb.shape == (120 * 120, 4) and xyb.dtype == np.float32
+    ref = oracle.rx_to_lyot(rx, t)
+    sb = oracle.get_near_field(t, rx, out=ref)
+    sel = ref[4] != 0
+    assert int(st[0]) == sel.sum() and ((np.abs(xyb).sum(axis=1) != 0) == sel).all()
+    assert np.abs(xyb[sel, 0] - sb.x_sim).max() < 1e-5 and np.abs(xyb[sel, 1] - sb.y_sim).max() < 1e-5
+    k = float(t.k)
+    p = k * (ref[3][sel] - ref[3][sel].mean()) / 1e3 / 2
+    bref = ref[4][sel] * np.exp(1j * p)
+    bgpu = xyb[sel, 2] + 1j * xyb[sel, 3]
+    assert np.abs(np.abs(bgpu) / np.abs(bref) - 1).max() < AMP_RTOL
+    assert phase_diff(np.angle(bgpu), np.angle(bref)).max() < PHASE_ATOL
+    th = np.linspace(-0.012, 0.012, 25)
+    TX, TY = np.meshgrid(th, th)
+    lam_cm = float(t.lambda_) * 100.0
+    dev, _ = rt.near_field_samples(t, rx, device=True)
+    B = oa.far_field_irregular(dev, None, None, TX, TY, lam_cm)
+    Bref = oracle.nudft_direct(sb.x_sim, sb.y_sim, bref, TX.ravel(), TY.ravel(), lam_cm).reshape(TX.shape)
+    assert np.abs(B - Bref).max() < 1e-4 * np.abs(Bref).max()
