@@ -22,6 +22,11 @@
  *   - numerical invalidity is not an error: an invalid ray gets amplitude = OPL = 0 exactly
  *     like ray_trace.py:1578-1580.
  *   - there is no CPU fallback anywhere in this library.
+ *   - threading: one host process per GPU is the intended use (torch.distributed for several).
+ *     Calls on one device may come from several host threads; the plan registry of the DFT
+ *     workspaces is mutex-protected.  The geometry and the per-call frequency table are
+ *     per-DEVICE __constant__ state written in stream order: trace calls that use different
+ *     geometries or frequency lists must not overlap on different streams of the same device.
  */
 #ifndef SOSAT_B200_H
 #define SOSAT_B200_H

@@ -29,6 +29,7 @@
 
 #include <cstdlib>
 #include <cstring>
+#include <mutex>
 
 #include "common.cuh"
 
@@ -715,6 +716,7 @@ struct PlanEntry {
 };
 static PlanEntry g_plans[64];
 static int g_num_plans = 0;
+static std::mutex g_plan_mutex;  // the registry is shared by all host threads of the process
 
 // The three centred transforms of opt_analyze.py as (output shift, input shift, sign, scale):
 //   FORWARD   fftshift(fft2(fftshift(x)))      a2b :225-228, beam_convolve :76-82
@@ -734,16 +736,18 @@ static int dft_kind_params(int kind, int n, int &so, int &si, int &sign, double 
 // dimension is always even, the other one only when np is a multiple of 256.
 constexpr int kKindZoom = 100;  // twiddles written by the caller (sosat_dft2_zoom): never cached
 
-static int ensure_plan(const DftWorkspace &w, int kind, cudaStream_t st, const PlanEntry **out) {
+// Returns a COPY of the plan (descriptors included): another host thread may re-plan the slot.
+static int ensure_plan(const DftWorkspace &w, int kind, cudaStream_t st, PlanEntry *out) {
     int dev = 0, so = 0, si = 0, sign = 0;
     double scale;
     SOSAT_CUDA_OK(cudaGetDevice(&dev));
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
     if (kind != kKindZoom)
         if (int rc = dft_kind_params(kind, w.n, so, si, sign, scale)) return rc;
     for (int i = 0; i < g_num_plans; ++i)
         if (g_plans[i].device == dev && g_plans[i].ws == w.base && g_plans[i].n == w.n &&
             g_plans[i].kind == kind && kind != kKindZoom) {
-            *out = &g_plans[i];
+            *out = g_plans[i];
             return 0;
         }
     PlanEntry e;
@@ -789,7 +793,7 @@ static int ensure_plan(const DftWorkspace &w, int kind, cudaStream_t st, const P
         if (g_plans[i].device == dev && g_plans[i].ws == w.base) slot = i;  // same buffer, re-planned
     if (slot < 0) slot = g_num_plans < 64 ? g_num_plans++ : 0;
     g_plans[slot] = e;
-    *out = &g_plans[slot];
+    *out = e;
     return 0;
 }
 
@@ -928,6 +932,7 @@ using namespace sosat;
 extern "C" size_t sosat_dft2_workspace_bytes(int n) { return n >= 1 ? workspace_bytes(n) : 0; }
 
 extern "C" int sosat_dft2_forget(const void *d_workspace) {
+    std::lock_guard<std::mutex> lock(g_plan_mutex);
     for (int i = 0; i < g_num_plans; ++i)
         if (g_plans[i].ws == d_workspace) g_plans[i] = g_plans[--g_num_plans], --i;
     return SOSAT_OK;
@@ -942,12 +947,12 @@ extern "C" int sosat_dft2_gemm_kind(const float *d_b, int n, float *d_B, int kin
     if (int rc = dft_kind_params(kind, n, so, si, sign, scale)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     DftWorkspace w = carve(d_workspace, n);
-    const PlanEntry *pl = nullptr;
+    PlanEntry pl;
     if (int rc = ensure_plan(w, kind, st, &pl)) return rc;
     const dim3 grid(w.np / 32, w.np / 32);
     if (int rc = launch_pdl(prep_b_c64_kernel, grid, dim3(32, 8), 0, st, 1, 1, (const float2 *)d_b, n,
                             w.np, w.b1_hi, w.b1_lo)) return rc;
-    return run_passes(w, *pl, (float)scale, d_B, st);
+    return run_passes(w, pl, (float)scale, d_B, st);
 }
 
 extern "C" int sosat_dft2_zoom(const float *d_b, int n, float *d_B, int n_out, const double *h_y,
@@ -960,7 +965,7 @@ extern "C" int sosat_dft2_zoom(const float *d_b, int n, float *d_B, int n_out, c
                   pad128(n), n);
     cudaStream_t st = (cudaStream_t)stream;
     DftWorkspace w = carve(d_workspace, n);
-    const PlanEntry *pl = nullptr;
+    PlanEntry pl;
     if (int rc = ensure_plan(w, kKindZoom, st, &pl)) return rc;
     // coordinates and angles staged at the start of the (otherwise unused here) complex64 area
     double *d_y = (double *)w.c64, *d_x = d_y + w.np, *d_thy = d_x + w.np, *d_thx = d_thy + w.np;
@@ -975,7 +980,7 @@ extern "C" int sosat_dft2_zoom(const float *d_b, int n, float *d_B, int n_out, c
     const dim3 grid(w.np / 32, w.np / 32);
     if (int rc = launch_pdl(prep_b_c64_kernel, grid, dim3(32, 8), 0, st, 1, 1, (const float2 *)d_b, n,
                             w.np, w.b1_hi, w.b1_lo)) return rc;
-    return run_passes(w, *pl, 1.0f, d_B, st, n_out);
+    return run_passes(w, pl, 1.0f, d_B, st, n_out);
 }
 
 extern "C" int sosat_dft2_gemm(const float *d_b, int n, float *d_B, void *d_workspace,
@@ -994,12 +999,12 @@ static int amp_phase_transform(const double *d_amp, const double *d_phi_deg, int
     if (int rc = dft_kind_params(kind, n, so, si, sign, scale)) return rc;
     cudaStream_t st = (cudaStream_t)stream;
     DftWorkspace w = carve(d_workspace, n);
-    const PlanEntry *pl = nullptr;
+    PlanEntry pl;
     if (int rc = ensure_plan(w, kind, st, &pl)) return rc;
     const dim3 grid(w.np / 32, w.np / 32);
     if (int rc = launch_pdl(prep_b_a2b_kernel, grid, dim3(32, 8), 0, st, 1, 1, d_amp, d_phi_deg, n,
                             w.np, w.b1_hi, w.b1_lo)) return rc;
-    if (int rc = run_passes(w, *pl, (float)scale, w.c64, st)) return rc;  // complex64 [n][n]
+    if (int rc = run_passes(w, pl, (float)scale, w.c64, st)) return rc;  // complex64 [n][n]
     const long long n2 = (long long)n * n;
     long long blocks = (n2 + 255) / 256;
     if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
