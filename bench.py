@@ -368,7 +368,7 @@ def run_ours(args):
 
     # ---- far-field transform time at 1024^2 and 2048^2 (metric 2) ----
     farfield = {}
-    for n in (1024, 2048):
+    for n in (1024, 2048, 4096):
         d = torch.randn(n, n, dtype=torch.complex64, device="cuda")
         for _ in range(3):
             opt_analyze.far_field(d, device=True)

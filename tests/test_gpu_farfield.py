@@ -348,3 +348,23 @@ def test_zoomed_far_field_on_chosen_angles(mods):
     assert _rel_peak(Bz, direct(b2, x2, 0.5 * th, th)) < FF_TOL
     with pytest.raises(ValueError):
         oa.far_field(b2, dx_cm, lam, theta_x=th)
+
+
+def test_far_field_4096_pair_kernel_at_scale(mods):
+    """Largest size exercised: 4096^2 (32 x 16 pair tiles per pass, 0.94 GB workspace), smooth
+    aperture with a tilt, against numpy's complex128 FFT; plus Parseval as a size-independent
+    property (sum |B|^2 = N^2 sum |b|^2)."""
+    oa = mods["oa"]
+    n = 4096
+    x = (np.arange(n) - n // 2) * 0.0125
+    X, Y = np.meshgrid(x, x)
+    R = np.hypot(X, Y)
+    b = (np.exp(-R ** 2 / (2 * 9.0 ** 2)) * (R < 20) *
+         np.exp(1j * (0.3 * np.cos(X / 3) + 0.05 * (R / 20) ** 4 + 0.1 * Y))).astype(np.complex64)
+    B = oa.far_field(b)
+    ref = np.fft.fftshift(np.fft.fft2(np.fft.fftshift(b.astype(np.complex128))))
+    assert _rel_peak(B, ref) < FF_TOL
+    e_in = float((np.abs(b.astype(np.complex128)) ** 2).sum()) * n * n
+    e_out = float((np.abs(B.astype(np.complex128)) ** 2).sum())
+    assert abs(e_out / e_in - 1) < 1e-4
+    oa.release_workspaces()
