@@ -183,6 +183,14 @@ enum { SOSAT_DFT_FORWARD = 0, SOSAT_DFT_INVERSE = 1, SOSAT_DFT_B2A = 2 };
 int sosat_dft2_gemm_kind(const float *d_b, int n, float *d_B, int kind, void *d_workspace,
                          size_t workspace_bytes, void *stream);
 
+/* Batched form for frequency / receiver sweeps: `batch` fields of one size [batch][n][n] through
+ * one transpose-and-split kernel and ONE launch per UMMA pass (the batch supplies the tiles that
+ * a single 1024^2 transform lacks to fill the machine with cta_group::2 pair tiles).  d_B:
+ * [batch][n][n][2] float32.  Workspace from sosat_dft2_batch_workspace_bytes(n, batch). */
+size_t sosat_dft2_batch_workspace_bytes(int n, int batch);
+int sosat_dft2_gemm_batch(const float *d_b, int n, int batch, float *d_B, int kind,
+                          void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* Zoomed far field on caller-chosen angles (the matrix-DFT form's advantage over
  * an FFT): for j, k < n_out
  *   B[j][k] = sum_{m,n} b[m][n] exp(-2 pi i (y_m thy_j + x_n thx_k) * inv_lambda)

@@ -385,6 +385,18 @@ __device__ __forceinline__ void umma2_commit_mc(uint32_t bar, uint16_t cta_mask)
         " [%0], %1;" ::"r"(bar), "h"(cta_mask) : "memory");
 }
 
+// Batched second pass (sosat_dft2_gemm_batch): the M tiles of all batch items are laid along
+// grid x, every item owns `mtiles` of them; the A operand of item i is the slice
+// D1[l][(c', i np + m)] of the pass-1 output of the whole batch, so k-block kb reads columns
+// (kb / kpc) seg + i kpc 64 + (kb % kpc) 64 of the [np][2 seg] view; the output of item i goes to
+// d_c64 + i out_stride.  All zero = the plain single-transform GEMM.
+struct PairBatch {
+    int kpc;        // k-blocks per c' segment (np / 64)
+    int seg;        // columns per c' segment of the D1 view (batch * np)
+    int mtiles;     // M tiles per batch item (np / 128)
+    long long out_stride;  // floats between the outputs of consecutive items (2 n^2)
+};
+
 template <int EPI, int BN2>
 __global__ void __launch_bounds__(128, 1)
 gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
@@ -392,7 +404,7 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                     const __grid_constant__ CUtensorMap map_b_hi,
                     const __grid_constant__ CUtensorMap map_b_lo, int num_kb, float *__restrict__ d_c64,
                     __nv_bfloat16 *__restrict__ d_hi, __nv_bfloat16 *__restrict__ d_lo, int ldd,
-                    int n_valid, float scale) {
+                    int n_valid, float scale, PairBatch pb) {
     using Cfg = PairCfg<BN2>;
     constexpr int kStages2 = Cfg::kStages, kStageBytes2 = Cfg::kStageBytes,
                   kHalfTileBytes = Cfg::kHalfBytes;
@@ -409,7 +421,10 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     // touches the whole twiddle matrix and DRAM traffic doubles (measured 280 vs 126 MB at 2048^2).
     const unsigned pair_id = (blockIdx.x >> 1) + (gridDim.x >> 1) * blockIdx.y;
     const int n0 = (int)(pair_id % gridDim.y) * BN2;
-    const int m0 = (int)(2 * (pair_id / gridDim.y) + rank) * BM;  // this CTA's own 128 rows of D
+    const int m_tile = (int)(2 * (pair_id / gridDim.y) + rank);  // this CTA's own 128 rows of D
+    const int item = pb.mtiles ? m_tile / pb.mtiles : 0;
+    const int m0 = (m_tile - item * pb.mtiles) * BM;             // rows within the batch item
+    const int a_col0 = item * pb.kpc * BK;
     const bool leader = rank == 0;
 
     if (threadIdx.x == 0) {
@@ -445,8 +460,9 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
             const uint32_t base = smem_u32(smem + s * kStageBytes2);
             if (leader) mbar_expect_tx(full0 + 8 * s, 2 * kStageBytes2);
             else mbar_arrive_cluster(lead_full);
-            tma_load_2d_pair(base, &map_a_hi, lead_full, kb * BK, m0);
-            tma_load_2d_pair(base + kTileBytes, &map_a_lo, lead_full, kb * BK, m0);
+            const int a_col = pb.kpc ? (kb / pb.kpc) * pb.seg + a_col0 + (kb % pb.kpc) * BK : kb * BK;
+            tma_load_2d_pair(base, &map_a_hi, lead_full, a_col, m0);
+            tma_load_2d_pair(base + kTileBytes, &map_a_lo, lead_full, a_col, m0);
             tma_load_2d_pair(base + 2 * kTileBytes, &map_b_hi, lead_full, kb * BK,
                              n0 + (int)rank * (BN2 / 2));
             tma_load_2d_pair(base + 2 * kTileBytes + kHalfTileBytes, &map_b_lo, lead_full, kb * BK,
@@ -481,7 +497,9 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     // ---- epilogue (both CTAs): own 128 TMEM lanes -> global ----
     mbar_wait(accum_bar, 0);
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
-    gemm_epilogue<EPI, BN2>(tmem_base, m0, n0, warp, lane, d_c64, d_hi, d_lo, ldd, n_valid, scale);
+    gemm_epilogue<EPI, BN2>(tmem_base, m0, n0, warp, lane,
+                            d_c64 ? d_c64 + (long long)item * pb.out_stride : nullptr, d_hi, d_lo, ldd,
+                            n_valid, scale);
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     cluster_sync_all();  // both CTAs are done with TMEM and with each other's barriers
     if (warp == 0)
@@ -595,12 +613,16 @@ __device__ __forceinline__ void prep_transposed(Load load, int n, int np, __nv_b
     }
 }
 
+// blockIdx.z = batch item: input item z at b + z n^2, operand rows z np .. (z+1) np
 __global__ void __launch_bounds__(256)
 prep_b_c64_kernel(const float2 *__restrict__ b, int n, int np, __nv_bfloat16 *b_hi,
                   __nv_bfloat16 *b_lo) {
     pdl_wait();
     pdl_launch_dependents();
-    prep_transposed([&](int r, int c) { return b[(size_t)r * n + c]; }, n, np, b_hi, b_lo);
+    const float2 *bz = b + (size_t)blockIdx.z * n * n;
+    const size_t off = (size_t)blockIdx.z * np * 2 * np;
+    prep_transposed([&](int r, int c) { return bz[(size_t)r * n + c]; }, n, np, b_hi + off,
+                    b_lo + off);
 }
 
 // a2b / b2a input: |A| exp(i phi pi/180), opt_analyze.py:211, 224 (amplitude and degrees, float64)
@@ -844,7 +866,7 @@ static int launch_gemm(dim3 grid, cudaStream_t st, const CUtensorMap *m, int num
 template <int EPI, int BN2>
 static int launch_gemm_pair(dim3 grid, cudaStream_t st, const CUtensorMap *m, int num_kb, float *c64,
                             __nv_bfloat16 *d_hi, __nv_bfloat16 *d_lo, int ldd, int n_valid,
-                            float scale) {
+                            float scale, PairBatch pb = PairBatch{0, 0, 0, 0}) {
     static bool attr_set[64] = {false};
     int dev = 0;
     SOSAT_CUDA_OK(cudaGetDevice(&dev));
@@ -855,7 +877,7 @@ static int launch_gemm_pair(dim3 grid, cudaStream_t st, const CUtensorMap *m, in
         attr_set[dev] = true;
     }
     return launch_pdl(gemm2_bf16x3_kernel<EPI, BN2>, grid, dim3(128), PairCfg<BN2>::kSmem, st, 2, 1,
-                      m[0], m[1], m[2], m[3], num_kb, c64, d_hi, d_lo, ldd, n_valid, scale);
+                      m[0], m[1], m[2], m[3], num_kb, c64, d_hi, d_lo, ldd, n_valid, scale, pb);
 }
 
 // Which UMMA kernel runs the passes.  Measured on B200 (1024^2 / 2048^2, ms per transform):
@@ -981,6 +1003,68 @@ extern "C" int sosat_dft2_zoom(const float *d_b, int n, float *d_B, int n_out, c
     if (int rc = launch_pdl(prep_b_c64_kernel, grid, dim3(32, 8), 0, st, 1, 1, (const float2 *)d_b, n,
                             w.np, w.b1_hi, w.b1_lo)) return rc;
     return run_passes(w, pl, 1.0f, d_B, st, n_out);
+}
+
+// ---- batched transform: many fields of one size through ONE pair of UMMA launches -------------
+static size_t batch_workspace_bytes(int n, int batch) {
+    const size_t np = pad128(n);
+    const size_t need = 256 + 32 * np * np + 16 * np * np * (size_t)batch;
+    return need > workspace_bytes(n) ? need : workspace_bytes(n);
+}
+
+extern "C" size_t sosat_dft2_batch_workspace_bytes(int n, int batch) {
+    return (n >= 1 && batch >= 1) ? batch_workspace_bytes(n, batch) : 0;
+}
+
+extern "C" int sosat_dft2_gemm_batch(const float *d_b, int n, int batch, float *d_B, int kind,
+                                     void *d_workspace, size_t workspace_bytes_, void *stream) {
+    SOSAT_REQUIRE(d_b && d_B, "sosat_dft2_gemm_batch: null pointer");
+    SOSAT_REQUIRE(batch >= 1 && batch <= 4096, "batch=%d out of range [1, 4096]", batch);
+    if (int rc = check_ws(d_workspace, workspace_bytes_, n)) return rc;
+    SOSAT_REQUIRE(workspace_bytes_ >= batch_workspace_bytes(n, batch),
+                  "workspace too small for batch %d: %zu < %zu bytes", batch, workspace_bytes_,
+                  batch_workspace_bytes(n, batch));
+    int so, si, sign;
+    double scale;
+    if (int rc = dft_kind_params(kind, n, so, si, sign, scale)) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    DftWorkspace w = carve(d_workspace, n);
+    PlanEntry pl;
+    if (int rc = ensure_plan(w, kind, st, &pl)) return rc;
+    const size_t np = w.np, n2 = (size_t)n * n;
+    if (!(pl.wide && BK == 64)) {
+        // sizes the pair kernel does not take (np not a multiple of 256): one transform at a time
+        const dim3 grid(w.np / 32, w.np / 32);
+        for (int i = 0; i < batch; ++i) {
+            if (int rc = launch_pdl(prep_b_c64_kernel, grid, dim3(32, 8), 0, st, 1, 1,
+                                    (const float2 *)d_b + i * n2, n, w.np, w.b1_hi, w.b1_lo)) return rc;
+            if (int rc = run_passes(w, pl, (float)scale, d_B + 2 * i * n2, st)) return rc;
+        }
+        return SOSAT_OK;
+    }
+    // operands of the whole batch behind the twiddles: X [batch np][2 np], D1 [2 np][batch np]
+    __nv_bfloat16 *xb_hi = w.b1_hi, *xb_lo = xb_hi + 2 * np * np * batch;
+    __nv_bfloat16 *d1_hi = xb_lo + 2 * np * np * batch, *d1_lo = d1_hi + 2 * np * np * batch;
+    CUtensorMap m1[4], m2[4];
+    int rc = 0;
+    m1[0] = pl.pair256[0];
+    m1[1] = pl.pair256[1];
+    if ((rc = make_map(&m1[2], xb_hi, np * batch, 2 * np, 128))) return rc;
+    if ((rc = make_map(&m1[3], xb_lo, np * batch, 2 * np, 128))) return rc;
+    if ((rc = make_map(&m2[0], d1_hi, np, 2 * np * batch, 128))) return rc;
+    if ((rc = make_map(&m2[1], d1_lo, np, 2 * np * batch, 128))) return rc;
+    m2[2] = pl.pair256[6];
+    m2[3] = pl.pair256[7];
+    const dim3 pgrid(w.np / 32, w.np / 32, batch);
+    if ((rc = launch_pdl(prep_b_c64_kernel, pgrid, dim3(32, 8), 0, st, 1, 1, (const float2 *)d_b, n,
+                         w.np, xb_hi, xb_lo))) return rc;
+    const int num_kb = 2 * w.np / BK;
+    if ((rc = launch_gemm_pair<EPI_SPLIT_BF16, 256>(dim3(2 * w.np / BM, w.np * batch / 256), st, m1,
+                                                    num_kb, nullptr, d1_hi, d1_lo, w.np * batch, 0,
+                                                    1.f))) return rc;
+    const PairBatch pb{w.np / BK, w.np * batch, w.np / BM, (long long)(2 * n2)};
+    return launch_gemm_pair<EPI_C64, 256>(dim3(w.np / BM * batch, 2 * w.np / 256), st, m2, num_kb, d_B,
+                                          nullptr, nullptr, 0, w.n, (float)scale, pb);
 }
 
 extern "C" int sosat_dft2_gemm(const float *d_b, int n, float *d_B, void *d_workspace,

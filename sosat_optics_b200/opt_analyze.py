@@ -25,7 +25,8 @@ import numpy as np
 from . import _lib
 from .ray_trace import _stream, _torch
 
-__all__ = ["a2b", "b2a", "beam_convolve", "far_field", "far_field_irregular", "zero_pad",
+__all__ = ["a2b", "b2a", "beam_convolve", "far_field", "far_field_batch", "far_field_irregular",
+           "zero_pad",
            "coords_spat_to_ang", "coords_ang_to_spat", "ghz_to_m", "m_to_ghz", "rad_to_arcmin"]
 
 
@@ -119,6 +120,7 @@ def _workspace(lib, torch, n: int, kind: int = _lib.DFT_FORWARD):
 
 def release_workspaces():
     _workspaces.clear()
+    _batch_workspaces.clear()
 
 
 def a2b(apert, phi):
@@ -260,6 +262,43 @@ def far_field(b, dx_cm=None, lam_m=None, theta_x=None, theta_y=None, *, device: 
     if dx_cm is not None and lam_m is not None:
         return res, far_field_angles(n, float(dx_cm) / 100.0, float(lam_m))
     return res
+
+
+_batch_workspaces = {}
+
+
+def far_field_batch(b, *, device: bool = False):
+    """Centred 2-D DFT of a stack of near fields ``b`` [K, N, N] (numpy complex or CUDA complex64
+    tensor), e.g. all frequencies or receivers of a sweep (``near_field_binned(...).b``): one
+    transpose/split kernel and one launch per UMMA pass for the whole stack, so that sizes too
+    small to fill the GPU on their own (N = 1024) run on the ``cta_group::2`` pair kernel.
+    Returns ``[K, N, N]`` complex64 (numpy, or a CUDA tensor with ``device=True``)."""
+    lib = _lib.require_gpu()
+    torch = _torch()
+    if isinstance(b, np.ndarray):
+        d_b = torch.from_numpy(np.ascontiguousarray(b.astype(np.complex64))).to("cuda")
+    else:
+        d_b = b.to(device="cuda", dtype=torch.complex64).contiguous()
+    if d_b.dim() != 3 or d_b.shape[1] != d_b.shape[2]:
+        raise ValueError("far_field_batch expects a [K, N, N] stack of square fields")
+    k, n = int(d_b.shape[0]), int(d_b.shape[1])
+    out = torch.empty((k, n, n), dtype=torch.complex64, device="cuda")
+    if k == 0:
+        return out if device else out.cpu().numpy()
+    key = (torch.cuda.current_device(), n, k)
+    ws = _batch_workspaces.get(key)
+    if ws is None:
+        for old in [q for q in _batch_workspaces if q[:2] == key[:2]]:  # one stack size per n
+            del _batch_workspaces[old]
+        nbytes = int(lib.sosat_dft2_batch_workspace_bytes(n, k))
+        ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+        ptr = ws.data_ptr()
+        weakref.finalize(ws, lambda p=ptr: lib.sosat_dft2_forget(ctypes.c_void_p(p)))
+        _batch_workspaces[key] = ws
+    _lib.check(lib.sosat_dft2_gemm_batch(ctypes.c_void_p(d_b.data_ptr()), n, k,
+                                         ctypes.c_void_p(out.data_ptr()), _lib.DFT_FORWARD,
+                                         ctypes.c_void_p(ws.data_ptr()), ws.numel(), _stream(torch)))
+    return out if device else out.cpu().numpy()
 
 
 def far_field_angles(n: int, dx_m: float, lam_m: float):

@@ -368,3 +368,19 @@ def test_far_field_4096_pair_kernel_at_scale(mods):
     e_out = float((np.abs(B.astype(np.complex128)) ** 2).sum())
     assert abs(e_out / e_in - 1) < 1e-4
     oa.release_workspaces()
+
+
+@pytest.mark.parametrize("n,k", [(512, 5), (1024, 3), (100, 4), (384, 2)])
+def test_far_field_batch_equals_single_transforms(mods, n, k):
+    """Batched sweep transform: every item equals its own far_field (and numpy's FFT); sizes the
+    pair kernel takes (np % 256 == 0) and sizes that fall back to one transform at a time."""
+    oa = mods["oa"]
+    rng = np.random.default_rng(n + k)
+    b = (rng.standard_normal((k, n, n)) + 1j * rng.standard_normal((k, n, n))).astype(np.complex64)
+    b[1] *= 1e-3  # items of very different scale must not leak into each other
+    B = oa.far_field_batch(b)
+    assert B.shape == (k, n, n) and B.dtype == np.complex64
+    for i in range(k):
+        ref = np.fft.fftshift(np.fft.fft2(np.fft.fftshift(b[i].astype(np.complex128))))
+        assert _rel_peak(B[i], ref) < FF_TOL
+    oa.release_workspaces()
