@@ -224,6 +224,16 @@ def other_configs(torch, ot_geo, opt_analyze, ray_trace, table):
     ms = timed(lambda: ray_trace.trace_bin_device(t, rxs, spec, 512, 420.0), reps=3)
     out["cfg3_receiver_sweep_n1000"] = {"ms": ms, "receivers": len(rxs),
                                         "rays_per_s": len(rxs) * 1e6 / (ms * 1e-3)}
+    # cfg 3 near + far field in one call: fused trace+bin, batched 1024^2 far fields (512^2 near
+    # field zero-padded), on-device FWHM search; host wall time incl. the scalar read-backs
+    ray_trace.beam_sweep(t, rxs[:16], spec, grid_n=512, extent_cm=42.0, pad=256)
+    t0 = time.perf_counter()
+    res = ray_trace.beam_sweep(t, rxs[:16], spec, grid_n=512, extent_cm=42.0, pad=256)
+    wall = time.perf_counter() - t0
+    out["cfg3_beam_sweep_16rx_near_plus_far_1024"] = {
+        "wall_ms": wall * 1e3, "receivers": 16, "rays": 16e6,
+        "fwhm_arcmin_boresight_like": float(np.median(res["fwhm_arcmin"]))}
+    opt_analyze.release_workspaces()
     return out
 
 

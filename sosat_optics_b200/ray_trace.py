@@ -35,7 +35,8 @@ from . import _lib, geometry
 
 __all__ = ["rx_to_lyot", "getNearField", "get_sim", "get_beam_cent", "get_fwhm",
            "get_angle_out", "ff_fwhm_est", "near_field_binned", "trace_stats",
-           "near_field_metrics", "near_field_samples", "ff_fwhm_device", "sim2d", "sim_data",
+           "near_field_metrics", "near_field_samples", "ff_fwhm_device", "beam_sweep", "sim2d",
+           "sim_data",
            "SimOutput", "BinnedField"]
 
 
@@ -444,6 +445,57 @@ def near_field_binned(tele_geo, rx, grid_n: int = 256, extent_cm: Optional[float
         re = re.cpu().numpy() if keep_sums else None
         im = im.cpu().numpy() if keep_sums else None
     return BinnedField(b, out_c, out_s, extent_cm, grid_n, re, im)
+
+
+def beam_sweep(tele_geo, rx_list, freqs, grid_n: int = 256, extent_cm: Optional[float] = None,
+               pad: int = 0):
+    """BASELINE configs[3]: near + far field of every (receiver, frequency) pair of a focal-plane
+    sweep, on the device end to end -- ONE fused trace+bin launch for all receivers and
+    frequencies, ONE batched far-field transform for all fields, and the far-field FWHM search
+    per field; only scalars come back.
+
+    ``freqs``: sequence of ``(k, th_fwhp_x, th_fwhp_y)``; ``pad``: zero cells added on every side
+    of the near field before the transform (finer angle sampling, like ``zero_pad``).  Returns a
+    dict of arrays ``[n_rx, n_freq]``: ``fwhm_arcmin`` (``ff_fwhm_est`` on the true FFT-bin
+    angles), ``peak`` (|B| at the beam peak), ``peak_index`` ``[n_rx, n_freq, 2]``, and per
+    receiver ``n_valid``, ``n_binned``, ``mean_opl``."""
+    from . import opt_analyze
+    torch = _torch()
+    if extent_cm is None:
+        extent_cm = geometry.scalar(getattr(tele_geo, "diam", 0.42)) * 100.0
+    specs = list(freqs)
+    if len(specs) > _lib.MAX_FREQS:
+        raise ValueError(f"at most {_lib.MAX_FREQS} frequencies per sweep call")
+    bf = near_field_binned(tele_geo, rx_list, grid_n, extent_cm, specs, device=True)
+    n_rx, n_freq = bf.b.shape[:2]
+    fields = bf.b.reshape(n_rx * n_freq, grid_n, grid_n)
+    if pad > 0:
+        fields = torch.nn.functional.pad(fields, (pad, pad, pad, pad))
+    n = fields.shape[-1]
+    B = opt_analyze.far_field_batch(fields, device=True)
+    dx_m = extent_cm / grid_n / 100.0
+    fwhm = np.zeros((n_rx, n_freq))
+    peak = np.zeros((n_rx, n_freq))
+    pidx = np.zeros((n_rx, n_freq, 2), dtype=np.int64)
+    lib = _lib.require_gpu()
+    idx = torch.empty(6, dtype=torch.int32, device="cuda")
+    val = torch.empty(1, dtype=torch.float32, device="cuda")
+    work = torch.empty(1, dtype=torch.int64, device="cuda")
+    for i in range(n_rx):
+        for f, (k, _, _) in enumerate(specs):
+            _lib.check(lib.sosat_ff_fwhm_indices(
+                ctypes.c_void_p(B[i * n_freq + f].data_ptr()), n, ctypes.c_void_p(idx.data_ptr()),
+                ctypes.c_void_p(val.data_ptr()), ctypes.c_void_p(work.data_ptr()), _stream(torch)))
+            pr, pc, c0, c1, r0, r1 = (int(v) for v in idx.cpu().numpy())
+            lam = 2 * np.pi / geometry.scalar(k)
+            dth = lam / (n * dx_m) * (180 * 60 / np.pi)  # arcmin per far-field cell
+            fwhm[i, f] = 0.5 * (abs(c1 - c0) + abs(r1 - r0)) * dth
+            peak[i, f] = float(np.sqrt(val.cpu().numpy()[0]))
+            pidx[i, f] = (pr, pc)
+    st = bf.stats
+    return {"fwhm_arcmin": fwhm, "peak": peak, "peak_index": pidx,
+            "n_valid": st[:, _lib.STAT_N_VALID].copy(), "n_binned": st[:, _lib.STAT_N_BINNED].copy(),
+            "mean_opl": bf.mean_opl}
 
 
 def trace_stats(tele_geo, rx):

@@ -519,3 +519,33 @@ def test_irregular_route_trace_samples_to_direct_sum_far_field(mods):
     B = oa.far_field_irregular(dev, None, None, TX, TY, lam_cm)
     Bref = oracle.nudft_direct(sb.x_sim, sb.y_sim, bref, TX.ravel(), TY.ravel(), lam_cm).reshape(TX.shape)
     assert np.abs(B - Bref).max() < 1e-4 * np.abs(Bref).max()
+
+
+def test_beam_sweep_near_and_far_field_of_a_receiver_sweep(mods, feed_table):
+    """configs[3] in one call (fused trace+bin for all receivers and frequencies, batched far
+    field, on-device FWHM search) against the same quantities assembled step by step from the
+    single-field entry points."""
+    rt, oa, geometry = mods["rt"], mods["oa"], mods["geometry"]
+    t = _bundle(mods, 300, y_off=200)
+    rxs = [[0, 0, 0], [100, 0, 60], [-60, 0, -120]]
+    specs = geometry.freq_specs_from_table([90.0, 150.0], feed_table)
+    res = rt.beam_sweep(t, rxs, specs, grid_n=128, extent_cm=42.0, pad=64)
+    assert res["fwhm_arcmin"].shape == (3, 2)
+    bf = rt.near_field_binned(t, rxs, 128, 42.0, specs)
+    assert np.array_equal(res["n_valid"], bf.stats[:, 0])
+    n = 128 + 2 * 64
+    for i in range(3):
+        for f, (k, _, _) in enumerate(specs):
+            b = np.pad(bf.b[i, f], 64)
+            B = oa.far_field(b)
+            lam = 2 * np.pi / float(k)
+            th = oa.far_field_angles(n, 42.0 / 128 / 100.0, lam)
+            x_ang, y_ang = np.meshgrid(th, th)
+            want = rt.ff_fwhm_est(B, x_ang, y_ang)
+            assert res["fwhm_arcmin"][i, f] == pytest.approx(want, rel=1e-6, abs=1e-9)
+            assert res["peak"][i, f] == pytest.approx(np.abs(B).max(), rel=1e-3)
+            assert tuple(res["peak_index"][i, f]) == np.unravel_index(np.argmax(np.abs(B)), B.shape)
+    # the beam narrows with frequency, and off-axis feeds steer it off the centre cell
+    assert (res["fwhm_arcmin"][:, 1] < res["fwhm_arcmin"][:, 0]).all()
+    assert tuple(res["peak_index"][0, 0]) == (n // 2, n // 2)
+    assert tuple(res["peak_index"][1, 0]) != (n // 2, n // 2)
