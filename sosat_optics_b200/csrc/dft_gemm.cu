@@ -507,6 +507,154 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                      "r"(Cfg::kTmem) : "memory");
 }
 
+// ---- persistent CTA-pair kernel: one pair per TPC, two TMEM accumulator stages -----------------
+// The 256 x 256 pair-tile kernel above as a persistent loop: a pair walks the pair tiles
+// t = pair, pair + P, ... and the accumulator alternates between two 256-column TMEM stages, so
+// that the epilogue of tile i (4 dedicated warps per CTA: TMEM -> registers -> global) runs under
+// the mainloop of tile i + 1, and barrier set-up / TMEM allocation / cluster sync happen once per
+// SM instead of once per tile.  Warps: 0 TMA producer, 1 MMA issuer (leader CTA only), 2-5
+// epilogue (warp w drains TMEM lanes 32 (w & 3) ..).  Barriers per CTA: smem ring full/empty as
+// above; tmem_full[a] (the leader's multicast commit, count 1); tmem_empty[a] on the LEADER
+// (count 8: one lane of each epilogue warp of both CTAs, the peer's through mapa).
+constexpr int kPersistThreads = 192;
+
+template <int EPI>
+__global__ void __launch_bounds__(kPersistThreads, 1)
+gemm2p_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
+                     const __grid_constant__ CUtensorMap map_a_lo,
+                     const __grid_constant__ CUtensorMap map_b_hi,
+                     const __grid_constant__ CUtensorMap map_b_lo, int num_kb, int m_pairs,
+                     int n_tiles, float *__restrict__ d_c64, __nv_bfloat16 *__restrict__ d_hi,
+                     __nv_bfloat16 *__restrict__ d_lo, int ldd, int n_valid, float scale,
+                     PairBatch pb) {
+    constexpr int BN2 = 256;
+    using Cfg = PairCfg<BN2>;
+    constexpr int kStages2 = Cfg::kStages, kStageBytes2 = Cfg::kStageBytes,
+                  kHalfTileBytes = Cfg::kHalfBytes;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = (uint64_t *)(smem + kStages2 * kStageBytes2);
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * kStages2 + 4);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages2),
+                   tfull0 = smem_u32(bars + 2 * kStages2), tempty0 = smem_u32(bars + 2 * kStages2 + 2);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();
+    const bool leader = rank == 0;
+    const int pair = blockIdx.x >> 1, n_pairs_resident = gridDim.x >> 1;
+    const int total_tiles = m_pairs * n_tiles;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages2; ++s) {
+            mbar_init(full0 + 8 * s, 2);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(tfull0 + 8 * a, 1);
+            mbar_init(tempty0 + 8 * a, 8);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"(512) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    cluster_sync_all();
+    pdl_wait();
+    pdl_launch_dependents();
+
+    // tile t of this pair -> (m pair, n tile), N fastest (see the rasterisation note above)
+    auto tile_coords = [&](int t, int &m0, int &n0, int &item, int &a_col0) {
+        n0 = (t % n_tiles) * BN2;
+        const int m_tile = 2 * (t / n_tiles) + (int)rank;
+        item = pb.mtiles ? m_tile / pb.mtiles : 0;
+        m0 = (m_tile - item * pb.mtiles) * BM;
+        a_col0 = item * pb.kpc * BK;
+    };
+
+    if (warp == 0 && lane == 0) {
+        // ---- TMA producer ----
+        uint32_t g = 0;  // k-blocks issued so far: ring position and phase run across tiles
+        for (int t = pair; t < total_tiles; t += n_pairs_resident) {
+            int m0, n0, item, a_col0;
+            tile_coords(t, m0, n0, item, a_col0);
+            for (int kb = 0; kb < num_kb; ++kb, ++g) {
+                const uint32_t s = g % kStages2, ph = (g / kStages2) & 1u;
+                mbar_wait(empty0 + 8 * s, ph ^ 1u);
+                const uint32_t lead_full = map_to_cta(full0 + 8 * s, 0);
+                const uint32_t base = smem_u32(smem + s * kStageBytes2);
+                if (leader) mbar_expect_tx(full0 + 8 * s, 2 * kStageBytes2);
+                else mbar_arrive_cluster(lead_full);
+                const int a_col = pb.kpc ? (kb / pb.kpc) * pb.seg + a_col0 + (kb % pb.kpc) * BK : kb * BK;
+                tma_load_2d_pair(base, &map_a_hi, lead_full, a_col, m0);
+                tma_load_2d_pair(base + kTileBytes, &map_a_lo, lead_full, a_col, m0);
+                tma_load_2d_pair(base + 2 * kTileBytes, &map_b_hi, lead_full, kb * BK,
+                                 n0 + (int)rank * (BN2 / 2));
+                tma_load_2d_pair(base + 2 * kTileBytes + kHalfTileBytes, &map_b_lo, lead_full, kb * BK,
+                                 n0 + (int)rank * (BN2 / 2));
+            }
+        }
+    } else if (warp == 1 && lane == 0 && leader) {
+        // ---- MMA issuer ----
+        constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN2);
+        uint32_t g = 0, it = 0;
+        for (int t = pair; t < total_tiles; t += n_pairs_resident, ++it) {
+            const uint32_t a = it & 1u, aph = (it >> 1) & 1u;
+            mbar_wait(tempty0 + 8 * a, aph ^ 1u);  // both CTAs' epilogues drained this stage
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t tmem_d = tmem_base + a * BN2;
+            for (int kb = 0; kb < num_kb; ++kb, ++g) {
+                const uint32_t s = g % kStages2, ph = (g / kStages2) & 1u;
+                mbar_wait(full0 + 8 * s, ph);
+                asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+                const uint32_t base = smem_u32(smem + s * kStageBytes2);
+                const uint64_t a_hi = umma_desc_sw128(base);
+                const uint64_t a_lo = umma_desc_sw128(base + kTileBytes);
+                const uint64_t b_hi = umma_desc_sw128(base + 2 * kTileBytes);
+                const uint64_t b_lo = umma_desc_sw128(base + 2 * kTileBytes + kHalfTileBytes);
+#pragma unroll
+                for (int k = 0; k < BK / UMMA_K; ++k) {
+                    const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+                    umma2_bf16(tmem_d, a_hi + adv, b_hi + adv, idesc, (kb | k) != 0);
+                    umma2_bf16(tmem_d, a_hi + adv, b_lo + adv, idesc, 1u);
+                    umma2_bf16(tmem_d, a_lo + adv, b_hi + adv, idesc, 1u);
+                }
+                umma2_commit_mc(empty0 + 8 * s, (uint16_t)0x3);
+            }
+            umma2_commit_mc(tfull0 + 8 * a, (uint16_t)0x3);  // accumulator stage a is complete
+        }
+    } else if (warp >= 2) {
+        // ---- epilogue warps (both CTAs) ----
+        const int q = warp & 3;  // TMEM lane quarter this warp may access
+        uint32_t it = 0;
+        for (int t = pair; t < total_tiles; t += n_pairs_resident, ++it) {
+            int m0, n0, item, a_col0;
+            tile_coords(t, m0, n0, item, a_col0);
+            const uint32_t a = it & 1u, aph = (it >> 1) & 1u;
+            mbar_wait(tfull0 + 8 * a, aph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            gemm_epilogue<EPI, BN2>(tmem_base + a * BN2, m0, n0, q, lane,
+                                    d_c64 ? d_c64 + (long long)item * pb.out_stride : nullptr, d_hi,
+                                    d_lo, ldd, n_valid, scale);
+            asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+            __syncwarp();
+            if (lane == 0) mbar_arrive_cluster(map_to_cta(tempty0 + 8 * a, 0));
+        }
+    }
+    __syncwarp();
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"(512) : "memory");
+}
+
 // ---- operand preparation (HBM-bound elementwise kernels) -----------------------------------
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
     hi = __float2bfloat16_rn(x);
@@ -880,6 +1028,39 @@ static int launch_gemm_pair(dim3 grid, cudaStream_t st, const CUtensorMap *m, in
                       m[0], m[1], m[2], m[3], num_kb, c64, d_hi, d_lo, ldd, n_valid, scale, pb);
 }
 
+// persistent form of the 256 x 256 pair kernel: grid = one pair per TPC (or per tile if fewer)
+template <int EPI>
+static int launch_gemm_pair_persistent(int m_tiles, int n_tiles256, cudaStream_t st,
+                                       const CUtensorMap *m, int num_kb, float *c64,
+                                       __nv_bfloat16 *d_hi, __nv_bfloat16 *d_lo, int ldd, int n_valid,
+                                       float scale, PairBatch pb = PairBatch{0, 0, 0, 0}) {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    SOSAT_CUDA_OK(cudaGetDevice(&dev));
+    constexpr int smem = PairCfg<256>::kSmem + 64;
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        SOSAT_CUDA_OK(cudaFuncSetAttribute(gemm2p_bf16x3_kernel<EPI>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set[dev] = true;
+    }
+    const int m_pairs = m_tiles / 2, tiles = m_pairs * n_tiles256;
+    int pairs = num_sms() / 2;
+    if (pairs > tiles) pairs = tiles;
+    return launch_pdl(gemm2p_bf16x3_kernel<EPI>, dim3(2 * pairs), dim3(kPersistThreads), smem, st, 2, 1,
+                      m[0], m[1], m[2], m[3], num_kb, m_pairs, n_tiles256, c64, d_hi, d_lo, ldd,
+                      n_valid, scale, pb);
+}
+
+// SOSAT_GEMM_PERSIST=0 selects the one-tile-per-CTA pair kernel for A/B runs
+static bool use_persistent_pair() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SOSAT_GEMM_PERSIST");
+        v = e ? (atoi(e) != 0) : 1;
+    }
+    return v != 0;
+}
+
 // Which UMMA kernel runs the passes.  Measured on B200 (1024^2 / 2048^2, ms per transform):
 //   single-CTA UMMA, 2 x 2 multicast clusters, 128 x 128 tiles   0.071 / 0.353
 //   CTA pair (cta_group::2), 256 x 128 pair tiles               0.089 / 0.527  (N = 128 UMMAs of a
@@ -908,6 +1089,13 @@ static int run_passes(const DftWorkspace &w, const PlanEntry &pl, float scale, f
     int rc;
     const int pw = BK == 64 ? pair_kernel_width(w.np) : 0;
     const unsigned mt1 = 2 * w.np / BM, mt2 = w.np / BM;  // M tiles of pass 1 / pass 2
+    if (pw == 256 && pl.wide && use_persistent_pair()) {
+        if ((rc = launch_gemm_pair_persistent<EPI_SPLIT_BF16>((int)mt1, w.np / 256, st, pl.pair256,
+                                                              num_kb, nullptr, w.d1_hi, w.d1_lo,
+                                                              w.np, 0, 1.f))) return rc;
+        return launch_gemm_pair_persistent<EPI_C64>((int)mt2, 2 * w.np / 256, st, pl.pair256 + 4,
+                                                    num_kb, d_c64, nullptr, nullptr, 0, n_out, scale);
+    }
     if (pw == 256 && pl.wide) {
         if ((rc = launch_gemm_pair<EPI_SPLIT_BF16, 256>(dim3(mt1, w.np / 256), st, pl.pair256, num_kb,
                                                         nullptr, w.d1_hi, w.d1_lo, w.np, 0, 1.f)))
@@ -1059,10 +1247,17 @@ extern "C" int sosat_dft2_gemm_batch(const float *d_b, int n, int batch, float *
     if ((rc = launch_pdl(prep_b_c64_kernel, pgrid, dim3(32, 8), 0, st, 1, 1, (const float2 *)d_b, n,
                          w.np, xb_hi, xb_lo))) return rc;
     const int num_kb = 2 * w.np / BK;
+    const PairBatch pb{w.np / BK, w.np * batch, w.np / BM, (long long)(2 * n2)};
+    if (use_persistent_pair()) {
+        if ((rc = launch_gemm_pair_persistent<EPI_SPLIT_BF16>(2 * w.np / BM, w.np * batch / 256, st, m1,
+                                                              num_kb, nullptr, d1_hi, d1_lo,
+                                                              w.np * batch, 0, 1.f))) return rc;
+        return launch_gemm_pair_persistent<EPI_C64>(w.np / BM * batch, 2 * w.np / 256, st, m2, num_kb,
+                                                    d_B, nullptr, nullptr, 0, w.n, (float)scale, pb);
+    }
     if ((rc = launch_gemm_pair<EPI_SPLIT_BF16, 256>(dim3(2 * w.np / BM, w.np * batch / 256), st, m1,
                                                     num_kb, nullptr, d1_hi, d1_lo, w.np * batch, 0,
                                                     1.f))) return rc;
-    const PairBatch pb{w.np / BK, w.np * batch, w.np / BM, (long long)(2 * n2)};
     return launch_gemm_pair<EPI_C64, 256>(dim3(w.np / BM * batch, 2 * w.np / 256), st, m2, num_kb, d_B,
                                           nullptr, nullptr, 0, w.n, (float)scale, pb);
 }
