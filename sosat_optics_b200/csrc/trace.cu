@@ -168,6 +168,16 @@ constexpr int kTileH = 2 * kBinWarps;
 #define SOSAT_BIN_NR 1
 #endif
 constexpr int kNR = SOSAT_BIN_NR;
+// Optional shared-memory bin tile (north_star: "shuffle, then shared-memory atomics"): the run
+// heads of all warps of a CTA add into an 8 x 8-bin window anchored at the CTA's smallest bin
+// coordinates (red.shared), and 64 threads flush the window with one global reduction per
+// touched cell and plane.  Costs two more CTA barriers per tile; single-frequency launches only.
+// Measured at configs[4] density: see DESIGN.md section 3 (off by default).
+#ifndef SOSAT_BIN_SMEM_TILE
+#define SOSAT_BIN_SMEM_TILE 0
+#endif
+constexpr int kWin = 8;  // window edge in bins
+static_assert(kWin > 0, "");
 constexpr int kTileW = kTile * kNR;
 constexpr int kTileMax = kTileH > kTileW ? kTileH : kTileW;
 
@@ -213,10 +223,19 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
     __shared__ double s_sum[4][kBinThreads];
     __shared__ unsigned long long s_valid_binned;  // n_valid | n_binned << 32
     __shared__ unsigned s_rare[2];                 // n_slow, n_bracket_fail
+#if SOSAT_BIN_SMEM_TILE
+    __shared__ float s_win[3][kWin * kWin];        // re, im, count of the CTA's bin window
+    __shared__ int s_win_min[2];                   // smallest ix, iz of the tile's binned rays
+#endif
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lth = (lane & 7) + 8 * (warp & 1);
     const int lph = (lane >> 3) + 4 * (warp >> 1);
+#if SOSAT_BIN_SMEM_TILE
+    const bool use_win = re != nullptr && p.n_freq == 1;
+    if (tid < kWin * kWin) s_win[0][tid] = s_win[1][tid] = s_win[2][tid] = 0.f;
+    if (tid < 2) s_win_min[tid] = 0x7fffffff;
+#endif
 
 #pragma unroll
     for (int q = 0; q < 4; ++q) s_sum[q][tid] = 0.0;
@@ -365,6 +384,9 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
             if (lane == 0 && vmask)
                 atomicAdd(&s_valid_binned, (unsigned long long)__popc(vmask) |
                                                ((unsigned long long)__popc(bmask) << 32));
+#if SOSAT_BIN_SMEM_TILE
+            if (use_win) continue;  // binned below, CTA-wide
+#endif
             if (re == nullptr || bmask == 0u) continue;
 
             // ---- run-length aggregation along the lane order --------------------------------
@@ -375,6 +397,9 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
             const unsigned m = ((heads >> lane) >> 1) | (1u << (31 - lane));
             const int rest = __ffs(m) - 1;  // lanes lane+1 .. lane+rest continue this lane's run
             const bool flush = head && bin >= 0;
+#if SOSAT_BIN_SMEM_TILE
+            if (use_win) continue;  // handled below, after the CTA agrees on the window origin
+#endif
             if (flush) atomicAdd(cnt + (long long)irx * plane + bin, (float)(rest + 1));
 
             const double dopl = r.opl - p.opl_ref;
@@ -408,6 +433,80 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
                 }
             }
         }
+#if SOSAT_BIN_SMEM_TILE
+        if (use_win) {
+            static_assert(kNR == 1, "the shared-memory bin window handles one ray per thread");
+            // every thread of the CTA comes through here (no early continue above in this mode)
+            RayResult &r = rr[0];
+            const bool live = tx * kTileW + lth < p.n_scan && iph < p.n_rows;
+            int bin = -1, ix = 0x7fffffff, iz = 0x7fffffff;
+            if (live && r.valid) {
+                const int jx = __double2int_rd((r.ax + p.half_extent) * p.inv_cell);
+                const int jz = __double2int_rd((r.az + p.half_extent) * p.inv_cell);
+                if ((unsigned)jx < (unsigned)p.grid_n && (unsigned)jz < (unsigned)p.grid_n) {
+                    bin = jz * p.grid_n + jx;
+                    ix = jx;
+                    iz = jz;
+                }
+            }
+            const int wx = __reduce_min_sync(0xffffffffu, ix), wz = __reduce_min_sync(0xffffffffu, iz);
+            if (lane == 0 && wx != 0x7fffffff) {
+                atomicMin(&s_win_min[0], wx);
+                atomicMin(&s_win_min[1], wz);
+            }
+            __syncthreads();
+            const int ox = s_win_min[0], oz = s_win_min[1];
+            const int prev = __shfl_up_sync(0xffffffffu, bin, 1);
+            const bool head = lane == 0 || prev != bin;
+            const unsigned heads = __ballot_sync(0xffffffffu, head);
+            const unsigned m = ((heads >> lane) >> 1) | (1u << (31 - lane));
+            const int rest = __ffs(m) - 1;
+            float vre = 0.f, vim = 0.f;
+            if (bin >= 0) {
+                const float a = s_amp[0][0][lth] * s_amp[0][1][lph];
+                double cyc = (r.opl - p.opl_ref) * g_freq.kk[0];
+                cyc -= __dadd_rn(__dadd_rn(cyc, 6755399441055744.0), -6755399441055744.0);
+                float sn, cs;
+                __sincosf(6.2831853071795865f * (float)cyc, &sn, &cs);
+                vre = a * cs;
+                vim = a * sn;
+            }
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) {
+                const float ore = __shfl_down_sync(0xffffffffu, vre, o);
+                const float oim = __shfl_down_sync(0xffffffffu, vim, o);
+                if (o <= rest) {
+                    vre += ore;
+                    vim += oim;
+                }
+            }
+            if (head && bin >= 0) {
+                const int dx = ix - ox, dz = iz - oz;
+                if (dx < kWin && dz < kWin) {  // shared-memory atomics into the CTA's window
+                    atomicAdd(&s_win[0][dz * kWin + dx], vre);
+                    atomicAdd(&s_win[1][dz * kWin + dx], vim);
+                    atomicAdd(&s_win[2][dz * kWin + dx], (float)(rest + 1));
+                } else {  // outliers (wild rays) go straight to global memory
+                    atomicAdd(re + (long long)irx * plane + bin, vre);
+                    atomicAdd(im + (long long)irx * plane + bin, vim);
+                    atomicAdd(cnt + (long long)irx * plane + bin, (float)(rest + 1));
+                }
+            }
+            __syncthreads();
+            if (tid < kWin * kWin) {
+                const float c = s_win[2][tid];
+                if (c != 0.f) {
+                    const int gx = ox + (tid & (kWin - 1)), gz = oz + tid / kWin;
+                    const long long g = (long long)irx * plane + (long long)gz * p.grid_n + gx;
+                    atomicAdd(re + g, s_win[0][tid]);
+                    atomicAdd(im + g, s_win[1][tid]);
+                    atomicAdd(cnt + g, c);
+                    s_win[0][tid] = s_win[1][tid] = s_win[2][tid] = 0.f;
+                }
+            }
+            if (tid < 2) s_win_min[tid] = 0x7fffffff;  // ordered by the barrier at the next tile's top
+        }
+#endif
     }
     if (acc_rx >= 0) flush_stats(acc_rx);
 }
