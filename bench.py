@@ -279,7 +279,7 @@ def run_ours(args):
         if kernel_events is not None:
             kernel_events[1].record()
         sdist.reduce_bins(re, im, cnt, stats, flat=planes_flat)
-        b, _ = ray_trace.bins_to_field_device(re, im, cnt, stats, spec)
+        b, _ = ray_trace.bins_to_field_device(re, im, cnt, stats, spec, sync=False)
         if kernel_events is not None:
             kernel_events[2].record()
         B = opt_analyze.far_field(b[0, 0], device=True)

@@ -159,6 +159,13 @@ int sosat_trace_bin(const double *d_rx, int n_rx, const sosat_freq_t *h_freq, in
 int sosat_bins_to_field(const float *d_re, const float *d_im, const float *d_cnt, int64_t n,
                         double phase_offset_rad, float *d_b, void *stream);
 
+/* The same with the phase reference taken on the device: phase_offset = k_over_2e3 *
+ * (mean OPL - opl_ref), mean OPL = d_stats[SUM_OPL] / d_stats[N_VALID] of the (already reduced)
+ * statistics row of this receiver -- no host round trip between the trace and the far field. */
+int sosat_bins_to_field_stats(const float *d_re, const float *d_im, const float *d_cnt, int64_t n,
+                              const double *d_stats, double k_over_2e3, double opl_ref,
+                              float *d_b, void *stream);
+
 /* ---- stage 2: far-field transform (opt_analyze.py:220-230 a2b) ----------------------- */
 /* B = W_r b W_c^T, W[k,n] = exp(-2 pi i (k - floor(N/2)) (n - ceil(N/2)) / N): identical to
  * fftshift(fft2(fftshift(b))).  Dense separable complex contraction executed as two

@@ -57,6 +57,8 @@ SIGNATURES = {
                                 c_void_p, c_void_p]),
     "sosat_bins_to_field": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p,
                                     c_void_p]),
+    "sosat_bins_to_field_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_double,
+                                          c_double, c_void_p, c_void_p]),
     "sosat_dft2_workspace_bytes": (c_size_t, [c_int]),
     "sosat_dft2_forget": (c_int, [c_void_p]),
     "sosat_dft2_gemm": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),

@@ -586,6 +586,30 @@ __global__ void bins_to_field_kernel(const float *__restrict__ re, const float *
     }
 }
 
+// Same normalisation with the phase reference taken on the device from the statistics row of the
+// launch (mean OPL of the valid rays): no host round trip between the trace and the far field.
+__global__ void bins_to_field_stats_kernel(const float *__restrict__ re, const float *__restrict__ im,
+                                           const float *__restrict__ cnt, long long n,
+                                           const double *__restrict__ stats, double k_over_2e3,
+                                           double opl_ref, float2 *__restrict__ b) {
+    const double nv = stats[SOSAT_STAT_N_VALID];
+    const double mean_opl = nv > 0 ? stats[SOSAT_STAT_SUM_OPL] / nv : 0.0;
+    double sn, cs;
+    sincos(k_over_2e3 * (mean_opl - opl_ref), &sn, &cs);
+    const float fcs = (float)cs, fsn = (float)sn;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float c = cnt[i];
+        float2 v = make_float2(0.f, 0.f);
+        if (c > 0.f) {
+            const float inv = 1.0f / c, x = re[i] * inv, y = im[i] * inv;
+            v.x = x * fcs + y * fsn;  // (x + i y) * exp(-i phi0)
+            v.y = y * fcs - x * fsn;
+        }
+        b[i] = v;
+    }
+}
+
 // ---- FP64 FMA throughput microkernel (roofline denominator of K1) ---------------------------
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b) {
     double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
@@ -903,6 +927,21 @@ extern "C" int sosat_bins_to_field(const float *d_re, const float *d_im, const f
     bins_to_field_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         d_re, d_im, d_cnt, n, (float)cos(phase_offset_rad), (float)sin(phase_offset_rad),
         (float2 *)d_b);
+    SOSAT_CUDA_OK(cudaGetLastError());
+    return SOSAT_OK;
+}
+
+extern "C" int sosat_bins_to_field_stats(const float *d_re, const float *d_im, const float *d_cnt,
+                                         int64_t n, const double *d_stats, double k_over_2e3,
+                                         double opl_ref, float *d_b, void *stream) {
+    SOSAT_REQUIRE(d_re && d_im && d_cnt && d_stats && d_b, "sosat_bins_to_field_stats: null pointer");
+    SOSAT_REQUIRE(n >= 0, "negative cell count");
+    if (n == 0) return SOSAT_OK;
+    long long blocks = (n + 255) / 256;
+    const long long cap = (long long)num_sms() * 8;
+    if (blocks > cap) blocks = cap;
+    bins_to_field_stats_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
+        d_re, d_im, d_cnt, n, d_stats, k_over_2e3, opl_ref, (float2 *)d_b);
     SOSAT_CUDA_OK(cudaGetLastError());
     return SOSAT_OK;
 }

@@ -388,13 +388,26 @@ def trace_bin_device(tele_geo, rx_list, freq_specs, grid_n, extent_mm, *, opl_re
     return re, im, cnt, stats
 
 
-def bins_to_field_device(re, im, cnt, stats, freq_specs, opl_ref=0.0):
+def bins_to_field_device(re, im, cnt, stats, freq_specs, opl_ref=0.0, *, sync: bool = True):
     """Normalise the accumulators to the mean field per cell and refer the phase to the mean
-    OPL of the valid rays (the reference's ``OPL - mean(OPL)``, ray_trace.py:1601)."""
+    OPL of the valid rays (the reference's ``OPL - mean(OPL)``, ray_trace.py:1601).
+
+    ``sync=False``: the mean OPL is read from ``stats`` ON THE DEVICE
+    (``sosat_bins_to_field_stats``), nothing is copied to the host and ``(b, None)`` is
+    returned, so trace -> field -> far field is one uninterrupted stream of launches."""
     lib = _lib.require_gpu()
     torch = _torch()
     n_rx, n_freq, n, _ = re.shape
     b = torch.empty((n_rx, n_freq, n, n, 2), dtype=torch.float32, device="cuda")
+    if not sync:
+        for i in range(n_rx):
+            for f, (k, _, _) in enumerate(freq_specs):
+                _lib.check(lib.sosat_bins_to_field_stats(
+                    ctypes.c_void_p(re[i, f].data_ptr()), ctypes.c_void_p(im[i, f].data_ptr()),
+                    ctypes.c_void_p(cnt[i].data_ptr()), n * n, ctypes.c_void_p(stats[i].data_ptr()),
+                    geometry.scalar(k) / 1e3 / 2, float(opl_ref),
+                    ctypes.c_void_p(b[i, f].data_ptr()), _stream(torch)))
+        return torch.view_as_complex(b), None
     h_stats = stats.cpu().numpy()
     for i in range(n_rx):
         nv = h_stats[i, _lib.STAT_N_VALID]

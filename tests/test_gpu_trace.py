@@ -549,3 +549,17 @@ def test_beam_sweep_near_and_far_field_of_a_receiver_sweep(mods, feed_table):
     assert (res["fwhm_arcmin"][:, 1] < res["fwhm_arcmin"][:, 0]).all()
     assert tuple(res["peak_index"][0, 0]) == (n // 2, n // 2)
     assert tuple(res["peak_index"][1, 0]) != (n // 2, n // 2)
+
+
+def test_bins_to_field_on_device_statistics(mods, feed_table):
+    """The normalisation with the phase reference read from the statistics on the device equals
+    the host-synchronising form (two receivers, two frequencies)."""
+    rt, geometry, torch = mods["rt"], mods["geometry"], mods["torch"]
+    t = _bundle(mods, 200)
+    specs = geometry.freq_specs_from_table([90.0, 150.0], feed_table)
+    rxs = np.array([[0.0, 0, 0], [80, 0, -50]])
+    re, im, cnt, st = rt.trace_bin_device(t, rxs, specs, 64, 420.0)
+    b_host, h = rt.bins_to_field_device(re, im, cnt, st, specs)
+    b_dev, none = rt.bins_to_field_device(re, im, cnt, st, specs, sync=False)
+    assert none is None and h.shape == (2, 8)
+    assert (b_host - b_dev).abs().max().item() < 2e-6 * b_host.abs().max().item()
