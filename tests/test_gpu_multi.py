@@ -64,3 +64,43 @@ def test_two_gpu_ray_sharding_matches_single_gpu():
         assert np.abs(b - one.b).max() < 1e-4 * np.abs(one.b).max()
         assert np.array_equal(stats[:, [0, 7]], one.stats[:, [0, 7]])
         assert np.allclose(stats[:, 1], one.stats[:, 1], rtol=1e-12)
+
+
+def test_side_stream_and_second_device_in_one_process():
+    """The library launches on the caller's current stream and keeps per-device state
+    (geometry in __constant__ memory, DFT plans): the same calls on a side stream, and on
+    cuda:1 of the same process when there is one, give the default-stream / cuda:0 results."""
+    import torch
+    from sosat_optics_b200 import opt_analyze, ot_geo, ray_trace
+    t = ot_geo.SatGeo()
+    t.n_scan = 96
+    t.y_source = ot_geo.y_lyot + 300
+    t.lambda_ = opt_analyze.ghz_to_m(90)
+    t.k = 2 * np.pi / t.lambda_
+    rng = np.random.default_rng(11)
+    b = (rng.standard_normal((200, 200)) + 1j * rng.standard_normal((200, 200))).astype(np.complex64)
+
+    def run():
+        bf = ray_trace.near_field_binned(t, [25, 0, -40], grid_n=48, extent_cm=42.0)
+        return bf.b.copy(), bf.count.copy(), opt_analyze.far_field(b), ray_trace.rx_to_lyot([25, 0, -40], t)
+
+    torch.cuda.set_device(0)
+    base = run()
+    side = torch.cuda.Stream()
+    with torch.cuda.stream(side):
+        on_side = run()
+    side.synchronize()
+    devices = [("side stream", on_side)]
+    if torch.cuda.device_count() >= 2:
+        torch.cuda.set_device(1)
+        try:
+            devices.append(("cuda:1", run()))
+        finally:
+            torch.cuda.set_device(0)
+    for name, got in devices:
+        assert np.array_equal(got[1], base[1]), name
+        assert np.abs(got[0] - base[0]).max() <= 1e-5 * np.abs(base[0]).max(), name
+        assert np.abs(got[2] - base[2]).max() <= 1e-6 * np.abs(base[2]).max(), name
+        assert np.array_equal(np.nan_to_num(got[3]), np.nan_to_num(base[3])), name
+    again = run()  # and device 0 still has its own geometry / plans
+    assert np.array_equal(again[1], base[1])
