@@ -153,11 +153,13 @@ __host__ __device__ constexpr uint32_t umma_idesc_bf16(int m, int n) {
            ((uint32_t)(m >> 4) << 24);
 }
 
-enum { EPI_C64 = 0, EPI_SPLIT_BF16 = 1 };
+enum { EPI_C64 = 0, EPI_SPLIT_BF16 = 1, EPI_RED_C64 = 2, EPI_RED_F32 = 3 };
 
 // TMEM accumulator tile (128 lanes x 128 fp32 columns) -> registers -> global.
 //   EPI_SPLIT_BF16: bf16 hi/lo planes d_hi/d_lo [M][ldd]
 //   EPI_C64:        times scale -> d_c64 [n_valid][2 n_valid] floats = complex64 [n][n]
+//   EPI_RED_C64:    the same with red.global.add (split-K partial sums into a zeroed output)
+//   EPI_RED_F32:    red.global.add.v4.f32 into the zeroed dense fp32 matrix d_c64 [M][ldd]
 template <int EPI, int NCOLS = BN>
 __device__ __forceinline__ void gemm_epilogue(uint32_t tmem_base, int m0, int n0, int warp, int lane,
                                               float *__restrict__ d_c64,
@@ -169,24 +171,37 @@ __device__ __forceinline__ void gemm_epilogue(uint32_t tmem_base, int m0, int n0
     for (int c = 0; c < NCOLS / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
-        if (EPI == EPI_C64) {
+        if (EPI == EPI_RED_F32) {
+            float4 *dst = (float4 *)(d_c64 + (size_t)row * ldd + n0 + c * 32);
+#pragma unroll
+            for (int q = 0; q < 8; ++q)
+                atomicAdd(dst + q, make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                                               __uint_as_float(v[4 * q + 2]),
+                                               __uint_as_float(v[4 * q + 3])));
+        } else if (EPI == EPI_C64 || EPI == EPI_RED_C64) {
             // row = l, columns = (k, re|im) interleaved: the complex64 row of B, n_valid wide
             const int j0 = n0 + c * 32;
             if (row < n_valid && j0 < 2 * n_valid) {
                 float *dst = d_c64 + (size_t)row * (2 * (size_t)n_valid) + j0;
                 if ((n_valid & 1) == 0 && j0 + 32 <= 2 * n_valid) {
 #pragma unroll
-                    for (int q = 0; q < 8; ++q)
-                        ((float4 *)dst)[q] = make_float4(scale * __uint_as_float(v[4 * q]),
-                                                         scale * __uint_as_float(v[4 * q + 1]),
-                                                         scale * __uint_as_float(v[4 * q + 2]),
-                                                         scale * __uint_as_float(v[4 * q + 3]));
+                    for (int q = 0; q < 8; ++q) {
+                        const float4 o = make_float4(scale * __uint_as_float(v[4 * q]),
+                                                     scale * __uint_as_float(v[4 * q + 1]),
+                                                     scale * __uint_as_float(v[4 * q + 2]),
+                                                     scale * __uint_as_float(v[4 * q + 3]));
+                        if (EPI == EPI_RED_C64) atomicAdd((float4 *)dst + q, o);
+                        else ((float4 *)dst)[q] = o;
+                    }
                 } else {
 #pragma unroll
                     for (int q = 0; q < 16; ++q)
-                        if (j0 + 2 * q + 1 < 2 * n_valid)
-                            ((float2 *)dst)[q] = make_float2(scale * __uint_as_float(v[2 * q]),
-                                                             scale * __uint_as_float(v[2 * q + 1]));
+                        if (j0 + 2 * q + 1 < 2 * n_valid) {
+                            const float2 o = make_float2(scale * __uint_as_float(v[2 * q]),
+                                                         scale * __uint_as_float(v[2 * q + 1]));
+                            if (EPI == EPI_RED_C64) atomicAdd((float2 *)dst + q, o);
+                            else ((float2 *)dst)[q] = o;
+                        }
                 }
             }
         } else {
@@ -524,9 +539,9 @@ gemm2p_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                      const __grid_constant__ CUtensorMap map_a_lo,
                      const __grid_constant__ CUtensorMap map_b_hi,
                      const __grid_constant__ CUtensorMap map_b_lo, int num_kb, int m_pairs,
-                     int n_tiles, float *__restrict__ d_c64, __nv_bfloat16 *__restrict__ d_hi,
-                     __nv_bfloat16 *__restrict__ d_lo, int ldd, int n_valid, float scale,
-                     PairBatch pb) {
+                     int n_tiles, int ksplit, float *__restrict__ d_c64,
+                     __nv_bfloat16 *__restrict__ d_hi, __nv_bfloat16 *__restrict__ d_lo, int ldd,
+                     int n_valid, float scale, PairBatch pb) {
     constexpr int BN2 = 256;
     using Cfg = PairCfg<BN2>;
     constexpr int kStages2 = Cfg::kStages, kStageBytes2 = Cfg::kStageBytes,
@@ -541,7 +556,11 @@ gemm2p_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     const uint32_t rank = cluster_ctarank();
     const bool leader = rank == 0;
     const int pair = blockIdx.x >> 1, n_pairs_resident = gridDim.x >> 1;
-    const int total_tiles = m_pairs * n_tiles;
+    // work item = (pair tile, K slice): with ksplit > 1 the slices of a tile run on different
+    // pairs and meet in the output through red.global.add (EPI_RED_*), so that sizes with fewer
+    // pair tiles than TPCs (1024^2: 32) still fill the machine
+    const int total_tiles = m_pairs * n_tiles * ksplit;
+    const int kb_per = num_kb / ksplit;
 
     if (threadIdx.x == 0) {
         for (int s = 0; s < kStages2; ++s) {
@@ -570,7 +589,8 @@ gemm2p_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
     pdl_launch_dependents();
 
     // tile t of this pair -> (m pair, n tile), N fastest (see the rasterisation note above)
-    auto tile_coords = [&](int t, int &m0, int &n0, int &item, int &a_col0) {
+    auto tile_coords = [&](int w, int &m0, int &n0, int &item, int &a_col0) {
+        const int t = w / ksplit;
         n0 = (t % n_tiles) * BN2;
         const int m_tile = 2 * (t / n_tiles) + (int)rank;
         item = pb.mtiles ? m_tile / pb.mtiles : 0;
@@ -584,7 +604,8 @@ gemm2p_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
         for (int t = pair; t < total_tiles; t += n_pairs_resident) {
             int m0, n0, item, a_col0;
             tile_coords(t, m0, n0, item, a_col0);
-            for (int kb = 0; kb < num_kb; ++kb, ++g) {
+            const int kb0 = (t % ksplit) * kb_per;
+            for (int kb = kb0; kb < kb0 + kb_per; ++kb, ++g) {
                 const uint32_t s = g % kStages2, ph = (g / kStages2) & 1u;
                 mbar_wait(empty0 + 8 * s, ph ^ 1u);
                 const uint32_t lead_full = map_to_cta(full0 + 8 * s, 0);
@@ -609,7 +630,7 @@ gemm2p_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
             mbar_wait(tempty0 + 8 * a, aph ^ 1u);  // both CTAs' epilogues drained this stage
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             const uint32_t tmem_d = tmem_base + a * BN2;
-            for (int kb = 0; kb < num_kb; ++kb, ++g) {
+            for (int kb = 0; kb < kb_per; ++kb, ++g) {
                 const uint32_t s = g % kStages2, ph = (g / kStages2) & 1u;
                 mbar_wait(full0 + 8 * s, ph);
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
@@ -788,6 +809,42 @@ prep_b_a2b_kernel(const double *__restrict__ amp, const double *__restrict__ phi
             return make_float2((float)(a * cs), (float)(a * sn));
         },
         n, np, b_hi, b_lo);
+}
+
+// Split-K pass 1 leaves fp32 sums in src [n]: split them into the bf16 hi/lo operand of pass 2,
+// zero src in place for the next transform and zero the output the second pass reduces into.
+__global__ void split_f32_kernel(float *__restrict__ src, long long n, __nv_bfloat16 *__restrict__ hi,
+                                 __nv_bfloat16 *__restrict__ lo, float *__restrict__ zero_dst,
+                                 long long n_zero) {
+    pdl_wait();
+    pdl_launch_dependents();
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n / 4; i += stride) {
+        const float4 v = ((const float4 *)src)[i];
+        __nv_bfloat16 h[4], l[4];
+        split_bf16(v.x, h[0], l[0]);
+        split_bf16(v.y, h[1], l[1]);
+        split_bf16(v.z, h[2], l[2]);
+        split_bf16(v.w, h[3], l[3]);
+        ((uint2 *)hi)[i] = make_uint2(
+            (uint32_t)__bfloat16_as_ushort(h[0]) | ((uint32_t)__bfloat16_as_ushort(h[1]) << 16),
+            (uint32_t)__bfloat16_as_ushort(h[2]) | ((uint32_t)__bfloat16_as_ushort(h[3]) << 16));
+        ((uint2 *)lo)[i] = make_uint2(
+            (uint32_t)__bfloat16_as_ushort(l[0]) | ((uint32_t)__bfloat16_as_ushort(l[1]) << 16),
+            (uint32_t)__bfloat16_as_ushort(l[2]) | ((uint32_t)__bfloat16_as_ushort(l[3]) << 16));
+        ((float4 *)src)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
+    }
+    if (zero_dst != src)
+        for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n_zero; i += stride)
+            zero_dst[i] = 0.f;
+}
+
+__global__ void zero_f32_kernel(float *__restrict__ dst, long long n) {
+    pdl_wait();
+    pdl_launch_dependents();
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n / 4;
+         i += (long long)gridDim.x * blockDim.x)
+        ((float4 *)dst)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
 // a2b / b2a outputs from the complex64 transform: complex128 field and phase =
@@ -1033,7 +1090,8 @@ template <int EPI>
 static int launch_gemm_pair_persistent(int m_tiles, int n_tiles256, cudaStream_t st,
                                        const CUtensorMap *m, int num_kb, float *c64,
                                        __nv_bfloat16 *d_hi, __nv_bfloat16 *d_lo, int ldd, int n_valid,
-                                       float scale, PairBatch pb = PairBatch{0, 0, 0, 0}) {
+                                       float scale, PairBatch pb = PairBatch{0, 0, 0, 0},
+                                       int ksplit = 1) {
     static bool attr_set[64] = {false};
     int dev = 0;
     SOSAT_CUDA_OK(cudaGetDevice(&dev));
@@ -1043,12 +1101,12 @@ static int launch_gemm_pair_persistent(int m_tiles, int n_tiles256, cudaStream_t
                                            cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
         attr_set[dev] = true;
     }
-    const int m_pairs = m_tiles / 2, tiles = m_pairs * n_tiles256;
+    const int m_pairs = m_tiles / 2, tiles = m_pairs * n_tiles256 * ksplit;
     int pairs = num_sms() / 2;
     if (pairs > tiles) pairs = tiles;
     return launch_pdl(gemm2p_bf16x3_kernel<EPI>, dim3(2 * pairs), dim3(kPersistThreads), smem, st, 2, 1,
-                      m[0], m[1], m[2], m[3], num_kb, m_pairs, n_tiles256, c64, d_hi, d_lo, ldd,
-                      n_valid, scale, pb);
+                      m[0], m[1], m[2], m[3], num_kb, m_pairs, n_tiles256, ksplit, c64, d_hi, d_lo,
+                      ldd, n_valid, scale, pb);
 }
 
 // SOSAT_GEMM_PERSIST=0 selects the one-tile-per-CTA pair kernel for A/B runs
@@ -1057,6 +1115,17 @@ static bool use_persistent_pair() {
     if (v < 0) {
         const char *e = getenv("SOSAT_GEMM_PERSIST");
         v = e ? (atoi(e) != 0) : 1;
+    }
+    return v != 0;
+}
+
+// SOSAT_GEMM_SPLITK=1 enables the split-K path of the small sizes (off by default: measured
+// slower, see run_passes)
+static bool use_split_k() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SOSAT_GEMM_SPLITK");
+        v = e ? (atoi(e) != 0) : 0;
     }
     return v != 0;
 }
@@ -1089,6 +1158,39 @@ static int run_passes(const DftWorkspace &w, const PlanEntry &pl, float scale, f
     int rc;
     const int pw = BK == 64 ? pair_kernel_width(w.np) : 0;
     const unsigned mt1 = 2 * w.np / BM, mt2 = w.np / BM;  // M tiles of pass 1 / pass 2
+    // Split-K on the pair kernel for sizes whose pair tiles alone cannot fill the machine
+    // (1024^2: 32 pair tiles on 74 TPCs): each tile's K range is cut into ksplit slices that run
+    // on different pairs and meet through vector red.global.add in a zeroed fp32 output.
+    //   prep -> zero D1f -> pass 1 (red into D1f [2np][np] fp32, the c64 staging area)
+    //   -> split (D1f -> bf16 hi/lo, zeroes D1f and the output) -> pass 2 (red into the output)
+    // Parity-green but OFF by default: at 1024^2 each split-K pass takes 28.4 us (the mainloop
+    // halves to ~13 us, but 1M float4 reductions per pass through L2 cost what it saves) against
+    // 27 us for the single-CTA kernel, plus 11 us of zero/split kernels: 0.084 vs 0.072 ms.
+    if (BK == 64 && pl.wide && use_persistent_pair() && pw == 0 && use_split_k()) {
+        const int tiles = (int)(mt1 / 2) * (w.np / 256);
+        int ksplit = 1;
+        while (ksplit < 8 && tiles * ksplit * 2 <= num_sms() / 2 && num_kb / (ksplit * 2) >= 8 &&
+               num_kb % (ksplit * 2) == 0)
+            ksplit *= 2;
+        if (ksplit > 1) {
+            float *d1f = w.c64;  // 2 np x np floats
+            const long long n1 = 2LL * w.np * w.np, n_out2 = 2LL * n_out * n_out;
+            long long blocks = (n1 / 4 + 255) / 256;
+            if (blocks > (long long)num_sms() * 8) blocks = (long long)num_sms() * 8;
+            if ((rc = launch_pdl(zero_f32_kernel, dim3((unsigned)blocks), dim3(256), 0, st, 1, 1, d1f,
+                                 n1))) return rc;
+            if ((rc = launch_gemm_pair_persistent<EPI_RED_F32>((int)mt1, w.np / 256, st, pl.pair256,
+                                                               num_kb, d1f, nullptr, nullptr, w.np, 0,
+                                                               1.f, PairBatch{0, 0, 0, 0}, ksplit)))
+                return rc;
+            if ((rc = launch_pdl(split_f32_kernel, dim3((unsigned)blocks), dim3(256), 0, st, 1, 1, d1f,
+                                 n1, w.d1_hi, w.d1_lo, d_c64, n_out2))) return rc;
+            return launch_gemm_pair_persistent<EPI_RED_C64>((int)mt2, 2 * w.np / 256, st,
+                                                            pl.pair256 + 4, num_kb, d_c64, nullptr,
+                                                            nullptr, 0, n_out, scale,
+                                                            PairBatch{0, 0, 0, 0}, ksplit);
+        }
+    }
     if (pw == 256 && pl.wide && use_persistent_pair()) {
         if ((rc = launch_gemm_pair_persistent<EPI_SPLIT_BF16>((int)mt1, w.np / 256, st, pl.pair256,
                                                               num_kb, nullptr, w.d1_hi, w.d1_lo,

@@ -290,7 +290,7 @@ def test_ff_fwhm_device_matches_host_estimator(mods):
     assert abs(rt.ff_fwhm_device(B, xa, ya) - rt.ff_fwhm_est(Bh, xa, ya)) < 1e-9
 
 
-@pytest.mark.parametrize("pair", ["0", "128", "256"])
+@pytest.mark.parametrize("pair", ["0", "128", "256", "splitk"])
 def test_all_umma_kernels_agree(mods, monkeypatch, pair):
     """The three UMMA kernels behind the passes (single-CTA with 2 x 2 multicast clusters,
     cta_group::2 pair tiles 256 x 128 and 256 x 256) on a size where all of them are legal and on
@@ -306,7 +306,12 @@ def test_all_umma_kernels_agree(mods, monkeypatch, pair):
         "    err = np.abs(oa.far_field(b) - ref).max() / np.abs(ref).max()\n"
         "    assert err < 1e-4, (n, err)\n"
         "print('ok')\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    env = dict(os.environ, SOSAT_GEMM_PAIR=pair)  # read once per process: run in a fresh one
+    env = dict(os.environ)  # the switches are read once per process: run in a fresh one
+    if pair == "splitk":   # split-K slices of the pair kernel meeting through red.global.add
+        env.update(SOSAT_GEMM_SPLITK="1")
+        env.pop("SOSAT_GEMM_PAIR", None)
+    else:
+        env.update(SOSAT_GEMM_PAIR=pair)
     r = subprocess.run([sys.executable, "-c", code], env=env, capture_output=True, text=True, timeout=300)
     assert r.returncode == 0 and "ok" in r.stdout, r.stderr[-2000:]
 
