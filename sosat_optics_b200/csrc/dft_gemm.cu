@@ -160,17 +160,29 @@ enum { EPI_C64 = 0, EPI_SPLIT_BF16 = 1, EPI_RED_C64 = 2, EPI_RED_F32 = 3 };
 //   EPI_C64:        times scale -> d_c64 [n_valid][2 n_valid] floats = complex64 [n][n]
 //   EPI_RED_C64:    the same with red.global.add (split-K partial sums into a zeroed output)
 //   EPI_RED_F32:    red.global.add.v4.f32 into the zeroed dense fp32 matrix d_c64 [M][ldd]
+// `partial` (optional): the other K slice's fp32 sums of this CTA's tile, stored by
+// store_partial_tile as float4 [NCOLS/4][128 rows] (row fastest: coalesced both ways); added in.
 template <int EPI, int NCOLS = BN>
 __device__ __forceinline__ void gemm_epilogue(uint32_t tmem_base, int m0, int n0, int warp, int lane,
                                               float *__restrict__ d_c64,
                                               __nv_bfloat16 *__restrict__ d_hi,
                                               __nv_bfloat16 *__restrict__ d_lo, int ldd, int n_valid,
-                                              float scale) {
+                                              float scale, const float4 *partial = nullptr) {
     const int row = m0 + warp * 32 + lane;  // TMEM lane == accumulator row
 #pragma unroll 1
     for (int c = 0; c < NCOLS / 32; ++c) {
         uint32_t v[32];
         tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
+        if (partial) {
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+                const float4 o = partial[(size_t)(c * 8 + q) * BM + warp * 32 + lane];
+                v[4 * q] = __float_as_uint(__uint_as_float(v[4 * q]) + o.x);
+                v[4 * q + 1] = __float_as_uint(__uint_as_float(v[4 * q + 1]) + o.y);
+                v[4 * q + 2] = __float_as_uint(__uint_as_float(v[4 * q + 2]) + o.z);
+                v[4 * q + 3] = __float_as_uint(__uint_as_float(v[4 * q + 3]) + o.w);
+            }
+        }
         if (EPI == EPI_RED_F32) {
             float4 *dst = (float4 *)(d_c64 + (size_t)row * ldd + n0 + c * 32);
 #pragma unroll
@@ -223,6 +235,21 @@ __device__ __forceinline__ void gemm_epilogue(uint32_t tmem_base, int m0, int n0
                 dl[q] = make_uint4(lo[4 * q], lo[4 * q + 1], lo[4 * q + 2], lo[4 * q + 3]);
             }
         }
+    }
+}
+
+template <int NCOLS>
+__device__ __forceinline__ void store_partial_tile(uint32_t tmem_base, int warp, int lane,
+                                                   float4 *__restrict__ partial) {
+#pragma unroll 1
+    for (int c = 0; c < NCOLS / 32; ++c) {
+        uint32_t v[32];
+        tmem_ld32(tmem_base + ((uint32_t)(warp * 32) << 16) + (uint32_t)(c * 32), v);
+#pragma unroll
+        for (int q = 0; q < 8; ++q)
+            partial[(size_t)(c * 8 + q) * BM + warp * 32 + lane] =
+                make_float4(__uint_as_float(v[4 * q]), __uint_as_float(v[4 * q + 1]),
+                            __uint_as_float(v[4 * q + 2]), __uint_as_float(v[4 * q + 3]));
     }
 }
 
@@ -676,6 +703,141 @@ gemm2p_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                      "r"(512) : "memory");
 }
 
+// ---- two CTA pairs per tile: split-K inside a cluster of four ---------------------------------
+// For sizes whose 256 x 256 pair tiles cannot fill the machine (1024^2: 32 tiles, 74 TPCs) a
+// cluster of FOUR CTAs takes one tile: ranks (0,1) and (2,3) are two cta_group::2 pairs, each
+// accumulating one half of K in its own TMEM.  Pair 1 then writes its fp32 sums to a scratch
+// tile (plain coalesced 16-byte stores, L2-resident) and releases them to pair 0 through a
+// cluster-scope mbarrier; pair 0 adds them in its epilogue.  No atomics, no extra kernels, and
+// the K loop per CTA halves.
+__device__ __forceinline__ void mbar_wait_cluster(uint32_t bar, uint32_t parity) {
+    uint32_t done = 0;
+    while (!done) {
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.acquire.cluster.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t}"
+            : "=r"(done)
+            : "r"(bar), "r"(parity)
+            : "memory");
+    }
+}
+
+template <int EPI>
+__global__ void __launch_bounds__(128, 1)
+gemm2k_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
+                     const __grid_constant__ CUtensorMap map_a_lo,
+                     const __grid_constant__ CUtensorMap map_b_hi,
+                     const __grid_constant__ CUtensorMap map_b_lo, int num_kb, int n_tiles,
+                     float4 *__restrict__ scratch, float *__restrict__ d_c64,
+                     __nv_bfloat16 *__restrict__ d_hi, __nv_bfloat16 *__restrict__ d_lo, int ldd,
+                     int n_valid, float scale) {
+    constexpr int BN2 = 256;
+    using Cfg = PairCfg<BN2>;
+    constexpr int kStages2 = Cfg::kStages, kStageBytes2 = Cfg::kStageBytes,
+                  kHalfTileBytes = Cfg::kHalfBytes;
+    extern __shared__ uint8_t smem_raw[];
+    uint8_t *smem = (uint8_t *)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+    uint64_t *bars = (uint64_t *)(smem + kStages2 * kStageBytes2);
+    uint32_t *tmem_slot = (uint32_t *)(bars + 2 * kStages2 + 2);
+    const uint32_t full0 = smem_u32(bars), empty0 = smem_u32(bars + kStages2),
+                   accum_bar = smem_u32(bars + 2 * kStages2),
+                   partial_bar = smem_u32(bars + 2 * kStages2 + 1);
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t rank = cluster_ctarank();   // 0,1: pair of K slice 0; 2,3: pair of K slice 1
+    const uint32_t prank = rank & 1u, lead = rank & ~1u, kslice = rank >> 1;
+    const bool leader = prank == 0;
+    const uint16_t pair_mask = (uint16_t)(0x3u << lead);
+    const int tile = blockIdx.x >> 2;
+    const int n0 = (tile % n_tiles) * BN2;
+    const int m0 = (2 * (tile / n_tiles) + (int)prank) * BM;
+    const int kb_per = num_kb / 2, kb0 = (int)kslice * kb_per;
+    float4 *my_scratch = scratch + (size_t)(tile * 2 + (int)prank) * (BN2 / 4) * BM;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < kStages2; ++s) {
+            mbar_init(full0 + 8 * s, 2);
+            mbar_init(empty0 + 8 * s, 1);
+        }
+        mbar_init(accum_bar, 1);
+        mbar_init(partial_bar, 4);  // the four epilogue warps of the partner CTA of slice 1
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+    }
+    if (warp == 0) {
+        __syncwarp();
+        asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;"
+                     ::"r"(smem_u32(tmem_slot)), "r"(BN2) : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    __syncthreads();
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    const uint32_t tmem_base = *tmem_slot;
+    cluster_sync_all();
+    pdl_wait();
+    pdl_launch_dependents();
+
+    if (warp == 0 && lane == 0) {
+        for (int i = 0; i < kb_per; ++i) {
+            const int kb = kb0 + i;
+            const uint32_t s = i % kStages2, ph = (i / kStages2) & 1u;
+            mbar_wait(empty0 + 8 * s, ph ^ 1u);
+            const uint32_t lead_full = map_to_cta(full0 + 8 * s, lead);
+            const uint32_t base = smem_u32(smem + s * kStageBytes2);
+            if (leader) mbar_expect_tx(full0 + 8 * s, 2 * kStageBytes2);
+            else mbar_arrive_cluster(lead_full);
+            tma_load_2d_pair(base, &map_a_hi, lead_full, kb * BK, m0);
+            tma_load_2d_pair(base + kTileBytes, &map_a_lo, lead_full, kb * BK, m0);
+            tma_load_2d_pair(base + 2 * kTileBytes, &map_b_hi, lead_full, kb * BK,
+                             n0 + (int)prank * (BN2 / 2));
+            tma_load_2d_pair(base + 2 * kTileBytes + kHalfTileBytes, &map_b_lo, lead_full, kb * BK,
+                             n0 + (int)prank * (BN2 / 2));
+        }
+    } else if (warp == 1 && lane == 0 && leader) {
+        constexpr uint32_t idesc = umma_idesc_bf16(2 * BM, BN2);
+        for (int i = 0; i < kb_per; ++i) {
+            const uint32_t s = i % kStages2, ph = (i / kStages2) & 1u;
+            mbar_wait(full0 + 8 * s, ph);
+            asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+            const uint32_t base = smem_u32(smem + s * kStageBytes2);
+            const uint64_t a_hi = umma_desc_sw128(base);
+            const uint64_t a_lo = umma_desc_sw128(base + kTileBytes);
+            const uint64_t b_hi = umma_desc_sw128(base + 2 * kTileBytes);
+            const uint64_t b_lo = umma_desc_sw128(base + 2 * kTileBytes + kHalfTileBytes);
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+                const uint64_t adv = (uint64_t)((k * UMMA_K * 2) >> 4);
+                umma2_bf16(tmem_base, a_hi + adv, b_hi + adv, idesc, (i | k) != 0);
+                umma2_bf16(tmem_base, a_hi + adv, b_lo + adv, idesc, 1u);
+                umma2_bf16(tmem_base, a_lo + adv, b_hi + adv, idesc, 1u);
+            }
+            umma2_commit_mc(empty0 + 8 * s, pair_mask);
+        }
+        umma2_commit_mc(accum_bar, pair_mask);
+    }
+    __syncwarp();
+
+    mbar_wait(accum_bar, 0);
+    asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+    if (kslice == 1) {
+        // K slice 1: hand the fp32 sums to the CTA of slice 0 that owns the same rows (rank - 2)
+        store_partial_tile<BN2>(tmem_base, warp, lane, my_scratch);
+        __threadfence();
+        __syncwarp();
+        if (lane == 0) mbar_arrive_cluster(map_to_cta(partial_bar, rank - 2));
+    } else {
+        mbar_wait_cluster(partial_bar, 0);
+        gemm_epilogue<EPI, BN2>(tmem_base, m0, n0, warp, lane, d_c64, d_hi, d_lo, ldd, n_valid, scale,
+                                my_scratch);
+    }
+    asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+    cluster_sync_all();
+    if (warp == 0)
+        asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base),
+                     "r"(BN2) : "memory");
+}
+
 // ---- operand preparation (HBM-bound elementwise kernels) -----------------------------------
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
     hi = __float2bfloat16_rn(x);
@@ -1119,6 +1281,36 @@ static bool use_persistent_pair() {
     return v != 0;
 }
 
+template <int EPI>
+static int launch_gemm_quad(int m_tiles, int n_tiles256, cudaStream_t st, const CUtensorMap *m,
+                            int num_kb, float4 *scratch, float *c64, __nv_bfloat16 *d_hi,
+                            __nv_bfloat16 *d_lo, int ldd, int n_valid, float scale) {
+    static bool attr_set[64] = {false};
+    int dev = 0;
+    SOSAT_CUDA_OK(cudaGetDevice(&dev));
+    constexpr int smem = PairCfg<256>::kSmem + 64;
+    if (dev >= 0 && dev < 64 && !attr_set[dev]) {
+        SOSAT_CUDA_OK(cudaFuncSetAttribute(gemm2k_bf16x3_kernel<EPI>,
+                                           cudaFuncAttributeMaxDynamicSharedMemorySize, smem));
+        attr_set[dev] = true;
+    }
+    const int tiles = (m_tiles / 2) * n_tiles256;
+    return launch_pdl(gemm2k_bf16x3_kernel<EPI>, dim3(4 * tiles), dim3(128), smem, st, 4, 1, m[0],
+                      m[1], m[2], m[3], num_kb, n_tiles256, scratch, c64, d_hi, d_lo, ldd, n_valid,
+                      scale);
+}
+
+// SOSAT_GEMM_QUAD=1 enables the cluster-of-four split-K kernel of the mid sizes (off by default:
+// measured slower, see run_passes)
+static bool use_quad_kernel() {
+    static int v = -1;
+    if (v < 0) {
+        const char *e = getenv("SOSAT_GEMM_QUAD");
+        v = e ? (atoi(e) != 0) : 0;
+    }
+    return v != 0;
+}
+
 // SOSAT_GEMM_SPLITK=1 enables the split-K path of the small sizes (off by default: measured
 // slower, see run_passes)
 static bool use_split_k() {
@@ -1158,6 +1350,21 @@ static int run_passes(const DftWorkspace &w, const PlanEntry &pl, float scale, f
     int rc;
     const int pw = BK == 64 ? pair_kernel_width(w.np) : 0;
     const unsigned mt1 = 2 * w.np / BM, mt2 = w.np / BM;  // M tiles of pass 1 / pass 2
+    // Cluster-of-four split-K (two CTA pairs per pair tile, partial sums through an L2-resident
+    // scratch tile) for sizes with at most one tile per four SMs: 512^2 ... 1024^2.  Scratch:
+    // pass 1 uses the complex64 staging area, pass 2 the (by then consumed) X operand.
+    // Parity-green but OFF by default: a pair-tile CTA with half the K loop (16 k-blocks) still
+    // takes 27-28 us at 1024^2 -- ~9 us of prologue (TMEM allocation, four-CTA cluster sync, first
+    // fills) and epilogue around a mainloop at ~78 % of the UMMA rate -- i.e. as long as the
+    // single-CTA kernel with the full K loop: 0.083 vs 0.072 ms.
+    if (BK == 64 && pl.wide && pw == 0 && use_quad_kernel() && !use_split_k() &&
+        (int)(mt1 / 2) * (w.np / 256) * 4 <= num_sms() && num_kb % 2 == 0 && num_kb / 2 >= 4) {
+        if ((rc = launch_gemm_quad<EPI_SPLIT_BF16>((int)mt1, w.np / 256, st, pl.pair256, num_kb,
+                                                   (float4 *)w.c64, nullptr, w.d1_hi, w.d1_lo, w.np,
+                                                   0, 1.f))) return rc;
+        return launch_gemm_quad<EPI_C64>((int)mt2, 2 * w.np / 256, st, pl.pair256 + 4, num_kb,
+                                         (float4 *)w.b1_hi, d_c64, nullptr, nullptr, 0, n_out, scale);
+    }
     // Split-K on the pair kernel for sizes whose pair tiles alone cannot fill the machine
     // (1024^2: 32 pair tiles on 74 TPCs): each tile's K range is cut into ksplit slices that run
     // on different pairs and meet through vector red.global.add in a zeroed fp32 output.

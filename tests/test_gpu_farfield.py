@@ -290,7 +290,7 @@ def test_ff_fwhm_device_matches_host_estimator(mods):
     assert abs(rt.ff_fwhm_device(B, xa, ya) - rt.ff_fwhm_est(Bh, xa, ya)) < 1e-9
 
 
-@pytest.mark.parametrize("pair", ["0", "128", "256", "splitk"])
+@pytest.mark.parametrize("pair", ["0", "128", "256", "splitk", "quad"])
 def test_all_umma_kernels_agree(mods, monkeypatch, pair):
     """The three UMMA kernels behind the passes (single-CTA with 2 x 2 multicast clusters,
     cta_group::2 pair tiles 256 x 128 and 256 x 256) on a size where all of them are legal and on
@@ -309,6 +309,9 @@ def test_all_umma_kernels_agree(mods, monkeypatch, pair):
     env = dict(os.environ)  # the switches are read once per process: run in a fresh one
     if pair == "splitk":   # split-K slices of the pair kernel meeting through red.global.add
         env.update(SOSAT_GEMM_SPLITK="1")
+        env.pop("SOSAT_GEMM_PAIR", None)
+    elif pair == "quad":   # two CTA pairs per tile in a cluster of four, partials through L2
+        env.update(SOSAT_GEMM_QUAD="1")
         env.pop("SOSAT_GEMM_PAIR", None)
     else:
         env.update(SOSAT_GEMM_PAIR=pair)
