@@ -825,6 +825,9 @@ static void launch_bin_minb(int geo, int minb, const BinParams &p, const double 
     if (geo == 1) return launch_bin<N32, N64, 4, 1>(p, rx, re, im, cnt, stats, st);
     switch (minb) {
         case 3: launch_bin<N32, N64, 3, 0>(p, rx, re, im, cnt, stats, st); break;
+#ifdef SOSAT_BIN_MINB5
+        case 5: launch_bin<N32, N64, 5, 0>(p, rx, re, im, cnt, stats, st); break;
+#endif
         default: launch_bin<N32, N64, 4, 0>(p, rx, re, im, cnt, stats, st); break;
     }
 }
