@@ -136,6 +136,35 @@ __device__ __forceinline__ double rsqrt_full(double x) {
 #ifndef SOSAT_RSQRT_SNELL
 #define SOSAT_RSQRT_SNELL rsqrt_full
 #endif
+// double <-> float for the SEEDS of the fp32 Newton steps.  F2F.F32.F64 costs ~9 cycles of the XU
+// pipe per warp instruction on B200 (scripts/xu_mix.cu) -- the pipe the MUFUs of the fp32
+// pre-iterations need -- so an integer bit-manipulation form (truncating, tiny values flushed
+// towards 0; NaN / Inf give garbage, harmless because the fp64 state they came from stays
+// NaN / Inf) is compiled with -DSOSAT_FAST_CVT=1.  It is parity-green but its 5-6 ALU
+// instructions per conversion cost more issue slots than the XU time they free: 1.67 -> 1.55e10
+// rays/s.  Off by default.
+#ifndef SOSAT_FAST_CVT
+#define SOSAT_FAST_CVT 0
+#endif
+__device__ __forceinline__ float d2f_seed(double x) {
+#if SOSAT_FAST_CVT
+    const int hi = __double2hiint(x), lo = __double2loint(x);
+    const int e = max((hi & 0x7fffffff) - 0x38000000, 0);  // rebias the exponent (1023 -> 127)
+    const unsigned f = __funnelshift_l((unsigned)lo, (unsigned)e, 3) | ((unsigned)hi & 0x80000000u);
+    return __uint_as_float(f);
+#else
+    return (float)x;
+#endif
+}
+__device__ __forceinline__ double f2d_seed(float x) {
+#if SOSAT_FAST_CVT
+    const unsigned f = __float_as_uint(x), m = f & 0x7fffffffu;
+    const unsigned hi = (f & 0x80000000u) | ((m >> 3) + (m ? 0x38000000u : 0u));
+    return __hiloint2double((int)hi, (int)(m << 29));
+#else
+    return (double)x;
+#endif
+}
 __device__ __forceinline__ float rcp_f32(float x) {
     float r;
     asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
@@ -288,8 +317,8 @@ __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, doub
         double t;
         if (N32 > 0) {
             const SurfF &F = g.f[si];
-            const float fPx = (float)Px, fPz = (float)Pz, fdx = (float)dx, fdy = (float)dy,
-                        fdz = (float)dz, fy0 = (float)y0Py;
+            const float fPx = d2f_seed(Px), fPz = d2f_seed(Pz), fdx = d2f_seed(dx), fdy = d2f_seed(dy),
+                        fdz = d2f_seed(dz), fy0 = d2f_seed(y0Py);
             float tf = fy0 * rcp_f32(fdy);  // vertex-plane guess
             if (!GENERIC && !((REFINE_MASK >> si) & 1)) {
                 const float fy0K = fy0 - F.cK;
@@ -307,7 +336,7 @@ __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, doub
                     tf = fmaf(-f, rcp_f32(fp), tf);
                 }
             }
-            t = (double)tf;
+            t = f2d_seed(tf);
         } else {
             t = y0Py * rcp_half(dy);  // vertex-plane guess
         }
