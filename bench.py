@@ -499,7 +499,7 @@ def run_ours(args):
                    "extent_cm": EXTENT_CM, "ghz": GHZ, "sharding": f"launch-row blocks x{world}, "
                    "one NCCL all-reduce of [re,im,count] planes (50 MB) + 8 fp64 sums",
                    "l2": "256 MiB flush write between timed steps; the kernel reads no input arrays",
-                   "newton_schedule": os.environ.get("SOSAT_TRACE_VARIANT", "default (2 fp32 + 2 fp64 steps; unconverged lanes re-traced adaptively)")},
+                   "newton_schedule": os.environ.get("SOSAT_TRACE_VARIANT", "default (fp32 Newton + Halley step, 1 fp64 Newton step, first-order slope update; long steps re-traced adaptively)")},
         "clocks": clocks,
         "e2e": {"value": e2e_value, "unit": "rays/s", "h2d_bytes_per_step": h2d,
                 "d2h_bytes_per_step": d2h},

@@ -19,11 +19,12 @@ t.k = 2 * np.pi / t.lambda_
 spec = [(t.k, t.th_fwhp_x, t.th_fwhp_y)]
 planes = None
 reps = int(os.environ.get("PROF_REPS", "3"))
+rx = [[float(v) for v in os.environ.get("PROF_RX", "0,0,0").split(",")]]
 ts = []
 for rep in range(reps):
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
-    re, im, cnt, st = ray_trace.trace_bin_device(t, [[0, 0, 0]], spec, 2048, 420.0, planes=planes)
+    re, im, cnt, st = ray_trace.trace_bin_device(t, rx, spec, 2048, 420.0, planes=planes)
     e1.record()
     torch.cuda.synchronize()
     planes = (re, im, cnt)

@@ -623,12 +623,14 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
 }
 
 // ---- host side ---------------------------------------------------------------------------------
-// Newton schedule (fp32 steps, fp64 steps) of the fast path: default 2 + 2 plus the adaptive
-// refinement; SOSAT_TRACE_VARIANT = 0: 0+5, 2: 3+2, 5: 0+4 select the other compiled
-// schedules for experiments.
+// Newton schedule (fp32 steps, fp64 steps) of the fast path.  Default "2 + 1": one Newton and
+// one Halley step in fp32, ONE fp64 Newton step, slope factor carried to the new root to first
+// order (trace_device.cuh), plus the adaptive refinement for lanes whose fp64 step is too long.
+// SOSAT_TRACE_VARIANT = 0: 0+5, 2: 3+2, 6: 2+2 (the default until v3) select the other
+// compiled schedules for experiments and for the parity test of the schedules.
 static int trace_variant() {
     const char *e = getenv("SOSAT_TRACE_VARIANT");
-    return e ? atoi(e) : 6;
+    return e ? atoi(e) : 7;
 }
 
 static void fill_linspace(double cone, int n_scan, double &start, double &stop, double &step) {
@@ -676,6 +678,8 @@ extern "C" int sosat_set_geometry(const sosat_geom_t *h, void *stream) {
         c.t_lo = s.t_lo;
         c.t_hi = s.t_hi;
         c.omm2 = 1.0 - c.mu2;
+        c.cKh = 0.5 * c.cp * c.Kp;
+        c.a3p12 = 12.0 * c.a3p;
         c.cK = c.Kp != 0.0 ? c.cp / c.Kp : 0.0;
         c.refine = fabs(c.cK) > 300.0;
         refine_mask |= c.refine << i;
@@ -686,6 +690,7 @@ extern "C" int sosat_set_geometry(const sosat_geom_t *h, void *stream) {
         f.a3p = (float)c.a3p; f.a1p2 = (float)c.a1p2; f.a2p4 = (float)c.a2p4;
         f.a3p6 = (float)c.a3p6;
         f.cK = (float)c.cK;
+        f.cKh = (float)c.cKh; f.a3p12 = (float)c.a3p12;
     }
     g.y_lyot = h->y_lyot;
     g.y_source = h->y_source;
@@ -745,12 +750,13 @@ static int trace_rows_common(const double *h_rx, const sosat_freq_t *h_freq, int
     cudaStream_t st = (cudaStream_t)stream;
     const int geo = g_geom_build[dev];
     if (d_samples) {
-        launch_rows<2, 2, true>(geo, p, nullptr, d_samples, d_stats, st);
+        launch_rows<2, 1, true>(geo, p, nullptr, d_samples, d_stats, st);
     } else {
         switch (trace_variant()) {
             case 0: launch_rows<0, 5, false>(geo, p, d_out, nullptr, d_stats, st); break;
             case 2: launch_rows<3, 2, false>(geo, p, d_out, nullptr, d_stats, st); break;
-            default: launch_rows<2, 2, false>(geo, p, d_out, nullptr, d_stats, st); break;
+            case 6: launch_rows<2, 2, false>(geo, p, d_out, nullptr, d_stats, st); break;
+            default: launch_rows<2, 1, false>(geo, p, d_out, nullptr, d_stats, st); break;
         }
     }
     SOSAT_CUDA_OK(cudaGetLastError());
@@ -891,7 +897,8 @@ extern "C" int sosat_trace_bin(const double *d_rx, int n_rx, const sosat_freq_t 
     switch (trace_variant()) {
         case 0: launch_bin_minb<0, 5>(geo, minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
         case 2: launch_bin_minb<3, 2>(geo, minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
-        default: launch_bin_minb<2, 2>(geo, minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
+        case 6: launch_bin_minb<2, 2>(geo, minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
+        default: launch_bin_minb<2, 1>(geo, minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
     }
     SOSAT_CUDA_OK(cudaGetLastError());
     // bf lives on this stack frame: the async symbol copy from pageable memory is staged

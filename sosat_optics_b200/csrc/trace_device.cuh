@@ -45,10 +45,12 @@ struct SurfC {
     double omm2;  // 1 - mu^2
     int refine;   // |cK| > 300 mm: s needs the fully refined rsqrt in the division-free form
     int pad_;
+    double cKh;    // c' K' / 2: d(c'/s)/du = cKh / s^3
+    double a3p12;  // 12 a3'
 };
 
 struct SurfF {
-    float Kp, cp, a1p, a2p, a3p, a1p2, a2p4, a3p6, cK;
+    float Kp, cp, a1p, a2p, a3p, a1p2, a2p4, a3p6, cK, cKh, a3p12;
 };
 
 struct GeomC {
@@ -69,6 +71,13 @@ struct GeomC {
 // with w = 1 - K'u below this are within ~8 mm of the domain edge r = 300.4 mm, where the
 // reference's brentq converges onto the sag discontinuity instead of a root.
 #define SOSAT_EDGE_W 0.05
+// Schedule "N32 + 1": ONE fp64 Newton step from the fp32 root.  Its error is kappa step^2 with
+// kappa = |f''/2f'| ~ 1e-3/mm on these surfaces, so a step below this bound leaves <= 1e-9 mm;
+// longer steps send the lane to the adaptive path.  The fp32 root sits at the fp32 floor
+// (steps of 1e-5 .. 3e-4 mm measured), so the bound is not on the hot path of any ray.
+#ifndef SOSAT_LINEAR_MAX_STEP
+#define SOSAT_LINEAR_MAX_STEP 1.0e-3
+#endif
 
 enum : unsigned {
     RAY_CLIPPED_L3 = 1u,  // ray_trace.py:1138-1140: whole output column stays zero
@@ -133,6 +142,12 @@ __device__ __forceinline__ double rsqrt_full(double x) {
 #ifndef SOSAT_RSQRT_EVAL
 #define SOSAT_RSQRT_EVAL rsqrt_fast
 #endif
+#ifndef SOSAT_REFRACT_JOINT
+#define SOSAT_REFRACT_JOINT 1
+#endif
+#ifndef SOSAT_LINEAR_RCP
+#define SOSAT_LINEAR_RCP rcp_seed
+#endif
 #ifndef SOSAT_RSQRT_SNELL
 #define SOSAT_RSQRT_SNELL rsqrt_full
 #endif
@@ -186,12 +201,13 @@ template <bool GENERIC>
 __device__ __forceinline__ void surf_eval(const SurfC &S, const bool refine, double Px, double Pz, double dx,
                                           double dy, double dz, double y0PyK, double t,
                                           double &f, double &fp, double &X, double &Z,
-                                          double &G, double &w) {
+                                          double &G, double &w, double &u, double &rs,
+                                          double &xd) {
     X = fma(dx, t, Px);
     Z = fma(dz, t, Pz);
-    const double u = fma(X, X, Z * Z);
+    u = fma(X, X, Z * Z);
     w = fma(-S.Kp, u, 1.0);
-    double rs = SOSAT_RSQRT_EVAL(w);
+    rs = SOSAT_RSQRT_EVAL(w);
     const double poly = fma(fma(S.a3p, u, S.a2p), u, S.a1p);
     const double base = fma(-u, poly, fma(-dy, t, y0PyK));
     if (GENERIC) {
@@ -206,7 +222,16 @@ __device__ __forceinline__ void surf_eval(const SurfC &S, const bool refine, dou
         f = fma(B, rs, base);  // ... - cK (1 - s)
     }
     G = fma(S.cp, rs, fma(u, fma(S.a3p6, u, S.a2p4), S.a1p2));  // c'/s + d(poly u)/du * 2
-    fp = fma(-G, fma(X, dx, Z * dz), -dy);
+    xd = fma(X, dx, Z * dz);                                     // (du/dt) / 2
+    fp = fma(-G, xd, -dy);
+}
+template <bool GENERIC>
+__device__ __forceinline__ void surf_eval(const SurfC &S, const bool refine, double Px, double Pz,
+                                          double dx, double dy, double dz, double y0PyK, double t,
+                                          double &f, double &fp, double &X, double &Z, double &G,
+                                          double &w) {
+    double u, rs, xd;
+    surf_eval<GENERIC>(S, refine, Px, Pz, dx, dy, dz, y0PyK, t, f, fp, X, Z, G, w, u, rs, xd);
 }
 
 // fp32 pre-iterations: same two forms (REFINE surfaces keep the division, where the (1 - s)
@@ -229,6 +254,33 @@ __device__ __forceinline__ void surf_eval_f32(const SurfF &S, float Px, float Pz
     const float G = fmaf(S.cp, rs, fmaf(u, fmaf(S.a3p6, u, S.a2p4), S.a1p2));
     fp = fmaf(-G, fmaf(X, dx, Z * dz), -dy);
 }
+// The same with the second derivative along the ray, for Halley steps (cubic convergence, no
+// further MUFU): f'' = -(G (dx^2 + dz^2) + dG/du (du/dt)^2 / 2), dd = dx^2 + dz^2.
+template <bool DIVFREE>
+__device__ __forceinline__ float halley_step_f32(const SurfF &S, float Px, float Pz, float dx,
+                                                 float dy, float dz, float dd, float y0PyK,
+                                                 float t) {
+    const float X = fmaf(dx, t, Px);
+    const float Z = fmaf(dz, t, Pz);
+    const float u = fmaf(X, X, Z * Z);
+    const float w = fmaf(-S.Kp, u, 1.0f);
+    const float rs = rsqrt_f32(w);
+    const float poly = fmaf(fmaf(S.a3p, u, S.a2p), u, S.a1p);
+    const float base = fmaf(-u, poly, fmaf(-dy, t, y0PyK));
+    float f;
+    if (DIVFREE)
+        f = fmaf(S.cK * w, rs, base);
+    else
+        f = fmaf(-u, S.cp * rcp_f32(fmaf(w, rs, 1.0f)), base);
+    const float G = fmaf(S.cp, rs, fmaf(u, fmaf(S.a3p6, u, S.a2p4), S.a1p2));
+    const float xd = fmaf(X, dx, Z * dz);
+    const float fp = fmaf(-G, xd, -dy);
+    const float dGdu = fmaf(S.cKh * (rs * rs), rs, fmaf(S.a3p12, u, S.a2p4));
+    const float nfpp = fmaf(G, dd, 2.0f * dGdu * (xd * xd));        // -f''
+    // t - 2 f f' / (2 f'^2 - f f'')
+    const float den = fmaf(fp + fp, fp, f * nfpp);
+    return fmaf(-(f + f) * fp, rcp_f32(den), t);
+}
 
 // Vector Snell refraction, ray_trace.py:27-35 with N x (-N x s) = s - N (N.s) and
 // |N x s|^2 = 1 - (N.s)^2:  s2 = mu s + (mu cos_i - sqrt(1 - mu^2 (1 - cos_i^2))) N.
@@ -246,8 +298,16 @@ __device__ __forceinline__ void refract(const SurfC &S, double X, double Z, doub
     L2 = fma(gx, gx, fma(gz, gz, 1.0));
     const double m = fma(gx, dx, fma(gz, dz, dy));
     const double D = fma(S.mu2, m * m, S.omm2 * L2);
+#if SOSAT_REFRACT_JOINT
+    // one fully refined rsqrt serves both sqrt(D)/L2 and 1/L2: y = 1/(sqrt(D) L2),
+    // sqrt(D)/L2 = D y, 1/L2 = (D y)(L2 y)
+    const double y = SOSAT_RSQRT_SNELL(D * (L2 * L2));
+    const double Dy = D * y;
+    const double beta = fma(S.mu * m, Dy * (L2 * y), -Dy);
+#else
     const double sqrtD = D * SOSAT_RSQRT_SNELL(D);
     const double beta = fma(S.mu, m, -sqrtD) * rcp_full(L2);
+#endif
     dx = fma(S.mu, dx, -(gx * beta));
     dy = fma(S.mu, dy, -beta);
     dz = fma(S.mu, dz, -(gz * beta));
@@ -310,6 +370,8 @@ __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, doub
     double opl = 0.0, r2a_sq = 0.0;
     double gx = 0.0, gz = 0.0, L2 = 1.0;
     unsigned flags = 0;
+    // N64 == 1: Halley steps in fp32, one fp64 Newton step, slope factor carried to first order
+    constexpr bool kLinear = N32 > 0 && N64 == 1 && !ADAPTIVE;
     SOSAT_SURFACE_LOOP_PRAGMA
     for (int si = 0; si < SOSAT_NUM_SURFACES; ++si) {
         const SurfC &S = g.s[si];
@@ -320,7 +382,27 @@ __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, doub
             const float fPx = d2f_seed(Px), fPz = d2f_seed(Pz), fdx = d2f_seed(dx), fdy = d2f_seed(dy),
                         fdz = d2f_seed(dz), fy0 = d2f_seed(y0Py);
             float tf = fy0 * rcp_f32(fdy);  // vertex-plane guess
-            if (!GENERIC && !((REFINE_MASK >> si) & 1)) {
+            if (kLinear) {
+                const float fdd = fmaf(fdx, fdx, fdz * fdz);
+                if (!GENERIC && !((REFINE_MASK >> si) & 1)) {
+                    const float fy0K = fy0 - F.cK;
+#pragma unroll
+                    for (int it = 0; it < N32 - 1; ++it) {
+                        float f, fp;
+                        surf_eval_f32<true>(F, fPx, fPz, fdx, fdy, fdz, fy0K, tf, f, fp);
+                        tf = fmaf(-f, rcp_f32(fp), tf);
+                    }
+                    tf = halley_step_f32<true>(F, fPx, fPz, fdx, fdy, fdz, fdd, fy0K, tf);
+                } else {
+#pragma unroll
+                    for (int it = 0; it < N32 - 1; ++it) {
+                        float f, fp;
+                        surf_eval_f32<false>(F, fPx, fPz, fdx, fdy, fdz, fy0, tf, f, fp);
+                        tf = fmaf(-f, rcp_f32(fp), tf);
+                    }
+                    tf = halley_step_f32<false>(F, fPx, fPz, fdx, fdy, fdz, fdd, fy0, tf);
+                }
+            } else if (!GENERIC && !((REFINE_MASK >> si) & 1)) {
                 const float fy0K = fy0 - F.cK;
 #pragma unroll
                 for (int it = 0; it < N32; ++it) {
@@ -342,12 +424,28 @@ __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, doub
         }
         double X, Z, G, w, step = 0.0;
         const double y0PyK = GENERIC ? y0Py : y0Py - S.cK;
-#pragma unroll
-        for (int it = 0; it < N64; ++it) {
-            double f, fp;
-            surf_eval<GENERIC>(S, ((REFINE_MASK >> si) & 1) != 0, Px, Pz, dx, dy, dz, y0PyK, t, f, fp, X, Z, G, w);
-            step = f * rcp_seed(fp);
+        if (kLinear) {
+            // The fp32 root is converged to the fp32 floor (~1e-4 mm), so one fp64 Newton step
+            // lands on the fp64 root and the slope factor and the hit coordinates are carried
+            // to the new t to first order instead of by a second evaluation (9 DP instead of
+            // 24 + 2 MUFU): dG/dt = dG/du du/dt, dG/du = 4 a2' + 12 a3' u + c'K'/(2 s^3)
+            double f, fp, u, rs, xd;
+            surf_eval<GENERIC>(S, ((REFINE_MASK >> si) & 1) != 0, Px, Pz, dx, dy, dz, y0PyK, t, f, fp, X, Z, G, w, u, rs, xd);
+            step = f * SOSAT_LINEAR_RCP(fp);  // the seed's 3e-5 relative error stays in t: <= 3e-8 mm
             t -= step;
+            const double dGdu = fma(S.cKh, rs * rs * rs, fma(S.a3p12, u, S.a2p4));
+            G = fma(dGdu * xd, -2.0 * step, G);
+            X = fma(-step, dx, X);
+            Z = fma(-step, dz, Z);
+            if (fabs(step) > SOSAT_LINEAR_MAX_STEP) flags |= RAY_UNCONVERGED;  // false for NaN
+        } else {
+#pragma unroll
+            for (int it = 0; it < N64; ++it) {
+                double f, fp;
+                surf_eval<GENERIC>(S, ((REFINE_MASK >> si) & 1) != 0, Px, Pz, dx, dy, dz, y0PyK, t, f, fp, X, Z, G, w);
+                step = f * rcp_seed(fp);
+                t -= step;
+            }
         }
         if (ADAPTIVE) {
 #pragma unroll 1
@@ -359,7 +457,7 @@ __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, doub
                 t -= step;
             }
             if (!(fabs(step) <= SOSAT_NEWTON_TOL)) flags |= RAY_FLAGGED;
-        } else {
+        } else if (!kLinear) {
             if (fabs(step) > SOSAT_NEWTON_REFINE) flags |= RAY_UNCONVERGED;  // false for NaN
         }
         if (((EDGE_MASK >> si) & 1) && (EDGE_MASK == 0x10 || S.Kp > 0.0) && !(w >= SOSAT_EDGE_W))

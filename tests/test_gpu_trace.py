@@ -123,7 +123,9 @@ def test_reqs_frequency_sweep_known_answers(mods, feed_table):
 def test_all_newton_schedules_agree(mods, monkeypatch):
     g = golden("trace_cfg1_n40_90ghz.npz")
     t = tele_geo_from_golden(g)
-    for var in (0, 2, 6):  # 0 + 5, 3 + 2, 2 + 2 (default) fp32 + fp64 Newton steps
+    # 0 + 5, 3 + 2, 2 + 2 fp32 + fp64 Newton steps; 7 = the default (Newton + Halley in fp32, one
+    # fp64 step, slope factor carried to first order)
+    for var in (0, 2, 6, 7):
         monkeypatch.setenv("SOSAT_TRACE_VARIANT", str(var))
         _check_rows(mods["rt"].rx_to_lyot([0, 0, 0], t), g["out"], float(g["k"]))
 
