@@ -256,6 +256,36 @@ int sosat_ff_fwhm_indices(const float *d_B, int n, int *d_idx, float *d_val, voi
                           void *stream);
 
 /* ---- measurement helpers --------------------------------------------------------------- */
+/* ---- multi-GPU: reduce of the bin planes over NVLink peer memory -----------
+ * The reference has no multi-device path; north_star shards the rays of a bundle over the GPUs
+ * of a node and reduces the bins once.  sosat_peer_* map one rank's accumulator buffer into the
+ * other ranks' address spaces (CUDA IPC; one process per GPU); sosat_bins_reduce_field is the
+ * reduce fused with its consumer (sosat_bins_to_field_stats' normalisation, the replacement of
+ * getNearField's post-processing, ray_trace.py:1599-1614) and with the gather of the result. */
+#define SOSAT_PEER_HANDLE_BYTES 64
+/* Exportable device buffer (its own cudaMalloc, zero-filled) / release. */
+int sosat_peer_alloc(int64_t bytes, void **d_ptr);
+int sosat_peer_free(void *d_ptr);
+/* handle: SOSAT_PEER_HANDLE_BYTES bytes to send to the other processes of the node. */
+int sosat_peer_export(const void *d_ptr, unsigned char *handle);
+/* Map a peer's buffer (handle from ANOTHER process); peer access is enabled on first use. */
+int sosat_peer_open(const unsigned char *handle, void **d_peer);
+int sosat_peer_close(void *d_peer);
+/* For the cells [cell_begin, cell_end) of one (receiver, frequency) field: sum re / im / count
+ * over the n_peers buffers (float32 planes at byte offsets re_off / im_off / cnt_off from each
+ * base, identical layout everywhere), sum their statistics rows (SOSAT_NUM_STATS doubles at
+ * stats_off), normalise as sosat_bins_to_field_stats does with the SUMMED statistics, and store
+ * the complex64 cells at byte offset out_off of each of the n_out destination buffers.
+ * h_peer_base / h_out_base: HOST arrays of device pointers (own buffer and sosat_peer_open
+ * mappings).  d_stats_sum (optional, local): receives the summed statistics row.  The caller
+ * orders the launch after every peer's trace and the next overwrite of the planes after every
+ * peer's launch (stream-ordered barriers).  At most 16 peers / destinations. */
+int sosat_bins_reduce_field(const void *const *h_peer_base, int n_peers, int64_t re_off,
+                            int64_t im_off, int64_t cnt_off, int64_t stats_off,
+                            int64_t cell_begin, int64_t cell_end, double k_over_2e3,
+                            double opl_ref, void *const *h_out_base, int n_out, int64_t out_off,
+                            double *d_stats_sum, void *stream);
+
 /* Dependent-free FP64 FMA throughput microkernel: returns achieved FLOP/s (2 per FMA) in
  * *flops_per_s; used by bench.py as the roofline denominator of the ray tracer because
  * MEASURED_PEAKS.json carries no FP64 peak. */

@@ -85,6 +85,14 @@ SIGNATURES = {
                                          c_int, c_void_p, c_void_p, c_void_p]),
     "sosat_ff_fwhm_indices": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
     "sosat_measure_fp64_peak": (c_int, [POINTER(c_double), POINTER(c_double)]),
+    "sosat_peer_alloc": (c_int, [c_int64, POINTER(c_void_p)]),
+    "sosat_peer_free": (c_int, [c_void_p]),
+    "sosat_peer_export": (c_int, [c_void_p, c_void_p]),
+    "sosat_peer_open": (c_int, [c_void_p, POINTER(c_void_p)]),
+    "sosat_peer_close": (c_int, [c_void_p]),
+    "sosat_bins_reduce_field": (c_int, [POINTER(c_void_p), c_int, c_int64, c_int64, c_int64, c_int64,
+                                        c_int64, c_int64, c_double, c_double, POINTER(c_void_p),
+                                        c_int, c_int64, c_void_p, c_void_p]),
 }
 
 _lib = None

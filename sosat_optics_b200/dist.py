@@ -3,8 +3,11 @@
 The path shards naturally:
 
 * **rays** of one bundle: contiguous blocks of launch rows (iphi) per rank, each rank bins into
-  its own full-size private grid, then ONE all-reduce(sum) of the ``[re, im, count]`` planes
-  plus the 8 fp64 statistics over NVLink (NCCL) -- the only collective of the data path;
+  its own full-size private grid, then ONE reduce of the ``[re, im, count]`` planes plus the 8
+  fp64 statistics over NVLink -- the only exchange of the data path.  Two implementations:
+  :func:`reduce_bins` (NCCL all-reduce, then the normalisation kernel) and
+  :class:`PeerPlanes` (one kernel per rank over peer-mapped memory that reduces its slab of
+  cells, normalises it and stores it to every rank: ``csrc/peer.cu``);
 * **frequencies / receiver positions**: independent problems, dealt round-robin to ranks with
   no data-path collective (results are gathered).
 
@@ -85,16 +88,153 @@ def reduce_bins(re, im, cnt, stats, group=None, flat=None):
     return re, im, cnt, stats
 
 
+class _RawDeviceBuffer:
+    """``__cuda_array_interface__`` holder for a buffer owned by libsosat_b200 (zero-copy view)."""
+
+    def __init__(self, ptr: int, nbytes: int):
+        self.__cuda_array_interface__ = {"shape": (nbytes,), "typestr": "|u1",
+                                         "data": (ptr, False), "version": 2}
+
+
+def peer_layout(n_rx: int, n_freq: int, grid_n: int) -> dict:
+    """Byte offsets of ``[re | im | cnt | stats | field]`` inside a :class:`PeerPlanes` buffer
+    (every region 256-byte aligned; identical on all ranks)."""
+    n_ri = n_rx * n_freq * grid_n * grid_n
+    n_c = n_rx * grid_n * grid_n
+    off, out = 0, {}
+    for name, nbytes in (("re", 4 * n_ri), ("im", 4 * n_ri), ("cnt", 4 * n_c),
+                         ("stats", 8 * 8 * n_rx), ("stats_sum", 8 * 8 * n_rx), ("field", 8 * n_ri)):
+        out[name] = off
+        off += (nbytes + 255) // 256 * 256
+    out["bytes"] = off
+    out["accum_bytes"] = out["stats_sum"]  # [re | im | cnt | stats]: what a step zeroes
+    return out
+
+
+def slab_cells(n_cells: int, world: int, rank: int, align: int = 4) -> Tuple[int, int]:
+    """Cells [begin, end) of one field that ``rank`` reduces (begin a multiple of ``align``)."""
+    return partition_rows(n_cells, world, rank, align)
+
+
+class PeerPlanes:
+    """Accumulator planes of every rank of the node, mapped into this rank's address space.
+
+    ``re, im, cnt, stats`` are torch views of the local buffer (pass them to
+    ``ray_trace.trace_bin_device``); :meth:`reduce_field` is the fused reduce + normalisation
+    + gather.  One process per GPU on ONE node (CUDA IPC over NVLink / PCIe peer access)."""
+
+    def __init__(self, n_rx: int, n_freq: int, grid_n: int, group=None):
+        import ctypes
+        import torch
+        from . import _lib
+        dist = _dist()
+        self.lib = _lib.require_gpu()
+        self.group = group
+        self.rank, self.world = world_info(group)
+        if self.world > 16:
+            raise ValueError("PeerPlanes supports at most 16 ranks (one node)")
+        self.shape = (n_rx, n_freq, grid_n)
+        self.layout = L = peer_layout(n_rx, n_freq, grid_n)
+        base = ctypes.c_void_p()
+        _lib.check(self.lib.sosat_peer_alloc(L["bytes"], ctypes.byref(base)))
+        self.base = base.value
+        self._raw = _RawDeviceBuffer(self.base, L["bytes"])
+        self.flat = torch.as_tensor(self._raw, device="cuda")
+        n_ri, n_c = n_rx * n_freq * grid_n * grid_n, n_rx * grid_n * grid_n
+
+        def view(name, nbytes, dtype, shape):
+            return self.flat[L[name]:L[name] + nbytes].view(dtype).view(shape)
+
+        self.re = view("re", 4 * n_ri, torch.float32, (n_rx, n_freq, grid_n, grid_n))
+        self.im = view("im", 4 * n_ri, torch.float32, (n_rx, n_freq, grid_n, grid_n))
+        self.cnt = view("cnt", 4 * n_c, torch.float32, (n_rx, grid_n, grid_n))
+        self.stats = view("stats", 64 * n_rx, torch.float64, (n_rx, 8))
+        self.stats_sum = view("stats_sum", 64 * n_rx, torch.float64, (n_rx, 8))
+        self.field = torch.view_as_complex(
+            view("field", 8 * n_ri, torch.float32, (n_rx, n_freq, grid_n, grid_n, 2)))
+        self.accum = self.flat[:L["accum_bytes"]]
+        self._flag = torch.zeros(1, dtype=torch.float32, device="cuda")
+        # exchange the IPC handles and map the peers
+        handle = (ctypes.c_ubyte * 64)()
+        _lib.check(self.lib.sosat_peer_export(ctypes.c_void_p(self.base), handle))
+        handles = [None] * self.world
+        if self.world > 1:
+            dist.all_gather_object(handles, bytes(handle), group=group)
+        else:
+            handles[0] = bytes(handle)
+        self.peer_base: List[int] = []
+        self._opened: List[int] = []
+        for r, h in enumerate(handles):
+            if r == self.rank:
+                self.peer_base.append(self.base)
+                continue
+            ptr = ctypes.c_void_p()
+            buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+            _lib.check(self.lib.sosat_peer_open(buf, ctypes.byref(ptr)))
+            self.peer_base.append(ptr.value)
+            self._opened.append(ptr.value)
+        self._c_peers = (ctypes.c_void_p * self.world)(*self.peer_base)
+
+    def zero(self):
+        """Zero the accumulators (planes and statistics) for the next step."""
+        self.accum.zero_()
+
+    def barrier(self):
+        """Stream-ordered barrier over the ranks (one-element NCCL all-reduce; no host sync)."""
+        if self.world > 1:
+            _dist().all_reduce(self._flag, group=self.group)
+
+    def reduce_field(self, freq_specs, opl_ref: float = 0.0, dest: Optional[Sequence[int]] = None):
+        """Sum every rank's planes and statistics, normalise to the complex field and store it
+        in ``self.field`` of the ranks in ``dest`` (default: all).  Collective: every rank calls
+        it after its trace.  Returns ``self.field`` (valid on the destination ranks)."""
+        import ctypes
+        import torch
+        from . import _lib, geometry
+        n_rx, n_freq, n = self.shape
+        L = self.layout
+        dest = list(range(self.world)) if dest is None else list(dest)
+        c_out = (ctypes.c_void_p * len(dest))(*[self.peer_base[d] for d in dest])
+        b0, b1 = slab_cells(n * n, self.world, self.rank)
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        self.barrier()  # every rank's trace has finished
+        for i in range(n_rx):
+            for f, (k, _, _) in enumerate(freq_specs):
+                fld = (i * n_freq + f) * n * n
+                _lib.check(self.lib.sosat_bins_reduce_field(
+                    self._c_peers, self.world, L["re"] + 4 * fld, L["im"] + 4 * fld,
+                    L["cnt"] + 4 * i * n * n, L["stats"] + 64 * i, b0, b1,
+                    geometry.scalar(k) / 1e3 / 2, float(opl_ref), c_out, len(dest),
+                    L["field"] + 8 * fld, ctypes.c_void_p(self.stats_sum[i].data_ptr()), stream))
+        self.barrier()  # every slab has landed; the planes may be overwritten
+        return self.field
+
+    def close(self):
+        import ctypes
+        from . import _lib
+        for ptr in self._opened:
+            _lib.check(self.lib.sosat_peer_close(ctypes.c_void_p(ptr)))
+        self._opened = []
+        if self.base:
+            for name in ("re", "im", "cnt", "stats", "stats_sum", "field", "accum", "flat", "_raw"):
+                setattr(self, name, None)
+            _lib.check(self.lib.sosat_peer_free(ctypes.c_void_p(self.base)))
+            self.base = 0
+
+
 def near_field_binned_distributed(tele_geo, rx, grid_n: int, extent_cm: float,
                                   freqs: Optional[Sequence] = None, group=None,
                                   trace_fn: Optional[Callable] = None,
-                                  field_fn: Optional[Callable] = None):
+                                  field_fn: Optional[Callable] = None,
+                                  peer: Optional["PeerPlanes"] = None):
     """Ray-sharded fused trace + binning: every rank traces its block of launch rows, the
-    bin planes are all-reduced, and every rank ends with the full field.
+    bin planes are reduced, and every rank ends with the full field.
 
     ``trace_fn`` / ``field_fn`` default to the CUDA entry points
     (:func:`ray_trace.trace_bin_device`, :func:`ray_trace.bins_to_field_device`); they are
     injectable so that the sharding and the reduce can be exercised on CPU with ``gloo``.
+    ``peer``: a :class:`PeerPlanes` of matching shape selects the fused peer-memory reduce
+    instead of the NCCL all-reduce (the counts are then not gathered: ``cnt`` is ``None``).
     Returns ``(b, cnt, stats)``: complex field ``[n_rx, n_freq, N, N]``, counts, host stats."""
     from . import ray_trace
     rank, world = world_info(group)
@@ -104,6 +244,14 @@ def near_field_binned_distributed(tele_geo, rx, grid_n: int, extent_cm: float,
         (tele_geo.k, tele_geo.th_fwhp_x, tele_geo.th_fwhp_y)]
     r0, r1 = partition_rows(int(tele_geo.n_scan), world, rank)
     rx_arr = np.asarray(rx, dtype=np.float64).reshape(-1, 3)
+    if peer is not None:
+        if peer.shape != (len(rx_arr), len(specs), grid_n):
+            raise ValueError("PeerPlanes shape %r does not match the request" % (peer.shape,))
+        peer.zero()
+        trace_fn(tele_geo, rx_arr, specs, grid_n, extent_cm * 10.0, row_begin=r0, row_end=r1,
+                 planes=(peer.re, peer.im, peer.cnt), stats=peer.stats)
+        b = peer.reduce_field(specs).clone()
+        return b, None, peer.stats_sum.cpu().numpy()
     re, im, cnt, stats = trace_fn(tele_geo, rx_arr, specs, grid_n, extent_cm * 10.0,
                                   row_begin=r0, row_end=r1)
     re, im, cnt, stats = reduce_bins(re, im, cnt, stats, group)

@@ -1,5 +1,5 @@
-"""GPU: the ray-sharded near field on 2 GPUs (NCCL all-reduce of the bin planes) equals the
-single-GPU result.  Skipped on a 1-GPU box; the sharding/reduce logic itself is covered on CPU
+"""GPU: the ray-sharded near field on 2 GPUs (NCCL all-reduce of the bin planes, and the fused
+reduce over peer-mapped memory) equals the single-GPU result.  Skipped on a 1-GPU box; the sharding/reduce logic itself is covered on CPU
 by tests/test_host_logic.py (gloo, world size 2)."""
 import os
 import socket
@@ -64,6 +64,68 @@ def test_two_gpu_ray_sharding_matches_single_gpu():
         assert np.abs(b - one.b).max() < 1e-4 * np.abs(one.b).max()
         assert np.array_equal(stats[:, [0, 7]], one.stats[:, [0, 7]])
         assert np.allclose(stats[:, 1], one.stats[:, 1], rtol=1e-12)
+
+
+RX_STEPS = ([[0, 0, 0], [100, 0, 60]], [[-80, 0, 40], [30, 0, -120]])
+
+
+def _peer_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        from sosat_optics_b200 import dist as sdist, opt_analyze, ot_geo
+        t = ot_geo.SatGeo()
+        t.n_scan = 700
+        t.y_source = ot_geo.y_lyot + 300
+        t.lambda_ = opt_analyze.ghz_to_m(90)
+        t.k = 2 * np.pi / t.lambda_
+        peer = sdist.PeerPlanes(2, 1, 128)
+        out = []
+        for rx in RX_STEPS:  # the same buffers twice: a stale read of a peer's planes would show
+            b, _, stats = sdist.near_field_binned_distributed(t, rx, 128, 42.0, peer=peer)
+            out.append((b.cpu().numpy(), stats))
+        torch.cuda.synchronize()
+        dist.barrier()
+        peer.close()
+        q.put((rank, out))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_peer_memory_reduce_matches_single_gpu():
+    """csrc/peer.cu: every rank reduces its slab of cells from both ranks' planes over peer
+    memory, normalises it and stores it to both ranks."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from sosat_optics_b200 import opt_analyze, ot_geo, ray_trace
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_peer_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda r: r[0])
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    t = ot_geo.SatGeo()
+    t.n_scan = 700
+    t.y_source = ot_geo.y_lyot + 300
+    t.lambda_ = opt_analyze.ghz_to_m(90)
+    t.k = 2 * np.pi / t.lambda_
+    for step, rx in enumerate(RX_STEPS):
+        one = ray_trace.near_field_binned(t, rx, grid_n=128, extent_cm=42.0)
+        for rank, out in res:
+            b, stats = out[step]
+            assert np.abs(b - one.b).max() < 1e-4 * np.abs(one.b).max(), (step, rank)
+            assert np.array_equal(stats[:, [0, 7]], one.stats[:, [0, 7]])
+            assert np.allclose(stats[:, 1], one.stats[:, 1], rtol=1e-12)
 
 
 def test_side_stream_and_second_device_in_one_process():

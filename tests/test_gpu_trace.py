@@ -565,3 +565,79 @@ def test_bins_to_field_on_device_statistics(mods, feed_table):
     b_dev, none = rt.bins_to_field_device(re, im, cnt, st, specs, sync=False)
     assert none is None and h.shape == (2, 8)
     assert (b_host - b_dev).abs().max().item() < 2e-6 * b_host.abs().max().item()
+
+
+def test_peer_reduce_kernel_on_one_device(mods, feed_table):
+    """csrc/peer.cu on one GPU: three buffers of the same device stand in for three ranks, each
+    holding the bins of a third of the launch rows.  Reducing slab by slab into two destination
+    buffers must give the field of the whole bundle (sosat_bins_to_field_stats on the summed
+    planes), for two receivers and two frequencies; a 1-rank PeerPlanes does the same through
+    the Python wrapper."""
+    import ctypes
+    rt, geometry, torch = mods["rt"], mods["geometry"], mods["torch"]
+    from sosat_optics_b200 import _lib, dist as sdist
+    lib = _lib.require_gpu()
+    t = _bundle(mods, 210)
+    specs = geometry.freq_specs_from_table([90.0, 150.0], feed_table)
+    rxs = np.array([[0.0, 0, 0], [80, 0, -50]])
+    n, n_rx, n_freq = 66, 2, 2   # 66^2 cells: slabs that are not multiples of 4 cells
+    L = sdist.peer_layout(n_rx, n_freq, n)
+    re, im, cnt, st = rt.trace_bin_device(t, rxs, specs, n, 420.0)
+    want, _ = rt.bins_to_field_device(re, im, cnt, st, specs, sync=False)
+
+    bufs, views = [], []
+    for r in range(3):
+        p = ctypes.c_void_p()
+        _lib.check(lib.sosat_peer_alloc(L["bytes"], ctypes.byref(p)))
+        bufs.append(p.value)
+        flat = torch.as_tensor(sdist._RawDeviceBuffer(p.value, L["bytes"]), device="cuda")
+        n_ri = n_rx * n_freq * n * n
+        v = {
+            "re": flat[L["re"]:L["re"] + 4 * n_ri].view(torch.float32).view(n_rx, n_freq, n, n),
+            "im": flat[L["im"]:L["im"] + 4 * n_ri].view(torch.float32).view(n_rx, n_freq, n, n),
+            "cnt": flat[L["cnt"]:L["cnt"] + 4 * n_rx * n * n].view(torch.float32).view(n_rx, n, n),
+            "stats": flat[L["stats"]:L["stats"] + 64 * n_rx].view(torch.float64).view(n_rx, 8),
+            "field": flat[L["field"]:L["field"] + 8 * n_ri].view(torch.float32).view(n_rx, n_freq, n, n, 2),
+            "flat": flat,
+        }
+        views.append(v)
+        r0, r1 = sdist.partition_rows(210, 3, r)
+        rt.trace_bin_device(t, rxs, specs, n, 420.0, row_begin=r0, row_end=r1,
+                            planes=(v["re"], v["im"], v["cnt"]), stats=v["stats"])
+    try:
+        c_peers = (ctypes.c_void_p * 3)(*bufs)
+        c_out = (ctypes.c_void_p * 2)(bufs[0], bufs[2])
+        ssum = torch.zeros((n_rx, 8), dtype=torch.float64, device="cuda")
+        stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+        for rank in range(3):  # the three "ranks" reduce their slabs one after the other
+            b0, b1 = sdist.slab_cells(n * n, 3, rank)
+            for i in range(n_rx):
+                for f, (k, _, _) in enumerate(specs):
+                    fld = (i * n_freq + f) * n * n
+                    _lib.check(lib.sosat_bins_reduce_field(
+                        c_peers, 3, L["re"] + 4 * fld, L["im"] + 4 * fld, L["cnt"] + 4 * i * n * n,
+                        L["stats"] + 64 * i, b0, b1, geometry.scalar(k) / 1e3 / 2, 0.0, c_out, 2,
+                        L["field"] + 8 * fld, ctypes.c_void_p(ssum[i].data_ptr()), stream))
+        torch.cuda.synchronize()
+        for d in (0, 2):
+            got = torch.view_as_complex(views[d]["field"])
+            assert (got - want).abs().max().item() < 3e-6 * want.abs().max().item()
+        assert views[1]["field"].abs().max().item() == 0.0  # not a destination
+        assert torch.equal(ssum[:, [0, 7]], st[:, [0, 7]])
+        assert torch.allclose(ssum[:, 1], st[:, 1], rtol=1e-12)
+        rc = lib.sosat_bins_reduce_field(c_peers, 3, L["re"], L["im"], L["cnt"], L["stats"], 2, 8,
+                                         1.0, 0.0, c_out, 2, L["field"], None, stream)
+        assert rc != 0 and b"multiple of 4" in lib.sosat_last_error()
+    finally:
+        views.clear()
+        for p in bufs:
+            _lib.check(lib.sosat_peer_free(ctypes.c_void_p(p)))
+
+    peer = sdist.PeerPlanes(n_rx, n_freq, n)   # world size 1: no process group needed
+    try:
+        b, none, stats = sdist.near_field_binned_distributed(t, rxs, n, 42.0, specs, peer=peer)
+        assert none is None
+        assert (b - want).abs().max().item() < 3e-6 * want.abs().max().item()
+        assert np.array_equal(stats[:, 0], st[:, 0].cpu().numpy())
+    finally:
+        peer.close()
