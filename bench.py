@@ -263,30 +263,46 @@ def run_ours(args):
     total_rays = n_scan * n_scan
     my_rays = (r1 - r0) * n_scan
 
-    re, im, cnt, planes_flat = sdist.alloc_planes(1, 1, GRID_N)  # one buffer: one collective
-    stats = torch.zeros((1, _lib.NUM_STATS), dtype=torch.float64, device="cuda")
+    # N > 1: the bin planes live in a buffer that every rank of the node maps (CUDA IPC), and one
+    # kernel per rank reduces its slab of cells from all peers over NVLink, normalises it and
+    # stores it into rank 0's field (csrc/peer.cu); --reduce nccl selects the all-reduce path
+    use_peer = world > 1 and args.reduce == "peer"
+    if use_peer:
+        peer = sdist.PeerPlanes(1, 1, GRID_N)
+        re, im, cnt, stats, planes_flat = peer.re, peer.im, peer.cnt, peer.stats, peer.accum
+    else:
+        re, im, cnt, planes_flat = sdist.alloc_planes(1, 1, GRID_N)  # one buffer: one collective
+        stats = torch.zeros((1, _lib.NUM_STATS), dtype=torch.float64, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     host_B = torch.empty((GRID_N, GRID_N), dtype=torch.complex64).pin_memory()
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
     def step(e2e=False, kernel_events=None):
         """One pass of the hot path.  Returns the far field (device tensor)."""
-        planes_flat.zero_(); stats.zero_()
+        planes_flat.zero_()
+        if not use_peer:
+            stats.zero_()
         if kernel_events is not None:
             kernel_events[0].record()
         ray_trace.trace_bin_device(t, rx, spec, GRID_N, EXTENT_CM * 10, row_begin=r0, row_end=r1,
                                    planes=(re, im, cnt), stats=stats)
         if kernel_events is not None:
             kernel_events[1].record()
-        sdist.reduce_bins(re, im, cnt, stats, flat=planes_flat)
-        b, _ = ray_trace.bins_to_field_device(re, im, cnt, stats, spec, sync=False)
+        if use_peer:
+            b = peer.reduce_field(spec, dest=[0])  # the job has ONE far field: rank 0 makes it
+        else:
+            sdist.reduce_bins(re, im, cnt, stats, flat=planes_flat)
+            b, _ = ray_trace.bins_to_field_device(re, im, cnt, stats, spec, sync=False)
         if kernel_events is not None:
             kernel_events[2].record()
-        B = opt_analyze.far_field(b[0, 0], device=True)
+        B = None
+        if rank == 0 or not use_peer:
+            B = opt_analyze.far_field(b[0, 0], device=True)
         if kernel_events is not None:
             kernel_events[3].record()
         if e2e:
-            host_B.copy_(B, non_blocking=True)
+            if B is not None:
+                host_B.copy_(B, non_blocking=True)
             torch.cuda.current_stream().synchronize()
         return B
 
@@ -301,7 +317,7 @@ def run_ours(args):
     barrier()
     sampler = ClockSampler(local)
     sampler.start()
-    step_ms, trace_ms, ff_ms = [], [], []
+    step_ms, trace_ms, ff_ms, red_ms = [], [], [], []
     barrier()
     t_wall0 = time.perf_counter()
     for _ in range(args.steps):
@@ -315,6 +331,7 @@ def run_ours(args):
         step_ms.append(e0.elapsed_time(e1))
         trace_ms.append(ke[0].elapsed_time(ke[1]))
         ff_ms.append(ke[2].elapsed_time(ke[3]))
+        red_ms.append(ke[1].elapsed_time(ke[2]))
     barrier()
     wall_s = time.perf_counter() - t_wall0
     clocks = sampler.result()
@@ -350,6 +367,9 @@ def run_ours(args):
 
     if rank != 0:
         if world > 1:
+            dist.barrier()
+            if use_peer:
+                peer.close()
             dist.destroy_process_group()
         return
 
@@ -496,8 +516,11 @@ def run_ours(args):
         "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
         "config": {"workload": WORKLOAD if n_scan == N_SCAN else f"REDUCED n_scan={n_scan}: " + WORKLOAD,
                    "n_scan": n_scan, "rays_per_step": total_rays, "grid_n": GRID_N,
-                   "extent_cm": EXTENT_CM, "ghz": GHZ, "sharding": f"launch-row blocks x{world}, "
-                   "one NCCL all-reduce of [re,im,count] planes (50 MB) + 8 fp64 sums",
+                   "extent_cm": EXTENT_CM, "ghz": GHZ, "sharding": f"launch-row blocks x{world}, " + (
+                       "fused reduce over peer-mapped memory: each rank sums its slab of the [re,im,count] "
+                       "planes and the 8 fp64 sums from all peers, normalises it and stores it to rank 0, "
+                       "which computes the far field" if use_peer else
+                       "one NCCL all-reduce of [re,im,count] planes (50 MB) + 8 fp64 sums"),
                    "l2": "256 MiB flush write between timed steps; the kernel reads no input arrays",
                    "newton_schedule": os.environ.get("SOSAT_TRACE_VARIANT", "default (fp32 Newton + Halley step, 1 fp64 Newton step, first-order slope update; long steps re-traced adaptively)")},
         "clocks": clocks,
@@ -510,10 +533,14 @@ def run_ours(args):
         "configs": configs,
         "wall_s_timed_region": wall_s,
         "far_field_ms_in_step": statistics.median(ff_ms),
+        "reduce_ms_in_step": statistics.median(red_ms),  # rank 0: reduce (+ wait for the slowest rank) + bins -> field
         "peaks": peaks_kind,
     }
     print(json.dumps(line), flush=True)
     if world > 1:
+        dist.barrier()
+        if use_peer:
+            peer.close()
         dist.destroy_process_group()
 
 
@@ -525,6 +552,8 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--n-scan", type=int, default=N_SCAN, help="reduce only for debugging")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--reduce", choices=["peer", "nccl"], default="peer",
+                    help="N > 1: fused peer-memory reduce (default) or NCCL all-reduce of the bin planes")
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3  # timing rule: at least 3 warm-up steps

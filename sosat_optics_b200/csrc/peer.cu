@@ -43,22 +43,21 @@ __device__ __forceinline__ float2 norm_cell(float r, float i, float c, float fcs
 __global__ void __launch_bounds__(256)
 bins_reduce_field_kernel(PeerArgs P, long long begin, long long end, double k_over_2e3,
                          double opl_ref, double *__restrict__ stats_sum) {
-    // statistics of the whole bundle: sum of the peers' rows (8 doubles each)
+    // statistics of the whole bundle: sum of the peers' rows (8 doubles each).  ONE thread per
+    // statistic and block fetches them (every thread reading the same remote sectors would
+    // serialise on the peers' L2: 1 ms at 8 GPUs, measured)
+    __shared__ double s_st[SOSAT_NUM_STATS];
+    if (threadIdx.x < SOSAT_NUM_STATS) {
+        double v = 0.0;
+        for (int p = 0; p < P.n_peers; ++p)
+            v += __ldcg((const double *)(P.base[p] + P.stats_off) + threadIdx.x);
+        s_st[threadIdx.x] = v;
+        if (stats_sum && blockIdx.x == 0) stats_sum[threadIdx.x] = v;
+    }
+    __syncthreads();
     double st[SOSAT_NUM_STATS];
 #pragma unroll
-    for (int q = 0; q < SOSAT_NUM_STATS; ++q) st[q] = 0.0;
-    for (int p = 0; p < P.n_peers; ++p) {
-        const double *s = (const double *)(P.base[p] + P.stats_off);
-#pragma unroll
-        for (int q = 0; q < SOSAT_NUM_STATS; ++q) st[q] += __ldcg(s + q);
-    }
-    if (stats_sum && blockIdx.x == 0 && threadIdx.x < SOSAT_NUM_STATS) {
-        // (static indexing keeps st[] in registers)
-        double v = 0.0;
-#pragma unroll
-        for (int q = 0; q < SOSAT_NUM_STATS; ++q) v = threadIdx.x == q ? st[q] : v;
-        stats_sum[threadIdx.x] = v;
-    }
+    for (int q = 0; q < SOSAT_NUM_STATS; ++q) st[q] = s_st[q];
     const double nv = st[SOSAT_STAT_N_VALID];
     const double mean_opl = nv > 0 ? st[SOSAT_STAT_SUM_OPL] / nv : 0.0;
     double sn, cs;
