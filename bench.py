@@ -483,7 +483,7 @@ def run_ours(args):
             "points": n_pts, "angles": n_ang, "ms_best": min(ts), "pairs_per_s": pairs,
             "bound": "sfu", "achieved_mufu_per_s": 2 * pairs, "peak_mufu_per_s": mufu_peak,
             "frac": 2 * pairs / mufu_peak,
-            "note": "2 MUFU (sin, cos) + ~10 FP32 per pair; 16 MUFU lanes/clk/SM (measured: "
+            "note": "2 MUFU (sin, cos) + 7 FP32 per pair, points split over gridDim.y; 16 MUFU lanes/clk/SM (measured: "
                     "8 cycles per warp instruction and SMSP, scripts/dp_latency.cu)"}
 
     # ---- the other BASELINE.json configs, one line each (N = 1 only; not the headline) ----

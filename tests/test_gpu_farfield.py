@@ -174,6 +174,20 @@ def test_nudft_direct_matches_oracle_and_regular_grid(mods):
     direct = oa.far_field_irregular(X.ravel(), Y.ravel(), field.ravel(), AX, AY, lam)
     gemm = oa.far_field(field.astype(np.complex64))
     assert _rel_peak(direct, gemm) < 2 * FF_TOL
+    # fewer points than one shared-memory chunk: a single point split, plain stores
+    out1 = oa.far_field_irregular(x[:500], y[:500], b[:500], TX, TY, lam)
+    ref1 = oracle.nudft_direct(x[:500], y[:500], b[:500], TX.ravel(), TY.ravel(), lam).reshape(TX.shape)
+    assert _rel_peak(out1, ref1) < FF_TOL
+    # phases of hundreds of revolutions (30 degrees off axis at 1 mm): the SFU sin/cos take the
+    # fractional part of the revolution count themselves; a beam steered to (0.45, -0.3) rad
+    lam_s = 1.0e-3
+    steer = np.exp(2j * np.pi * (x * 0.45 - y * 0.3) / lam_s)
+    th2 = np.linspace(-0.02, 0.02, 21)
+    SX, SY = np.meshgrid(0.45 + th2, -0.3 + th2)
+    out2 = oa.far_field_irregular(x, y, steer, SX, SY, lam_s)
+    ref2 = oracle.nudft_direct(x, y, steer, SX.ravel(), SY.ravel(), lam_s).reshape(SX.shape)
+    assert abs(abs(ref2[10, 10]) - npts) < 1e-6 * npts      # the steered peak
+    assert _rel_peak(out2, ref2) < FF_TOL
     # empty inputs
     assert oa.far_field_irregular([], [], [], TX, TY, lam).shape == TX.shape
     assert np.all(oa.far_field_irregular([], [], [], TX, TY, lam) == 0)
