@@ -173,3 +173,28 @@ def test_sim_data_glue_matches_reference_golden():
     assert np.abs(d.a_data - g["a_data"]).max() < 1e-12
     assert np.abs(d.p_data - g["p_data"]).max() < 1e-12
     assert np.array_equal(d.x_data, g["x_data"]) and np.array_equal(d.y_data, g["y_data"])
+
+
+def test_peer_plane_layout_and_cell_slabs():
+    """Host logic of the fused peer-memory reduce (dist.PeerPlanes / csrc/peer.cu): the buffer
+    layout is aligned and disjoint, and the cell slabs tile a field exactly with every slab
+    starting on a multiple of 4 cells (the kernel's 16-byte loads)."""
+    from sosat_optics_b200 import dist as sdist
+    for n_rx, n_freq, n in ((1, 1, 2048), (2, 3, 66), (3, 1, 7)):
+        L = sdist.peer_layout(n_rx, n_freq, n)
+        n_ri, n_c = n_rx * n_freq * n * n, n_rx * n * n
+        regions = [("re", 4 * n_ri), ("im", 4 * n_ri), ("cnt", 4 * n_c), ("stats", 64 * n_rx),
+                   ("stats_sum", 64 * n_rx), ("field", 8 * n_ri)]
+        end = 0
+        for name, nbytes in regions:
+            assert L[name] % 256 == 0 and L[name] >= end, name
+            end = L[name] + nbytes
+        assert L["bytes"] >= end and L["accum_bytes"] == L["stats_sum"]
+        for world in (1, 2, 3, 8, 16):
+            slabs = [sdist.slab_cells(n * n, world, r) for r in range(world)]
+            assert slabs[0][0] == 0 and slabs[-1][1] == n * n
+            for (a0, a1), (b0, b1) in zip(slabs, slabs[1:]):
+                assert a1 == b0
+            assert all(b % 4 == 0 and e >= b for b, e in slabs)
+            sizes = [e - b for b, e in slabs if e > b]
+            assert max(sizes) - min(sizes) < 8 or len(sizes) < world  # one 4-cell unit + ragged tail
