@@ -150,7 +150,8 @@ extern "C" int sosat_bins_reduce_field(const void *const *h_peer_base, int n_pee
     SOSAT_REQUIRE(n_peers >= 1 && n_peers <= kMaxPeers && n_out >= 1 && n_out <= kMaxPeers,
                   "sosat_bins_reduce_field: between 1 and %d peers / destinations", kMaxPeers);
     SOSAT_REQUIRE(cell_begin >= 0 && cell_end >= cell_begin, "bad cell range");
-    SOSAT_REQUIRE(cell_begin % 4 == 0, "cell_begin must be a multiple of 4");
+    // (an empty slab -- more ranks than 4-cell units -- still launches: it sums the statistics)
+    SOSAT_REQUIRE(cell_begin % 4 == 0 || cell_begin == cell_end, "cell_begin must be a multiple of 4");
     SOSAT_REQUIRE(re_off % 16 == 0 && im_off % 16 == 0 && cnt_off % 16 == 0 && out_off % 16 == 0 &&
                       stats_off % 8 == 0,
                   "sosat_bins_reduce_field: misaligned plane offset");

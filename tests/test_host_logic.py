@@ -195,6 +195,6 @@ def test_peer_plane_layout_and_cell_slabs():
             assert slabs[0][0] == 0 and slabs[-1][1] == n * n
             for (a0, a1), (b0, b1) in zip(slabs, slabs[1:]):
                 assert a1 == b0
-            assert all(b % 4 == 0 and e >= b for b, e in slabs)
+            assert all((b % 4 == 0 and e > b) or e == b for b, e in slabs)  # empty slabs allowed
             sizes = [e - b for b, e in slabs if e > b]
             assert max(sizes) - min(sizes) < 8 or len(sizes) < world  # one 4-cell unit + ragged tail
