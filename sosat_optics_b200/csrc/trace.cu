@@ -168,16 +168,10 @@ constexpr int kTileH = 2 * kBinWarps;
 #define SOSAT_BIN_NR 1
 #endif
 constexpr int kNR = SOSAT_BIN_NR;
-// Optional shared-memory bin tile (north_star: "shuffle, then shared-memory atomics"): the run
-// heads of all warps of a CTA add into an 8 x 8-bin window anchored at the CTA's smallest bin
-// coordinates (red.shared), and 64 threads flush the window with one global reduction per
-// touched cell and plane.  Costs two more CTA barriers per tile; single-frequency launches only.
-// Measured at configs[4] density: see DESIGN.md section 3 (off by default).
-#ifndef SOSAT_BIN_SMEM_TILE
-#define SOSAT_BIN_SMEM_TILE 0
-#endif
-constexpr int kWin = 8;  // window edge in bins
-static_assert(kWin > 0, "");
+// (A shared-memory bin window per CTA -- north_star's "shuffle, then shared-memory atomics" --
+// was built and measured at -8 %: after the run-length aggregation a warp issues only 3-6
+// global reductions per 32 rays.  DESIGN.md section 3; the code is in the history, commit
+// 3515e61.)
 constexpr int kTileW = kTile * kNR;
 constexpr int kTileMax = kTileH > kTileW ? kTileH : kTileW;
 
@@ -218,31 +212,21 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
     __shared__ double2 s_rot[16 + 64 + 64];
     __shared__ float s_amp[SOSAT_MAX_FREQS][2][kTileMax];  // [freq][theta|phi][index in tile]
     // Running statistics.  fp64 sums: one shared-memory slot per thread (no conflicts, no
-    // registers held across the tracer).  Counters: warp ballots added by lane 0 to packed
-    // 64-bit shared counters; the rare slow-path events use plain shared atomics.
+    // registers held across the tracer).  Counters: warp ballots added by lane 0 to its warp's
+    // shared slot (a 64-bit shared atomicAdd is a CAS loop: 25 instructions per warp and ray,
+    // measured); the rare slow-path events use plain shared atomics.
     __shared__ double s_sum[4][kBinThreads];
-    __shared__ unsigned long long s_valid_binned;  // n_valid | n_binned << 32
+    __shared__ unsigned s_nvalid[kBinWarps], s_nbinned[kBinWarps];  // one slot per warp: no atomics
     __shared__ unsigned s_rare[2];                 // n_slow, n_bracket_fail
-#if SOSAT_BIN_SMEM_TILE
-    __shared__ float s_win[3][kWin * kWin];        // re, im, count of the CTA's bin window
-    __shared__ int s_win_min[2];                   // smallest ix, iz of the tile's binned rays
-#endif
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lth = (lane & 7) + 8 * (warp & 1);
     const int lph = (lane >> 3) + 4 * (warp >> 1);
-#if SOSAT_BIN_SMEM_TILE
-    const bool use_win = re != nullptr && p.n_freq == 1;
-    if (tid < kWin * kWin) s_win[0][tid] = s_win[1][tid] = s_win[2][tid] = 0.f;
-    if (tid < 2) s_win_min[tid] = 0x7fffffff;
-#endif
 
 #pragma unroll
     for (int q = 0; q < 4; ++q) s_sum[q][tid] = 0.0;
-    if (tid == 0) {
-        s_valid_binned = 0ull;
-        s_rare[0] = s_rare[1] = 0u;
-    }
+    if (tid < kBinWarps) s_nvalid[tid] = s_nbinned[tid] = 0u;
+    if (tid == 0) s_rare[0] = s_rare[1] = 0u;
     const bool use_rot = p.n_scan <= 65536;
     if (use_rot) {
         for (int e = tid; e < 16 + 64 + 64; e += kBinThreads) {
@@ -262,32 +246,55 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
 
     auto flush_stats = [&](int irx_done) {
         __syncthreads();  // all counter updates of the finished receiver are in
-        const unsigned long long vb = s_valid_binned;
         const bool t0 = tid == 0;
+        unsigned nv = 0u, nb = 0u;
+        if (t0) {
+#pragma unroll
+            for (int w = 0; w < kBinWarps; ++w) {
+                nv += s_nvalid[w];
+                nb += s_nbinned[w];
+            }
+        }
         double acc[SOSAT_NUM_STATS];
-        acc[SOSAT_STAT_N_VALID] = t0 ? (double)(unsigned)(vb & 0xffffffffull) : 0.0;
+        acc[SOSAT_STAT_N_VALID] = (double)nv;
         acc[SOSAT_STAT_SUM_OPL] = s_sum[0][tid];
         acc[SOSAT_STAT_SUM_DX] = s_sum[1][tid];
         acc[SOSAT_STAT_SUM_DY] = s_sum[2][tid];
         acc[SOSAT_STAT_SUM_DZ] = s_sum[3][tid];
         acc[SOSAT_STAT_N_SLOW] = t0 ? (double)s_rare[0] : 0.0;
         acc[SOSAT_STAT_N_BRACKET_FAIL] = t0 ? (double)s_rare[1] : 0.0;
-        acc[SOSAT_STAT_N_BINNED] = t0 ? (double)(unsigned)(vb >> 32) : 0.0;
+        acc[SOSAT_STAT_N_BINNED] = (double)nb;
         if (stats) block_accumulate<SOSAT_NUM_STATS>(acc, stats + (long long)irx_done * SOSAT_NUM_STATS);
         __syncthreads();
 #pragma unroll
         for (int q = 0; q < 4; ++q) s_sum[q][tid] = 0.0;
-        if (t0) {
-            s_valid_binned = 0ull;
-            s_rare[0] = s_rare[1] = 0u;
-        }
+        if (tid < kBinWarps) s_nvalid[tid] = s_nbinned[tid] = 0u;
+        if (t0) s_rare[0] = s_rare[1] = 0u;
     };
 
-    const unsigned n_tiles = (unsigned)p.n_tiles;
-    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-        const int irx = (int)(tile / tiles_per_rx);
-        const unsigned trem = tile - (unsigned)irx * tiles_per_rx;
-        const int ty = (int)(trem / (unsigned)p.tiles_x), tx = (int)(trem - (unsigned)ty * (unsigned)p.tiles_x);
+    // tile = (irx, ty, tx): divided out once per CTA and then advanced by the grid stride with
+    // carries (the three 32-bit divisions per tile were 45 instructions per ray, measured)
+    const unsigned n_tiles = (unsigned)p.n_tiles, ntx = (unsigned)p.tiles_x, nty = (unsigned)p.tiles_y;
+    unsigned u_rx = blockIdx.x / tiles_per_rx, u_ty, u_tx;
+    {
+        const unsigned trem = blockIdx.x - u_rx * tiles_per_rx;
+        u_ty = trem / ntx;
+        u_tx = trem - u_ty * ntx;
+    }
+    const unsigned step_rx = gridDim.x / tiles_per_rx;
+    const unsigned step_rem = gridDim.x - step_rx * tiles_per_rx;
+    const unsigned step_ty = step_rem / ntx, step_tx = step_rem - step_ty * ntx;
+    auto next_tile = [&]() {
+        u_tx += step_tx;
+        unsigned carry = u_tx >= ntx ? 1u : 0u;
+        u_tx -= carry ? ntx : 0u;
+        u_ty += step_ty + carry;
+        carry = u_ty >= nty ? 1u : 0u;
+        u_ty -= carry ? nty : 0u;
+        u_rx += step_rx + carry;
+    };
+    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, next_tile()) {
+        const int irx = (int)u_rx, ty = (int)u_ty, tx = (int)u_tx;
         if (irx != acc_rx) {
             if (acc_rx >= 0) flush_stats(acc_rx);
             acc_rx = irx;
@@ -381,12 +388,10 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
             }
             const unsigned vmask = __ballot_sync(0xffffffffu, valid);
             const unsigned bmask = __ballot_sync(0xffffffffu, bin >= 0);
-            if (lane == 0 && vmask)
-                atomicAdd(&s_valid_binned, (unsigned long long)__popc(vmask) |
-                                               ((unsigned long long)__popc(bmask) << 32));
-#if SOSAT_BIN_SMEM_TILE
-            if (use_win) continue;  // binned below, CTA-wide
-#endif
+            if (lane == 0 && vmask) {
+                s_nvalid[warp] += __popc(vmask);
+                s_nbinned[warp] += __popc(bmask);
+            }
             if (re == nullptr || bmask == 0u) continue;
 
             // ---- run-length aggregation along the lane order --------------------------------
@@ -397,9 +402,6 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
             const unsigned m = ((heads >> lane) >> 1) | (1u << (31 - lane));
             const int rest = __ffs(m) - 1;  // lanes lane+1 .. lane+rest continue this lane's run
             const bool flush = head && bin >= 0;
-#if SOSAT_BIN_SMEM_TILE
-            if (use_win) continue;  // handled below, after the CTA agrees on the window origin
-#endif
             if (flush) atomicAdd(cnt + (long long)irx * plane + bin, (float)(rest + 1));
 
             const double dopl = r.opl - p.opl_ref;
@@ -433,80 +435,6 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
                 }
             }
         }
-#if SOSAT_BIN_SMEM_TILE
-        if (use_win) {
-            static_assert(kNR == 1, "the shared-memory bin window handles one ray per thread");
-            // every thread of the CTA comes through here (no early continue above in this mode)
-            RayResult &r = rr[0];
-            const bool live = tx * kTileW + lth < p.n_scan && iph < p.n_rows;
-            int bin = -1, ix = 0x7fffffff, iz = 0x7fffffff;
-            if (live && r.valid) {
-                const int jx = __double2int_rd((r.ax + p.half_extent) * p.inv_cell);
-                const int jz = __double2int_rd((r.az + p.half_extent) * p.inv_cell);
-                if ((unsigned)jx < (unsigned)p.grid_n && (unsigned)jz < (unsigned)p.grid_n) {
-                    bin = jz * p.grid_n + jx;
-                    ix = jx;
-                    iz = jz;
-                }
-            }
-            const int wx = __reduce_min_sync(0xffffffffu, ix), wz = __reduce_min_sync(0xffffffffu, iz);
-            if (lane == 0 && wx != 0x7fffffff) {
-                atomicMin(&s_win_min[0], wx);
-                atomicMin(&s_win_min[1], wz);
-            }
-            __syncthreads();
-            const int ox = s_win_min[0], oz = s_win_min[1];
-            const int prev = __shfl_up_sync(0xffffffffu, bin, 1);
-            const bool head = lane == 0 || prev != bin;
-            const unsigned heads = __ballot_sync(0xffffffffu, head);
-            const unsigned m = ((heads >> lane) >> 1) | (1u << (31 - lane));
-            const int rest = __ffs(m) - 1;
-            float vre = 0.f, vim = 0.f;
-            if (bin >= 0) {
-                const float a = s_amp[0][0][lth] * s_amp[0][1][lph];
-                double cyc = (r.opl - p.opl_ref) * g_freq.kk[0];
-                cyc -= __dadd_rn(__dadd_rn(cyc, 6755399441055744.0), -6755399441055744.0);
-                float sn, cs;
-                __sincosf(6.2831853071795865f * (float)cyc, &sn, &cs);
-                vre = a * cs;
-                vim = a * sn;
-            }
-#pragma unroll
-            for (int o = 1; o < 32; o <<= 1) {
-                const float ore = __shfl_down_sync(0xffffffffu, vre, o);
-                const float oim = __shfl_down_sync(0xffffffffu, vim, o);
-                if (o <= rest) {
-                    vre += ore;
-                    vim += oim;
-                }
-            }
-            if (head && bin >= 0) {
-                const int dx = ix - ox, dz = iz - oz;
-                if (dx < kWin && dz < kWin) {  // shared-memory atomics into the CTA's window
-                    atomicAdd(&s_win[0][dz * kWin + dx], vre);
-                    atomicAdd(&s_win[1][dz * kWin + dx], vim);
-                    atomicAdd(&s_win[2][dz * kWin + dx], (float)(rest + 1));
-                } else {  // outliers (wild rays) go straight to global memory
-                    atomicAdd(re + (long long)irx * plane + bin, vre);
-                    atomicAdd(im + (long long)irx * plane + bin, vim);
-                    atomicAdd(cnt + (long long)irx * plane + bin, (float)(rest + 1));
-                }
-            }
-            __syncthreads();
-            if (tid < kWin * kWin) {
-                const float c = s_win[2][tid];
-                if (c != 0.f) {
-                    const int gx = ox + (tid & (kWin - 1)), gz = oz + tid / kWin;
-                    const long long g = (long long)irx * plane + (long long)gz * p.grid_n + gx;
-                    atomicAdd(re + g, s_win[0][tid]);
-                    atomicAdd(im + g, s_win[1][tid]);
-                    atomicAdd(cnt + g, c);
-                    s_win[0][tid] = s_win[1][tid] = s_win[2][tid] = 0.f;
-                }
-            }
-            if (tid < 2) s_win_min[tid] = 0x7fffffff;  // ordered by the barrier at the next tile's top
-        }
-#endif
     }
     if (acc_rx >= 0) flush_stats(acc_rx);
 }
