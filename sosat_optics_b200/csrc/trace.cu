@@ -607,8 +607,8 @@ extern "C" int sosat_set_geometry(const sosat_geom_t *h, void *stream) {
         c.t_hi = s.t_hi;
         c.omm2 = 1.0 - c.mu2;
         c.cKh = 0.5 * c.cp * c.Kp;
-        c.a3p12 = 12.0 * c.a3p;
         c.cK = c.Kp != 0.0 ? c.cp / c.Kp : 0.0;
+        c.y0K = c.y0 - c.cK;
         c.refine = fabs(c.cK) > 300.0;
         refine_mask |= c.refine << i;
         edge_mask |= (c.Kp > 0.0) << i;
@@ -618,7 +618,7 @@ extern "C" int sosat_set_geometry(const sosat_geom_t *h, void *stream) {
         f.a3p = (float)c.a3p; f.a1p2 = (float)c.a1p2; f.a2p4 = (float)c.a2p4;
         f.a3p6 = (float)c.a3p6;
         f.cK = (float)c.cK;
-        f.cKh = (float)c.cKh; f.a3p12 = (float)c.a3p12;
+        f.cKh = (float)c.cKh;
     }
     g.y_lyot = h->y_lyot;
     g.y_source = h->y_source;

@@ -46,11 +46,11 @@ struct SurfC {
     int refine;   // |cK| > 300 mm: s needs the fully refined rsqrt in the division-free form
     int pad_;
     double cKh;    // c' K' / 2: d(c'/s)/du = cKh / s^3
-    double a3p12;  // 12 a3'
+    double y0K;    // y0 - cK
 };
 
 struct SurfF {
-    float Kp, cp, a1p, a2p, a3p, a1p2, a2p4, a3p6, cK, cKh, a3p12;
+    float Kp, cp, a1p, a2p, a3p, a1p2, a2p4, a3p6, cK, cKh;
 };
 
 struct GeomC {
@@ -75,8 +75,9 @@ struct GeomC {
 // kappa = |f''/2f'| ~ 1e-3/mm on these surfaces, so a step below this bound leaves <= 1e-9 mm;
 // longer steps send the lane to the adaptive path.  The fp32 root sits at the fp32 floor
 // (steps of 1e-5 .. 3e-4 mm measured), so the bound is not on the hot path of any ray.
-#ifndef SOSAT_LINEAR_MAX_STEP
-#define SOSAT_LINEAR_MAX_STEP 1.0e-3
+// The bound is a power of two so that it can be tested on the exponent field: 2^-10 mm.
+#ifndef SOSAT_LINEAR_MAX_STEP_LOG2
+#define SOSAT_LINEAR_MAX_STEP_LOG2 10
 #endif
 
 enum : unsigned {
@@ -202,7 +203,7 @@ __device__ __forceinline__ void surf_eval(const SurfC &S, const bool refine, dou
                                           double dy, double dz, double y0PyK, double t,
                                           double &f, double &fp, double &X, double &Z,
                                           double &G, double &w, double &u, double &rs,
-                                          double &xd) {
+                                          double &xd, double &h) {
     X = fma(dx, t, Px);
     Z = fma(dz, t, Pz);
     u = fma(X, X, Z * Z);
@@ -221,8 +222,9 @@ __device__ __forceinline__ void surf_eval(const SurfC &S, const bool refine, dou
         }
         f = fma(B, rs, base);  // ... - cK (1 - s)
     }
-    G = fma(S.cp, rs, fma(u, fma(S.a3p6, u, S.a2p4), S.a1p2));  // c'/s + d(poly u)/du * 2
-    xd = fma(X, dx, Z * dz);                                     // (du/dt) / 2
+    h = fma(S.a3p6, u, S.a2p4);
+    G = fma(S.cp, rs, fma(u, h, S.a1p2));  // c'/s + d(poly u)/du * 2
+    xd = fma(X, dx, Z * dz);               // (du/dt) / 2
     fp = fma(-G, xd, -dy);
 }
 template <bool GENERIC>
@@ -230,8 +232,8 @@ __device__ __forceinline__ void surf_eval(const SurfC &S, const bool refine, dou
                                           double dx, double dy, double dz, double y0PyK, double t,
                                           double &f, double &fp, double &X, double &Z, double &G,
                                           double &w) {
-    double u, rs, xd;
-    surf_eval<GENERIC>(S, refine, Px, Pz, dx, dy, dz, y0PyK, t, f, fp, X, Z, G, w, u, rs, xd);
+    double u, rs, xd, h;
+    surf_eval<GENERIC>(S, refine, Px, Pz, dx, dy, dz, y0PyK, t, f, fp, X, Z, G, w, u, rs, xd, h);
 }
 
 // fp32 pre-iterations: same two forms (REFINE surfaces keep the division, where the (1 - s)
@@ -272,10 +274,11 @@ __device__ __forceinline__ float halley_step_f32(const SurfF &S, float Px, float
         f = fmaf(S.cK * w, rs, base);
     else
         f = fmaf(-u, S.cp * rcp_f32(fmaf(w, rs, 1.0f)), base);
-    const float G = fmaf(S.cp, rs, fmaf(u, fmaf(S.a3p6, u, S.a2p4), S.a1p2));
+    const float h = fmaf(S.a3p6, u, S.a2p4);
+    const float G = fmaf(S.cp, rs, fmaf(u, h, S.a1p2));
     const float xd = fmaf(X, dx, Z * dz);
     const float fp = fmaf(-G, xd, -dy);
-    const float dGdu = fmaf(S.cKh * (rs * rs), rs, fmaf(S.a3p12, u, S.a2p4));
+    const float dGdu = fmaf(S.cKh * (rs * rs), rs, fmaf(S.a3p6, u, h));
     const float nfpp = fmaf(G, dd, 2.0f * dGdu * (xd * xd));        // -f''
     // t - 2 f f' / (2 f'^2 - f f'')
     const float den = fmaf(fp + fp, fp, f * nfpp);
@@ -370,22 +373,29 @@ __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, doub
     double opl = 0.0, r2a_sq = 0.0;
     double gx = 0.0, gz = 0.0, L2 = 1.0;
     unsigned flags = 0;
+    int step_hi = 0;
     // N64 == 1: Halley steps in fp32, one fp64 Newton step, slope factor carried to first order
     constexpr bool kLinear = N32 > 0 && N64 == 1 && !ADAPTIVE;
     SOSAT_SURFACE_LOOP_PRAGMA
     for (int si = 0; si < SOSAT_NUM_SURFACES; ++si) {
         const SurfC &S = g.s[si];
-        const double y0Py = S.y0 - Py;
+        // division-free surfaces of the default schedule carry only y0PyK = (y0 - cK) - Py (one
+        // DADD); the others need y0 - Py itself for the fp32 division form
+        const bool lean = kLinear && !GENERIC && !((REFINE_MASK >> si) & 1);
+        const double y0Py = lean ? 0.0 : S.y0 - Py;
+        const double y0PyK = lean ? S.y0K - Py : (GENERIC ? y0Py : y0Py - S.cK);
         double t;
         if (N32 > 0) {
             const SurfF &F = g.f[si];
             const float fPx = d2f_seed(Px), fPz = d2f_seed(Pz), fdx = d2f_seed(dx), fdy = d2f_seed(dy),
-                        fdz = d2f_seed(dz), fy0 = d2f_seed(y0Py);
+                        fdz = d2f_seed(dz);
+            const float fyK = lean ? d2f_seed(y0PyK) : 0.f;
+            const float fy0 = lean ? fyK + F.cK : d2f_seed(y0Py);
             float tf = fy0 * rcp_f32(fdy);  // vertex-plane guess
             if (kLinear) {
                 const float fdd = fmaf(fdx, fdx, fdz * fdz);
                 if (!GENERIC && !((REFINE_MASK >> si) & 1)) {
-                    const float fy0K = fy0 - F.cK;
+                    const float fy0K = lean ? fyK : fy0 - F.cK;
 #pragma unroll
                     for (int it = 0; it < N32 - 1; ++it) {
                         float f, fp;
@@ -423,21 +433,23 @@ __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, doub
             t = y0Py * rcp_half(dy);  // vertex-plane guess
         }
         double X, Z, G, w, step = 0.0;
-        const double y0PyK = GENERIC ? y0Py : y0Py - S.cK;
         if (kLinear) {
             // The fp32 root is converged to the fp32 floor (~1e-4 mm), so one fp64 Newton step
             // lands on the fp64 root and the slope factor and the hit coordinates are carried
             // to the new t to first order instead of by a second evaluation (9 DP instead of
             // 24 + 2 MUFU): dG/dt = dG/du du/dt, dG/du = 4 a2' + 12 a3' u + c'K'/(2 s^3)
-            double f, fp, u, rs, xd;
-            surf_eval<GENERIC>(S, ((REFINE_MASK >> si) & 1) != 0, Px, Pz, dx, dy, dz, y0PyK, t, f, fp, X, Z, G, w, u, rs, xd);
+            double f, fp, u, rs, xd, h;
+            surf_eval<GENERIC>(S, ((REFINE_MASK >> si) & 1) != 0, Px, Pz, dx, dy, dz, y0PyK, t, f, fp, X, Z, G, w, u, rs, xd, h);
             step = f * SOSAT_LINEAR_RCP(fp);  // the seed's 3e-5 relative error stays in t: <= 3e-8 mm
             t -= step;
-            const double dGdu = fma(S.cKh, rs * rs * rs, fma(S.a3p12, u, S.a2p4));
+            // 4 a2' + 12 a3' u = h + 6 a3' u with h = 4 a2' + 6 a3' u from the evaluation of G
+            const double dGdu = fma(S.cKh, rs * rs * rs, fma(S.a3p6, u, h));
             G = fma(dGdu * xd, -2.0 * step, G);
             X = fma(-step, dx, X);
             Z = fma(-step, dz, Z);
-            if (fabs(step) > SOSAT_LINEAR_MAX_STEP) flags |= RAY_UNCONVERGED;  // false for NaN
+            // largest |step| of the ray, tracked on the high word (2 ALU instructions per surface
+            // instead of a DSETP on the fp64 pipe) and tested once after the last surface
+            step_hi = max(step_hi, __double2hiint(step) & 0x7fffffff);
         } else {
 #pragma unroll
             for (int it = 0; it < N64; ++it) {
@@ -472,6 +484,11 @@ __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, doub
         if (si == 3) r2a_sq = fma(Px, Px, Pz * Pz);
         opl = fma(t, S.n_in, opl);  // dist_* = |hit - previous| = t for unit d
         refract(S, X, Z, G, dx, dy, dz, gx, gz, L2);
+    }
+    if (kLinear) {
+        // |step| > MAX on some surface; NaN (exponent all ones) is not "unconverged", as before
+        constexpr int kMaxHi = (int)(0x3ff00000u - ((unsigned)SOSAT_LINEAR_MAX_STEP_LOG2 << 20));
+        if (step_hi >= kMaxHi && step_hi < 0x7ff00000) flags |= RAY_UNCONVERGED;
     }
     unit_normal(gx, gz, L2, r.nx, r.ny, r.nz);
     finish_ray(g, Px, Py, Pz, dx, dy, dz, opl, r2a_sq, r);
