@@ -267,8 +267,23 @@ def run_ours(args):
     # kernel per rank reduces its slab of cells from all peers over NVLink, normalises it and
     # stores it into rank 0's field (csrc/peer.cu); --reduce nccl selects the all-reduce path
     use_peer = world > 1 and args.reduce == "peer"
+    peer_note = None
     if use_peer:
-        peer = sdist.PeerPlanes(1, 1, GRID_N)
+        # all ranks must take the same path: agree on whether the peer mapping worked everywhere
+        peer, err = None, ""
+        try:
+            peer = sdist.PeerPlanes(1, 1, GRID_N)
+        except Exception as exc:  # no P2P between these devices, IPC disabled in the container ...
+            err = repr(exc)
+        ok = torch.tensor([1.0 if peer is not None else 0.0], device="cuda")
+        dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+        if ok.item() < 1.0:
+            if peer is not None:
+                peer.close()
+            use_peer = False
+            peer_note = "peer mapping unavailable on some rank, NCCL all-reduce used instead: " + err
+            print(f"[bench rank {rank}] {peer_note}", file=sys.stderr, flush=True)
+    if use_peer:
         re, im, cnt, stats, planes_flat = peer.re, peer.im, peer.cnt, peer.stats, peer.accum
     else:
         re, im, cnt, planes_flat = sdist.alloc_planes(1, 1, GRID_N)  # one buffer: one collective
@@ -520,7 +535,8 @@ def run_ours(args):
                        "fused reduce over peer-mapped memory: each rank sums its slab of the [re,im,count] "
                        "planes and the 8 fp64 sums from all peers, normalises it and stores it to rank 0, "
                        "which computes the far field" if use_peer else
-                       "one NCCL all-reduce of [re,im,count] planes (50 MB) + 8 fp64 sums"),
+                       "one NCCL all-reduce of [re,im,count] planes (50 MB) + 8 fp64 sums" + (
+                           f" ({peer_note})" if peer_note else "")),
                    "l2": "256 MiB flush write between timed steps; the kernel reads no input arrays",
                    "newton_schedule": os.environ.get("SOSAT_TRACE_VARIANT", "default (fp32 Newton + Halley step, 1 fp64 Newton step, first-order slope update; long steps re-traced adaptively)")},
         "clocks": clocks,

@@ -127,7 +127,6 @@ class PeerPlanes:
         import ctypes
         import torch
         from . import _lib
-        dist = _dist()
         self.lib = _lib.require_gpu()
         self.group = group
         self.rank, self.world = world_info(group)
@@ -135,9 +134,33 @@ class PeerPlanes:
             raise ValueError("PeerPlanes supports at most 16 ranks (one node)")
         self.shape = (n_rx, n_freq, grid_n)
         self.layout = L = peer_layout(n_rx, n_freq, grid_n)
-        base = ctypes.c_void_p()
-        _lib.check(self.lib.sosat_peer_alloc(L["bytes"], ctypes.byref(base)))
-        self.base = base.value
+        # Every step that can fail locally (allocation, export, mapping a peer) is followed by
+        # an exchange of the outcome, so that all ranks raise together instead of one rank
+        # raising while the others wait in a collective.
+        self.base, self._opened, self.peer_base = 0, [], []
+        err, handle = None, (ctypes.c_ubyte * 64)()
+        try:
+            base = ctypes.c_void_p()
+            _lib.check(self.lib.sosat_peer_alloc(L["bytes"], ctypes.byref(base)))
+            self.base = base.value
+            _lib.check(self.lib.sosat_peer_export(ctypes.c_void_p(self.base), handle))
+        except Exception as exc:  # noqa: BLE001 - reported to every rank below
+            err = repr(exc)
+        handles = self._exchange(None if err else bytes(handle))
+        self._raise_together(err, [h is None for h in handles], "allocating / exporting")
+        try:
+            for r, h in enumerate(handles):
+                if r == self.rank:
+                    self.peer_base.append(self.base)
+                    continue
+                ptr = ctypes.c_void_p()
+                buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                _lib.check(self.lib.sosat_peer_open(buf, ctypes.byref(ptr)))
+                self.peer_base.append(ptr.value)
+                self._opened.append(ptr.value)
+        except Exception as exc:  # noqa: BLE001
+            err = repr(exc)
+        self._raise_together(err, [f is not None for f in self._exchange(err)], "mapping a peer of")
         self._raw = _RawDeviceBuffer(self.base, L["bytes"])
         self.flat = torch.as_tensor(self._raw, device="cuda")
         n_ri, n_c = n_rx * n_freq * grid_n * grid_n, n_rx * grid_n * grid_n
@@ -154,26 +177,21 @@ class PeerPlanes:
             view("field", 8 * n_ri, torch.float32, (n_rx, n_freq, grid_n, grid_n, 2)))
         self.accum = self.flat[:L["accum_bytes"]]
         self._flag = torch.zeros(1, dtype=torch.float32, device="cuda")
-        # exchange the IPC handles and map the peers
-        handle = (ctypes.c_ubyte * 64)()
-        _lib.check(self.lib.sosat_peer_export(ctypes.c_void_p(self.base), handle))
-        handles = [None] * self.world
-        if self.world > 1:
-            dist.all_gather_object(handles, bytes(handle), group=group)
-        else:
-            handles[0] = bytes(handle)
-        self.peer_base: List[int] = []
-        self._opened: List[int] = []
-        for r, h in enumerate(handles):
-            if r == self.rank:
-                self.peer_base.append(self.base)
-                continue
-            ptr = ctypes.c_void_p()
-            buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
-            _lib.check(self.lib.sosat_peer_open(buf, ctypes.byref(ptr)))
-            self.peer_base.append(ptr.value)
-            self._opened.append(ptr.value)
         self._c_peers = (ctypes.c_void_p * self.world)(*self.peer_base)
+
+    def _exchange(self, obj):
+        if self.world == 1:
+            return [obj]
+        out = [None] * self.world
+        _dist().all_gather_object(out, obj, group=self.group)
+        return out
+
+    def _raise_together(self, err, failed, what):
+        if any(failed):
+            self.close()
+            bad = [r for r, f in enumerate(failed) if f]
+            raise RuntimeError(f"PeerPlanes: {what} the accumulator buffer failed on rank(s) {bad}"
+                               + (f": {err}" if err else ""))
 
     def zero(self):
         """Zero the accumulators (planes and statistics) for the next step."""
@@ -217,7 +235,8 @@ class PeerPlanes:
         self._opened = []
         if self.base:
             for name in ("re", "im", "cnt", "stats", "stats_sum", "field", "accum", "flat", "_raw"):
-                setattr(self, name, None)
+                if hasattr(self, name):
+                    setattr(self, name, None)
             _lib.check(self.lib.sosat_peer_free(ctypes.c_void_p(self.base)))
             self.base = 0
 
