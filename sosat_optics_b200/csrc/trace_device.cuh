@@ -248,12 +248,13 @@ __device__ __forceinline__ void surf_eval_f32(const SurfF &S, float Px, float Pz
     const float w = fmaf(-S.Kp, u, 1.0f);
     const float rs = rsqrt_f32(w);
     const float poly = fmaf(fmaf(S.a3p, u, S.a2p), u, S.a1p);
+    const float Gp = fmaf(u, fmaf(S.a3p6, u, S.a2p4), S.a1p2);
     const float base = fmaf(-u, poly, fmaf(-dy, t, y0PyK));
     if (DIVFREE)
         f = fmaf(S.cK * w, rs, base);
     else
         f = fmaf(-u, S.cp * rcp_f32(fmaf(w, rs, 1.0f)), base);
-    const float G = fmaf(S.cp, rs, fmaf(u, fmaf(S.a3p6, u, S.a2p4), S.a1p2));
+    const float G = fmaf(S.cp, rs, Gp);
     fp = fmaf(-G, fmaf(X, dx, Z * dz), -dy);
 }
 // The same with the second derivative along the ray, for Halley steps (cubic convergence, no
@@ -268,14 +269,15 @@ __device__ __forceinline__ float halley_step_f32(const SurfF &S, float Px, float
     const float w = fmaf(-S.Kp, u, 1.0f);
     const float rs = rsqrt_f32(w);
     const float poly = fmaf(fmaf(S.a3p, u, S.a2p), u, S.a1p);
+    const float h = fmaf(S.a3p6, u, S.a2p4);
+    const float Gp = fmaf(u, h, S.a1p2);
     const float base = fmaf(-u, poly, fmaf(-dy, t, y0PyK));
     float f;
     if (DIVFREE)
         f = fmaf(S.cK * w, rs, base);
     else
         f = fmaf(-u, S.cp * rcp_f32(fmaf(w, rs, 1.0f)), base);
-    const float h = fmaf(S.a3p6, u, S.a2p4);
-    const float G = fmaf(S.cp, rs, fmaf(u, h, S.a1p2));
+    const float G = fmaf(S.cp, rs, Gp);
     const float xd = fmaf(X, dx, Z * dz);
     const float fp = fmaf(-G, xd, -dy);
     const float dGdu = fmaf(S.cKh * (rs * rs), rs, fmaf(S.a3p6, u, h));
