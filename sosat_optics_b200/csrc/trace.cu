@@ -330,14 +330,26 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
         const int iph = ty * kTileH + lph;  // relative to row_begin
         const double *rx = s_rx;  // feed position [mm], staged with the tables
         RayResult rr[kNR];
-#pragma unroll
-        for (int q = 0; q < kNR; ++q) {
-            // lanes past the edge of the launch grid trace the clamped (edge) ray so that whole
-            // warps stay converged; their result is dropped
-            const double sth = s_sin[0][lth + kTile * q], cth = s_cos[0][lth + kTile * q];
+        if (kNR == 2) {
+            // two rays 16 launch columns apart, skewed by half a surface (trace_ray_newton_pair)
             const double sph = s_sin[1][lph], cph = s_cos[1][lph];
-            trace_ray_newton<N32, N64, GeoBuild<GEO>::generic, GeoBuild<GEO>::mask, GeoBuild<GEO>::edge,
-                             false>(g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph, cth, rr[q]);
+            const double st0 = s_sin[0][lth], ct0 = s_cos[0][lth];
+            const double st1 = s_sin[0][lth + kTile], ct1 = s_cos[0][lth + kTile];
+            trace_ray_newton_pair<N32, N64, GeoBuild<GEO>::generic, GeoBuild<GEO>::mask,
+                                  GeoBuild<GEO>::edge, false>(
+                g_geom, rx[0], rx[1], rx[2], st0 * cph, st0 * sph, ct0, st1 * cph, st1 * sph, ct1,
+                rr[0], rr[kNR - 1]);
+        } else {
+#pragma unroll
+            for (int q = 0; q < kNR; ++q) {
+                // lanes past the edge of the launch grid trace the clamped (edge) ray so that
+                // whole warps stay converged; their result is dropped
+                const double sth = s_sin[0][lth + kTile * q], cth = s_cos[0][lth + kTile * q];
+                const double sph = s_sin[1][lph], cph = s_cos[1][lph];
+                trace_ray_newton<N32, N64, GeoBuild<GEO>::generic, GeoBuild<GEO>::mask,
+                                 GeoBuild<GEO>::edge, false>(g_geom, rx[0], rx[1], rx[2], sth * cph,
+                                                             sth * sph, cth, rr[q]);
+            }
         }
 #pragma unroll
         for (int q = 0; q < kNR; ++q) {

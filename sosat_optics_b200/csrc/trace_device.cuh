@@ -368,137 +368,205 @@ __device__ __forceinline__ void finish_ray(const GeomC &g, double Px, double Py,
 // (out of line: essentially never taken for the boresight bundle, so the refinement loops
 // stay out of the hot instruction stream).  ADAPTIVE = true: up to SOSAT_NEWTON_EXTRA more
 // fp64 steps per surface; a lane still above TOL (or NaN) is marked for the bracketed solve.
-template <int N32, int N64, bool GENERIC, int REFINE_MASK, int EDGE_MASK, bool ADAPTIVE>
-__device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, double Py,
-                                                 double Pz, double dx, double dy, double dz,
-                                                 RayResult &r) {
-    double opl = 0.0, r2a_sq = 0.0;
-    double gx = 0.0, gz = 0.0, L2 = 1.0;
-    unsigned flags = 0;
-    int step_hi = 0;
-    // N64 == 1: Halley steps in fp32, one fp64 Newton step, slope factor carried to first order
+// State of one ray between surfaces.
+struct RayState {
+    double Px, Py, Pz, dx, dy, dz;  // last hit point (or the feed) and direction
+    double opl, r2a_sq;             // optical path so far; x^2 + z^2 at lens 2a (stop clip)
+    double gx, gz, L2;              // unnormalised normal of the last surface
+    unsigned flags;
+    int step_hi;                    // high word of the largest |fp64 step| (N64 == 1 schedule)
+};
+__device__ __forceinline__ void ray_start(RayState &R, double Px, double Py, double Pz, double dx,
+                                          double dy, double dz) {
+    R.Px = Px; R.Py = Py; R.Pz = Pz;
+    R.dx = dx; R.dy = dy; R.dz = dz;
+    R.opl = 0.0; R.r2a_sq = 0.0;
+    R.gx = 0.0; R.gz = 0.0; R.L2 = 1.0;
+    R.flags = 0u;
+    R.step_hi = 0;
+}
+
+#define SOSAT_SCHED_TPL \
+    template <int N32, int N64, bool GENERIC, int REFINE_MASK, int EDGE_MASK, bool ADAPTIVE>
+#define SOSAT_SCHED_ARGS N32, N64, GENERIC, REFINE_MASK, EDGE_MASK, ADAPTIVE
+
+// y0 - Py (for the fp32 division form and the vertex-plane guess) and y0 - cK - Py.  The
+// division-free surfaces of the default schedule ("lean") carry only the latter: one DADD.
+SOSAT_SCHED_TPL __device__ __forceinline__ void surface_offsets(const GeomC &g, const int si,
+                                                                const RayState &R, double &y0Py,
+                                                                double &y0PyK) {
     constexpr bool kLinear = N32 > 0 && N64 == 1 && !ADAPTIVE;
-    SOSAT_SURFACE_LOOP_PRAGMA
-    for (int si = 0; si < SOSAT_NUM_SURFACES; ++si) {
-        const SurfC &S = g.s[si];
-        // division-free surfaces of the default schedule carry only y0PyK = (y0 - cK) - Py (one
-        // DADD); the others need y0 - Py itself for the fp32 division form
-        const bool lean = kLinear && !GENERIC && !((REFINE_MASK >> si) & 1);
-        const double y0Py = lean ? 0.0 : S.y0 - Py;
-        const double y0PyK = lean ? S.y0K - Py : (GENERIC ? y0Py : y0Py - S.cK);
-        double t;
-        if (N32 > 0) {
-            const SurfF &F = g.f[si];
-            const float fPx = d2f_seed(Px), fPz = d2f_seed(Pz), fdx = d2f_seed(dx), fdy = d2f_seed(dy),
-                        fdz = d2f_seed(dz);
-            const float fyK = lean ? d2f_seed(y0PyK) : 0.f;
-            const float fy0 = lean ? fyK + F.cK : d2f_seed(y0Py);
-            float tf = fy0 * rcp_f32(fdy);  // vertex-plane guess
-            if (kLinear) {
-                const float fdd = fmaf(fdx, fdx, fdz * fdz);
-                if (!GENERIC && !((REFINE_MASK >> si) & 1)) {
-                    const float fy0K = lean ? fyK : fy0 - F.cK;
+    const SurfC &S = g.s[si];
+    const bool lean = kLinear && !GENERIC && !((REFINE_MASK >> si) & 1);
+    y0Py = lean ? 0.0 : S.y0 - R.Py;
+    y0PyK = lean ? S.y0K - R.Py : (GENERIC ? y0Py : y0Py - S.cK);
+}
+
+// Stage 1 of a surface: the root parameter t from the fp32 steps (or the vertex-plane guess).
+SOSAT_SCHED_TPL __device__ __forceinline__ double surface_seed(const GeomC &g, const int si,
+                                                               const RayState &R) {
+    // N64 == 1: Newton + Halley in fp32, one fp64 Newton step, slope factor carried to first order
+    constexpr bool kLinear = N32 > 0 && N64 == 1 && !ADAPTIVE;
+    const bool lean = kLinear && !GENERIC && !((REFINE_MASK >> si) & 1);
+    double y0Py, y0PyK;
+    surface_offsets<SOSAT_SCHED_ARGS>(g, si, R, y0Py, y0PyK);
+    if (N32 == 0) return y0Py * rcp_half(R.dy);  // vertex-plane guess
+    const SurfF &F = g.f[si];
+    const float fPx = d2f_seed(R.Px), fPz = d2f_seed(R.Pz), fdx = d2f_seed(R.dx),
+                fdy = d2f_seed(R.dy), fdz = d2f_seed(R.dz);
+    const float fyK = lean ? d2f_seed(y0PyK) : 0.f;
+    const float fy0 = lean ? fyK + F.cK : d2f_seed(y0Py);
+    float tf = fy0 * rcp_f32(fdy);  // vertex-plane guess
+    if (kLinear) {
+        const float fdd = fmaf(fdx, fdx, fdz * fdz);
+        if (!GENERIC && !((REFINE_MASK >> si) & 1)) {
+            const float fy0K = lean ? fyK : fy0 - F.cK;
 #pragma unroll
-                    for (int it = 0; it < N32 - 1; ++it) {
-                        float f, fp;
-                        surf_eval_f32<true>(F, fPx, fPz, fdx, fdy, fdz, fy0K, tf, f, fp);
-                        tf = fmaf(-f, rcp_f32(fp), tf);
-                    }
-                    tf = halley_step_f32<true>(F, fPx, fPz, fdx, fdy, fdz, fdd, fy0K, tf);
-                } else {
-#pragma unroll
-                    for (int it = 0; it < N32 - 1; ++it) {
-                        float f, fp;
-                        surf_eval_f32<false>(F, fPx, fPz, fdx, fdy, fdz, fy0, tf, f, fp);
-                        tf = fmaf(-f, rcp_f32(fp), tf);
-                    }
-                    tf = halley_step_f32<false>(F, fPx, fPz, fdx, fdy, fdz, fdd, fy0, tf);
-                }
-            } else if (!GENERIC && !((REFINE_MASK >> si) & 1)) {
-                const float fy0K = fy0 - F.cK;
-#pragma unroll
-                for (int it = 0; it < N32; ++it) {
-                    float f, fp;
-                    surf_eval_f32<true>(F, fPx, fPz, fdx, fdy, fdz, fy0K, tf, f, fp);
-                    tf = fmaf(-f, rcp_f32(fp), tf);
-                }
-            } else {
-#pragma unroll
-                for (int it = 0; it < N32; ++it) {
-                    float f, fp;
-                    surf_eval_f32<false>(F, fPx, fPz, fdx, fdy, fdz, fy0, tf, f, fp);
-                    tf = fmaf(-f, rcp_f32(fp), tf);
-                }
+            for (int it = 0; it < N32 - 1; ++it) {
+                float f, fp;
+                surf_eval_f32<true>(F, fPx, fPz, fdx, fdy, fdz, fy0K, tf, f, fp);
+                tf = fmaf(-f, rcp_f32(fp), tf);
             }
-            t = f2d_seed(tf);
-        } else {
-            t = y0Py * rcp_half(dy);  // vertex-plane guess
-        }
-        double X, Z, G, w, step = 0.0;
-        if (kLinear) {
-            // The fp32 root is converged to the fp32 floor (~1e-4 mm), so one fp64 Newton step
-            // lands on the fp64 root and the slope factor and the hit coordinates are carried
-            // to the new t to first order instead of by a second evaluation (9 DP instead of
-            // 24 + 2 MUFU): dG/dt = dG/du du/dt, dG/du = 4 a2' + 12 a3' u + c'K'/(2 s^3)
-            double f, fp, u, rs, xd, h;
-            surf_eval<GENERIC>(S, ((REFINE_MASK >> si) & 1) != 0, Px, Pz, dx, dy, dz, y0PyK, t, f, fp, X, Z, G, w, u, rs, xd, h);
-            step = f * SOSAT_LINEAR_RCP(fp);  // the seed's 3e-5 relative error stays in t: <= 3e-8 mm
-            t -= step;
-            // 4 a2' + 12 a3' u = h + 6 a3' u with h = 4 a2' + 6 a3' u from the evaluation of G
-            const double dGdu = fma(S.cKh, rs * rs * rs, fma(S.a3p6, u, h));
-            G = fma(dGdu * xd, -2.0 * step, G);
-            X = fma(-step, dx, X);
-            Z = fma(-step, dz, Z);
-            // largest |step| of the ray, tracked on the high word (2 ALU instructions per surface
-            // instead of a DSETP on the fp64 pipe) and tested once after the last surface
-            step_hi = max(step_hi, __double2hiint(step) & 0x7fffffff);
+            tf = halley_step_f32<true>(F, fPx, fPz, fdx, fdy, fdz, fdd, fy0K, tf);
         } else {
 #pragma unroll
-            for (int it = 0; it < N64; ++it) {
-                double f, fp;
-                surf_eval<GENERIC>(S, ((REFINE_MASK >> si) & 1) != 0, Px, Pz, dx, dy, dz, y0PyK, t, f, fp, X, Z, G, w);
-                step = f * rcp_seed(fp);
-                t -= step;
+            for (int it = 0; it < N32 - 1; ++it) {
+                float f, fp;
+                surf_eval_f32<false>(F, fPx, fPz, fdx, fdy, fdz, fy0, tf, f, fp);
+                tf = fmaf(-f, rcp_f32(fp), tf);
             }
+            tf = halley_step_f32<false>(F, fPx, fPz, fdx, fdy, fdz, fdd, fy0, tf);
         }
-        if (ADAPTIVE) {
-#pragma unroll 1
-            for (int extra = 0; extra < SOSAT_NEWTON_EXTRA && fabs(step) > SOSAT_NEWTON_REFINE;
-                 ++extra) {
-                double f, fp;
-                surf_eval<GENERIC>(S, ((REFINE_MASK >> si) & 1) != 0, Px, Pz, dx, dy, dz, y0PyK, t, f, fp, X, Z, G, w);
-                step = f * rcp_seed(fp);
-                t -= step;
-            }
-            if (!(fabs(step) <= SOSAT_NEWTON_TOL)) flags |= RAY_FLAGGED;
-        } else if (!kLinear) {
-            if (fabs(step) > SOSAT_NEWTON_REFINE) flags |= RAY_UNCONVERGED;  // false for NaN
+    } else if (!GENERIC && !((REFINE_MASK >> si) & 1)) {
+        const float fy0K = fy0 - F.cK;
+#pragma unroll
+        for (int it = 0; it < N32; ++it) {
+            float f, fp;
+            surf_eval_f32<true>(F, fPx, fPz, fdx, fdy, fdz, fy0K, tf, f, fp);
+            tf = fmaf(-f, rcp_f32(fp), tf);
         }
-        if (((EDGE_MASK >> si) & 1) && (EDGE_MASK == 0x10 || S.Kp > 0.0) && !(w >= SOSAT_EDGE_W))
-            flags |= RAY_FLAGGED;
-        // hit point (ray_trace.py:1133-1136 and equivalents)
-        Px = fma(dx, t, Px);
-        Py = fma(dy, t, Py);
-        Pz = fma(dz, t, Pz);
-        // lens-3 clip (ray_trace.py:1138-1140): the reference skips the ray; here the lane keeps
-        // tracing so that the warp stays converged, and the result is discarded at the end
-        if (si == 0 && fma(Px, Px, Pz * Pz) >= g.clip_l3_sq) flags |= RAY_CLIPPED_L3;
-        if (si == 3) r2a_sq = fma(Px, Px, Pz * Pz);
-        opl = fma(t, S.n_in, opl);  // dist_* = |hit - previous| = t for unit d
-        refract(S, X, Z, G, dx, dy, dz, gx, gz, L2);
+    } else {
+#pragma unroll
+        for (int it = 0; it < N32; ++it) {
+            float f, fp;
+            surf_eval_f32<false>(F, fPx, fPz, fdx, fdy, fdz, fy0, tf, f, fp);
+            tf = fmaf(-f, rcp_f32(fp), tf);
+        }
     }
+    return f2d_seed(tf);
+}
+
+// Stage 2 of a surface: fp64 step(s) from the seed, hit point, OPL, refraction.
+SOSAT_SCHED_TPL __device__ __forceinline__ void surface_hit(const GeomC &g, const int si,
+                                                            RayState &R, double t) {
+    constexpr bool kLinear = N32 > 0 && N64 == 1 && !ADAPTIVE;
+    const SurfC &S = g.s[si];
+    const bool refine = ((REFINE_MASK >> si) & 1) != 0;
+    double y0Py, y0PyK;
+    surface_offsets<SOSAT_SCHED_ARGS>(g, si, R, y0Py, y0PyK);
+    double X, Z, G, w, step = 0.0;
+    if (kLinear) {
+        // The fp32 root is converged to the fp32 floor (~1e-4 mm), so one fp64 Newton step
+        // lands on the fp64 root and the slope factor and the hit coordinates are carried
+        // to the new t to first order instead of by a second evaluation (9 DP instead of
+        // 24 + 2 MUFU): dG/dt = dG/du du/dt, dG/du = 4 a2' + 12 a3' u + c'K'/(2 s^3)
+        double f, fp, u, rs, xd, h;
+        surf_eval<GENERIC>(S, refine, R.Px, R.Pz, R.dx, R.dy, R.dz, y0PyK, t, f, fp, X, Z, G, w, u, rs, xd, h);
+        step = f * SOSAT_LINEAR_RCP(fp);  // the seed's 3e-5 relative error stays in t: <= 3e-8 mm
+        t -= step;
+        // 4 a2' + 12 a3' u = h + 6 a3' u with h = 4 a2' + 6 a3' u from the evaluation of G
+        const double dGdu = fma(S.cKh, rs * rs * rs, fma(S.a3p6, u, h));
+        G = fma(dGdu * xd, -2.0 * step, G);
+        X = fma(-step, R.dx, X);
+        Z = fma(-step, R.dz, Z);
+        // largest |step| of the ray, tracked on the high word (2 ALU instructions per surface
+        // instead of a DSETP on the fp64 pipe) and tested once after the last surface
+        R.step_hi = max(R.step_hi, __double2hiint(step) & 0x7fffffff);
+    } else {
+#pragma unroll
+        for (int it = 0; it < N64; ++it) {
+            double f, fp;
+            surf_eval<GENERIC>(S, refine, R.Px, R.Pz, R.dx, R.dy, R.dz, y0PyK, t, f, fp, X, Z, G, w);
+            step = f * rcp_seed(fp);
+            t -= step;
+        }
+    }
+    if (ADAPTIVE) {
+#pragma unroll 1
+        for (int extra = 0; extra < SOSAT_NEWTON_EXTRA && fabs(step) > SOSAT_NEWTON_REFINE;
+             ++extra) {
+            double f, fp;
+            surf_eval<GENERIC>(S, refine, R.Px, R.Pz, R.dx, R.dy, R.dz, y0PyK, t, f, fp, X, Z, G, w);
+            step = f * rcp_seed(fp);
+            t -= step;
+        }
+        if (!(fabs(step) <= SOSAT_NEWTON_TOL)) R.flags |= RAY_FLAGGED;
+    } else if (!kLinear) {
+        if (fabs(step) > SOSAT_NEWTON_REFINE) R.flags |= RAY_UNCONVERGED;  // false for NaN
+    }
+    if (((EDGE_MASK >> si) & 1) && (EDGE_MASK == 0x10 || S.Kp > 0.0) && !(w >= SOSAT_EDGE_W))
+        R.flags |= RAY_FLAGGED;
+    // hit point (ray_trace.py:1133-1136 and equivalents)
+    R.Px = fma(R.dx, t, R.Px);
+    R.Py = fma(R.dy, t, R.Py);
+    R.Pz = fma(R.dz, t, R.Pz);
+    // lens-3 clip (ray_trace.py:1138-1140): the reference skips the ray; here the lane keeps
+    // tracing so that the warp stays converged, and the result is discarded at the end
+    if (si == 0 && fma(R.Px, R.Px, R.Pz * R.Pz) >= g.clip_l3_sq) R.flags |= RAY_CLIPPED_L3;
+    if (si == 3) R.r2a_sq = fma(R.Px, R.Px, R.Pz * R.Pz);
+    R.opl = fma(t, S.n_in, R.opl);  // dist_* = |hit - previous| = t for unit d
+    refract(S, X, Z, G, R.dx, R.dy, R.dz, R.gx, R.gz, R.L2);
+}
+
+SOSAT_SCHED_TPL __device__ __forceinline__ void ray_finish(const GeomC &g, RayState &R,
+                                                           RayResult &r) {
+    constexpr bool kLinear = N32 > 0 && N64 == 1 && !ADAPTIVE;
     if (kLinear) {
         // |step| > MAX on some surface; NaN (exponent all ones) is not "unconverged", as before
         constexpr int kMaxHi = (int)(0x3ff00000u - ((unsigned)SOSAT_LINEAR_MAX_STEP_LOG2 << 20));
-        if (step_hi >= kMaxHi && step_hi < 0x7ff00000) flags |= RAY_UNCONVERGED;
+        if (R.step_hi >= kMaxHi && R.step_hi < 0x7ff00000) R.flags |= RAY_UNCONVERGED;
     }
-    unit_normal(gx, gz, L2, r.nx, r.ny, r.nz);
-    finish_ray(g, Px, Py, Pz, dx, dy, dz, opl, r2a_sq, r);
-    r.flags = flags;
-    if (flags & RAY_CLIPPED_L3) {
+    unit_normal(R.gx, R.gz, R.L2, r.nx, r.ny, r.nz);
+    finish_ray(g, R.Px, R.Py, R.Pz, R.dx, R.dy, R.dz, R.opl, R.r2a_sq, r);
+    r.flags = R.flags;
+    if (R.flags & RAY_CLIPPED_L3) {
         r.flags = RAY_CLIPPED_L3;
         r.valid = false;
     }
+}
+
+SOSAT_SCHED_TPL __device__ __forceinline__ void trace_ray_newton(const GeomC &g, double Px, double Py,
+                                                                 double Pz, double dx, double dy,
+                                                                 double dz, RayResult &r) {
+    RayState R;
+    ray_start(R, Px, Py, Pz, dx, dy, dz);
+    SOSAT_SURFACE_LOOP_PRAGMA
+    for (int si = 0; si < SOSAT_NUM_SURFACES; ++si) {
+        const double t = surface_seed<SOSAT_SCHED_ARGS>(g, si, R);
+        surface_hit<SOSAT_SCHED_ARGS>(g, si, R, t);
+    }
+    ray_finish<SOSAT_SCHED_ARGS>(g, R, r);
+}
+
+// Two rays of one thread, skewed by half a surface: the fp32 steps of one ray are issued next
+// to the fp64 step of the other (independent streams in ONE warp; a half-rate DFMA hides one
+// full-rate instruction of the same warp).
+SOSAT_SCHED_TPL __device__ __forceinline__ void trace_ray_newton_pair(
+    const GeomC &g, double Px, double Py, double Pz, double dxa, double dya, double dza,
+    double dxb, double dyb, double dzb, RayResult &ra, RayResult &rb) {
+    RayState A, B;
+    ray_start(A, Px, Py, Pz, dxa, dya, dza);
+    ray_start(B, Px, Py, Pz, dxb, dyb, dzb);
+    double ta = surface_seed<SOSAT_SCHED_ARGS>(g, 0, A);
+#pragma unroll
+    for (int si = 0; si < SOSAT_NUM_SURFACES; ++si) {
+        const double tb = surface_seed<SOSAT_SCHED_ARGS>(g, si, B);  // next to A's fp64 step
+        surface_hit<SOSAT_SCHED_ARGS>(g, si, A, ta);
+        if (si + 1 < SOSAT_NUM_SURFACES) ta = surface_seed<SOSAT_SCHED_ARGS>(g, si + 1, A);  // next to B's
+        surface_hit<SOSAT_SCHED_ARGS>(g, si, B, tb);
+    }
+    ray_finish<SOSAT_SCHED_ARGS>(g, A, ra);
+    ray_finish<SOSAT_SCHED_ARGS>(g, B, rb);
 }
 
 // ---- slow path: the reference's bracketed solve ---------------------------------------------
