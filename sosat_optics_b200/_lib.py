@@ -135,3 +135,23 @@ def require_gpu():
         raise SosatError("no CUDA device visible: sosat_optics_b200 runs only on the GPU "
                          "(there is deliberately no CPU fallback)")
     return lib
+
+
+PINNED_LIMIT_BYTES = 1 << 30
+
+
+def to_numpy(t):
+    """Device tensor -> numpy array through PINNED host memory (one DMA at PCIe speed, no
+    pageable staging and no page faults on a fresh allocation; torch's caching host allocator
+    recycles the block when the array is dropped).  The array is a view of the pinned tensor,
+    which it keeps alive.  Results above PINNED_LIMIT_BYTES take the ordinary pageable copy."""
+    import torch
+    if t.device.type != "cuda":
+        return t.numpy()
+    nbytes = t.numel() * t.element_size()
+    if nbytes == 0 or nbytes > PINNED_LIMIT_BYTES:
+        return t.cpu().numpy()
+    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    h.copy_(t, non_blocking=True)
+    torch.cuda.current_stream().synchronize()
+    return h.numpy()

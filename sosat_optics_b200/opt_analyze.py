@@ -150,7 +150,7 @@ def _amp_phase_transform(fn_name, amp, phase_deg, kind):
     _lib.check(fn(ctypes.c_void_p(d_a.data_ptr()), ctypes.c_void_p(d_p.data_ptr()), n,
                   ctypes.c_void_p(field.data_ptr()), ctypes.c_void_p(phase.data_ptr()),
                   ctypes.c_void_p(ws.data_ptr()), ws.numel(), _stream(torch)))
-    return torch.view_as_complex(field).cpu().numpy(), phase.cpu().numpy()
+    return _lib.to_numpy(torch.view_as_complex(field)), _lib.to_numpy(phase)
 
 
 def b2a(beam, phase):
@@ -211,7 +211,7 @@ def beam_convolve(x, y, beam, apert1, apert2, plots=0):
                               ctypes.c_void_p(disc_fft.data_ptr()), n * n,
                               ctypes.c_void_p(conv.data_ptr()), _stream(torch)))
     final = _dft_kind(lib, torch, conv, _lib.DFT_INVERSE)
-    return x, y, final.cpu().numpy().astype(np.complex128) * (scale * peak)
+    return x, y, _lib.to_numpy(final).astype(np.complex128) * (scale * peak)
 
 
 def far_field(b, dx_cm=None, lam_m=None, theta_x=None, theta_y=None, *, device: bool = False):
@@ -252,13 +252,13 @@ def far_field(b, dx_cm=None, lam_m=None, theta_x=None, theta_y=None, *, device: 
                                        dp(tx), 1.0 / float(lam_m), ctypes.c_void_p(ws.data_ptr()),
                                        ws.numel(), _stream(torch)))
         torch.cuda.current_stream().synchronize()  # the host arrays above are read asynchronously
-        return out if device else out.cpu().numpy()
+        return out if device else _lib.to_numpy(out)
     out = torch.empty((n, n), dtype=torch.complex64, device="cuda")
     ws = _workspace(lib, torch, n)
     _lib.check(lib.sosat_dft2_gemm(ctypes.c_void_p(d_b.data_ptr()), n,
                                    ctypes.c_void_p(out.data_ptr()),
                                    ctypes.c_void_p(ws.data_ptr()), ws.numel(), _stream(torch)))
-    res = out if device else out.cpu().numpy()
+    res = out if device else _lib.to_numpy(out)
     if dx_cm is not None and lam_m is not None:
         return res, far_field_angles(n, float(dx_cm) / 100.0, float(lam_m))
     return res
@@ -284,7 +284,7 @@ def far_field_batch(b, *, device: bool = False):
     k, n = int(d_b.shape[0]), int(d_b.shape[1])
     out = torch.empty((k, n, n), dtype=torch.complex64, device="cuda")
     if k == 0:
-        return out if device else out.cpu().numpy()
+        return out if device else _lib.to_numpy(out)
     key = (torch.cuda.current_device(), n, k)
     ws = _batch_workspaces.get(key)
     if ws is None:
@@ -298,7 +298,7 @@ def far_field_batch(b, *, device: bool = False):
     _lib.check(lib.sosat_dft2_gemm_batch(ctypes.c_void_p(d_b.data_ptr()), n, k,
                                          ctypes.c_void_p(out.data_ptr()), _lib.DFT_FORWARD,
                                          ctypes.c_void_p(ws.data_ptr()), ws.numel(), _stream(torch)))
-    return out if device else out.cpu().numpy()
+    return out if device else _lib.to_numpy(out)
 
 
 def far_field_angles(n: int, dx_m: float, lam_m: float):
@@ -347,5 +347,5 @@ def far_field_irregular(x, y, b, theta_x, theta_y, lam):
                                       ctypes.c_void_p(d_th.data_ptr()), th.shape[0],
                                       1.0 / float(lam), ctypes.c_void_p(out.data_ptr()),
                                       _stream(torch)))
-    res = out.cpu().numpy()
+    res = _lib.to_numpy(out)
     return (res[:, 0] + 1j * res[:, 1]).reshape(tx.shape)

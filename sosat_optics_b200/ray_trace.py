@@ -91,7 +91,7 @@ def _trace_device(P_rx, tele_geo, ray_begin=0, ray_end=None):
         rx.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.byref(freq), n_scan,
         ray_begin, ray_end, ctypes.c_void_p(out.data_ptr()), ctypes.c_void_p(stats.data_ptr()),
         _stream(torch)))
-    h_stats = stats.cpu().numpy()
+    h_stats = _lib.to_numpy(stats)
     if h_stats[_lib.STAT_N_BRACKET_FAIL] > 0:
         # scipy.optimize.brentq's error, which aborts the reference's whole run
         raise ValueError("f(a) and f(b) must have different signs")
@@ -104,7 +104,7 @@ def rx_to_lyot(P_rx, tele_geo, plot=False, col="b"):
     rows 0-2 position on the source plane, 3 optical path length, 4 amplitude, 5-7 last surface
     normal, 8-10 exit direction, 11-16 zero."""
     out, _ = _trace_device(P_rx, tele_geo)
-    return out.cpu().numpy()
+    return _lib.to_numpy(out)
 
 
 class SimOutput:
@@ -134,9 +134,9 @@ def getNearField(tele_geo, rx, plot=False):
         ctypes.c_void_p(out.data_ptr()), n, geometry.scalar(tele_geo.k),
         ctypes.c_void_p(xyap.data_ptr()), ctypes.c_void_p(mask.data_ptr()),
         ctypes.c_void_p(tan_og.data_ptr()), ctypes.c_void_p(work.data_ptr()), _stream(torch)))
-    sel = xyap[:, mask.bool()].cpu().numpy()  # xx = np.where(out[4] != 0): order-preserving
+    sel = _lib.to_numpy(xyap[:, mask.bool()])  # xx = np.where(out[4] != 0): order-preserving
     return SimOutput(sel[0].copy(), sel[1].copy(), sel[2].copy(), sel[3].copy(),
-                     tan_og.cpu().numpy())
+                     _lib.to_numpy(tan_og))
 
 
 # --- host helpers over the returned arrays (ray_trace.py:1648-1672, 1757-1779) ------------
@@ -199,7 +199,7 @@ def near_field_samples(tele_geo, rx, *, device: bool = False):
     _lib.check(lib.sosat_trace_samples(
         rxa.ctypes.data_as(ctypes.POINTER(ctypes.c_double)), ctypes.byref(freq), n_scan, 0, n, 0.0,
         ctypes.c_void_p(xyb.data_ptr()), ctypes.c_void_p(stats.data_ptr()), _stream(torch)))
-    h_stats = stats.cpu().numpy()
+    h_stats = _lib.to_numpy(stats)
     if h_stats[_lib.STAT_N_BRACKET_FAIL] > 0:
         raise ValueError("f(a) and f(b) must have different signs")
     nv = h_stats[_lib.STAT_N_VALID]
@@ -207,7 +207,7 @@ def near_field_samples(tele_geo, rx, *, device: bool = False):
     phi0 = float(np.mod(geometry.scalar(tele_geo.k) / 1e3 / 2 * mean_opl, 2 * np.pi))
     b = torch.view_as_complex(xyb[:, 2:4].contiguous()) * complex(np.cos(phi0), -np.sin(phi0))
     xyb[:, 2:4] = torch.view_as_real(b)
-    return (xyb if device else xyb.cpu().numpy()), h_stats
+    return (xyb if device else _lib.to_numpy(xyb)), h_stats
 
 
 # --- on-device reductions for sweeps -------------------------------
@@ -236,7 +236,7 @@ def near_field_metrics(tele_geo, rx, freqs: Optional[Sequence] = None):
             ctypes.c_void_p(out.data_ptr()), out.shape[1], n_scan, 0, geometry.ot_geo.CONE_HALF_ANGLE,
             chunk, len(chunk), ctypes.c_void_p(result.data_ptr()), ctypes.c_void_p(work.data_ptr()),
             _stream(torch)))
-        h = result.cpu().numpy()
+        h = _lib.to_numpy(result)
         head = h[:6]
         res_all.append(h[6:6 + 2 * len(chunk)].reshape(-1, 2))
     tan_og = head[3:6].copy()
@@ -263,7 +263,7 @@ def ff_fwhm_device(beam_fft, x_ang, y_ang):
                                          ctypes.c_void_p(idx.data_ptr()),
                                          ctypes.c_void_p(val.data_ptr()),
                                          ctypes.c_void_p(work.data_ptr()), _stream(torch)))
-    pr, pc, c0, c1, r0, r1 = (int(v) for v in idx.cpu().numpy())
+    pr, pc, c0, c1, r0, r1 = (int(v) for v in _lib.to_numpy(idx))
     x_out, y_out = y_ang, x_ang  # the reference's swap, ray_trace.py:1759-1760
     scale = 60 * 180 / np.pi
     fwhm1 = abs(y_out[pr, c0] * scale - y_out[pr, c1] * scale)
@@ -408,7 +408,7 @@ def bins_to_field_device(re, im, cnt, stats, freq_specs, opl_ref=0.0, *, sync: b
                     geometry.scalar(k) / 1e3 / 2, float(opl_ref),
                     ctypes.c_void_p(b[i, f].data_ptr()), _stream(torch)))
         return torch.view_as_complex(b), None
-    h_stats = stats.cpu().numpy()
+    h_stats = _lib.to_numpy(stats)
     for i in range(n_rx):
         nv = h_stats[i, _lib.STAT_N_VALID]
         mean_opl = h_stats[i, _lib.STAT_SUM_OPL] / nv if nv > 0 else 0.0
@@ -454,9 +454,9 @@ def near_field_binned(tele_geo, rx, grid_n: int = 256, extent_cm: Optional[float
     re = torch.cat(out_re, dim=1) if keep_sums else None
     im = torch.cat(out_im, dim=1) if keep_sums else None
     if not device:
-        b, out_c = b.cpu().numpy(), out_c.cpu().numpy()
-        re = re.cpu().numpy() if keep_sums else None
-        im = im.cpu().numpy() if keep_sums else None
+        b, out_c = _lib.to_numpy(b), _lib.to_numpy(out_c)
+        re = _lib.to_numpy(re) if keep_sums else None
+        im = _lib.to_numpy(im) if keep_sums else None
     return BinnedField(b, out_c, out_s, extent_cm, grid_n, re, im)
 
 
@@ -499,11 +499,11 @@ def beam_sweep(tele_geo, rx_list, freqs, grid_n: int = 256, extent_cm: Optional[
             _lib.check(lib.sosat_ff_fwhm_indices(
                 ctypes.c_void_p(B[i * n_freq + f].data_ptr()), n, ctypes.c_void_p(idx.data_ptr()),
                 ctypes.c_void_p(val.data_ptr()), ctypes.c_void_p(work.data_ptr()), _stream(torch)))
-            pr, pc, c0, c1, r0, r1 = (int(v) for v in idx.cpu().numpy())
+            pr, pc, c0, c1, r0, r1 = (int(v) for v in _lib.to_numpy(idx))
             lam = 2 * np.pi / geometry.scalar(k)
             dth = lam / (n * dx_m) * (180 * 60 / np.pi)  # arcmin per far-field cell
             fwhm[i, f] = 0.5 * (abs(c1 - c0) + abs(r1 - r0)) * dth
-            peak[i, f] = float(np.sqrt(val.cpu().numpy()[0]))
+            peak[i, f] = float(np.sqrt(_lib.to_numpy(val)[0]))
             pidx[i, f] = (pr, pc)
     st = bf.stats
     return {"fwhm_arcmin": fwhm, "peak": peak, "peak_index": pidx,
@@ -516,4 +516,4 @@ def trace_stats(tele_geo, rx):
     rx_arr = np.asarray(rx, dtype=np.float64).reshape(-1, 3)
     spec = [(tele_geo.k, tele_geo.th_fwhp_x, tele_geo.th_fwhp_y)]
     _, _, _, stats = trace_bin_device(tele_geo, rx_arr, spec, 0, 0.0, bins=False)
-    return stats.cpu().numpy()
+    return _lib.to_numpy(stats)
