@@ -151,7 +151,10 @@ def to_numpy(t):
     nbytes = t.numel() * t.element_size()
     if nbytes == 0 or nbytes > PINNED_LIMIT_BYTES:
         return t.cpu().numpy()
-    h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    try:
+        h = torch.empty(t.shape, dtype=t.dtype, pin_memory=True)
+    except RuntimeError:  # page-locked memory exhausted: the pageable copy still works
+        return t.cpu().numpy()
     h.copy_(t, non_blocking=True)
     torch.cuda.current_stream().synchronize()
     return h.numpy()
