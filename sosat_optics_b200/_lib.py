@@ -14,6 +14,7 @@ NUM_SURFACES = 6
 OUT_ROWS = 17
 MAX_FREQS = 64
 NUM_STATS = 8
+PEER_HANDLE_BYTES = 64  # SOSAT_PEER_HANDLE_BYTES
 DFT_FORWARD, DFT_INVERSE, DFT_B2A = 0, 1, 2
 (STAT_N_VALID, STAT_SUM_OPL, STAT_SUM_DX, STAT_SUM_DY, STAT_SUM_DZ, STAT_N_SLOW,
  STAT_N_BRACKET_FAIL, STAT_N_BINNED) = range(8)

@@ -138,7 +138,7 @@ class PeerPlanes:
         # an exchange of the outcome, so that all ranks raise together instead of one rank
         # raising while the others wait in a collective.
         self.base, self._opened, self.peer_base = 0, [], []
-        err, handle = None, (ctypes.c_ubyte * 64)()
+        err, handle = None, (ctypes.c_ubyte * _lib.PEER_HANDLE_BYTES)()
         try:
             base = ctypes.c_void_p()
             _lib.check(self.lib.sosat_peer_alloc(L["bytes"], ctypes.byref(base)))
@@ -154,7 +154,7 @@ class PeerPlanes:
                     self.peer_base.append(self.base)
                     continue
                 ptr = ctypes.c_void_p()
-                buf = (ctypes.c_ubyte * 64).from_buffer_copy(h)
+                buf = (ctypes.c_ubyte * _lib.PEER_HANDLE_BYTES).from_buffer_copy(h)
                 _lib.check(self.lib.sosat_peer_open(buf, ctypes.byref(ptr)))
                 self.peer_base.append(ptr.value)
                 self._opened.append(ptr.value)

@@ -99,3 +99,30 @@ def test_geometry_marshalling():
     # a user may change the refractive index on the instance
     t.n_si = 3.38
     assert geometry.make_geom(t).surf[0].n_out == 3.38
+
+
+def test_peer_reduce_argument_checks_need_no_gpu():
+    """sosat_bins_reduce_field validates its arguments before touching CUDA: the error codes and
+    messages of the multi-GPU entry point can be checked on a CPU-only machine."""
+    import ctypes
+    lib = _lib.load()
+    one = (ctypes.c_void_p * 1)(ctypes.c_void_p(256))
+    many = (ctypes.c_void_p * 17)(*[ctypes.c_void_p(256)] * 17)
+
+    def call(peers, n_peers, begin=0, end=8, re_off=0, outs=one, n_out=1):
+        return lib.sosat_bins_reduce_field(peers, n_peers, re_off, 256, 512, 768, begin, end, 1.0, 0.0,
+                                           outs, n_out, 1024, None, None)
+
+    assert call(None, 1) != 0 and b"null pointer" in lib.sosat_last_error()
+    assert call(one, 0) != 0 and b"between 1 and 16" in lib.sosat_last_error()
+    assert call(many, 17) != 0 and b"between 1 and 16" in lib.sosat_last_error()
+    assert call(one, 1, outs=many, n_out=17) != 0 and b"between 1 and 16" in lib.sosat_last_error()
+    assert call(one, 1, begin=8, end=4) != 0 and b"bad cell range" in lib.sosat_last_error()
+    assert call(one, 1, begin=2, end=8) != 0 and b"multiple of 4" in lib.sosat_last_error()
+    assert call(one, 1, re_off=8) != 0 and b"misaligned plane offset" in lib.sosat_last_error()
+    null_base = (ctypes.c_void_p * 1)(None)
+    assert call(null_base, 1) != 0 and b"peer base null or misaligned" in lib.sosat_last_error()
+    handle = (ctypes.c_ubyte * _lib.PEER_HANDLE_BYTES)()
+    assert lib.sosat_peer_export(None, handle) != 0 and b"null pointer" in lib.sosat_last_error()
+    assert lib.sosat_peer_open(None, None) != 0 and b"null pointer" in lib.sosat_last_error()
+    assert lib.sosat_peer_free(None) == 0 and lib.sosat_peer_close(None) == 0
