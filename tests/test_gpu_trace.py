@@ -641,3 +641,63 @@ def test_peer_reduce_kernel_on_one_device(mods, feed_table):
         assert np.array_equal(stats[:, 0], st[:, 0].cpu().numpy())
     finally:
         peer.close()
+
+
+def test_full_size_bundle_properties(mods):
+    """BASELINE.json configs[4] at its full size -- 1.000014e9 rays (n_scan = 31623) into 2048^2
+    bins -- through size-independent properties, since no oracle finishes 10^9 rays:
+    conservation (every valid ray inside the grid is counted once), mirror symmetry of the
+    boresight bundle in x and in z (the launch grid is symmetric about the axis), additivity of
+    row shards (what the multi-GPU path relies on), and agreement of the bundle's statistics
+    with a coarser bundle of the same cone."""
+    rt, torch = mods["rt"], mods["torch"]
+    from sosat_optics_b200 import _lib
+    n_scan, n = 31623, 2048
+    t = _bundle(mods, n_scan)
+    spec = [(t.k, t.th_fwhp_x, t.th_fwhp_y)]
+    re, im, cnt, st = rt.trace_bin_device(t, [[0, 0, 0]], spec, n, 420.0)
+    torch.cuda.synchronize()
+    s = st.cpu().numpy()[0]
+    n_valid, n_binned = int(s[_lib.STAT_N_VALID]), int(s[_lib.STAT_N_BINNED])
+    total = float(cnt.double().sum().item())
+    assert total == n_binned and 0 < n_binned <= n_valid < n_scan * n_scan
+    assert 0.55 < n_valid / n_scan ** 2 < 0.8          # 68.9 % of the 0.4 rad cone passes the stop
+    assert int(s[_lib.STAT_N_BRACKET_FAIL]) == 0
+    c = cnt[0]
+    # mirror symmetry: x -> -x is column j -> n-1-j, z -> -z is row i -> n-1-i (cells are
+    # [-L/2 + j d, -L/2 + (j+1) d)); only rays within rounding of a cell edge may differ
+    # (the central launch column / row lands ON the edge between cells n/2-1 and n/2, at
+    # x = +-1e-14 mm, so those two columns / rows of cells are left out of the comparison)
+    mid = slice(n // 2 - 1, n // 2 + 1)
+    b, _ = rt.bins_to_field_device(re, im, cnt, st, spec, sync=False)
+    f = b[0, 0]
+    peak = f.abs().max().item()
+    for dim in (1, 0):
+        cc, ff = c.clone(), f.clone()
+        if dim == 1:
+            cc[:, mid] = 0
+            ff[:, mid] = 0
+        else:
+            cc[mid, :] = 0
+            ff[mid, :] = 0
+        assert float((cc - torch.flip(cc, dims=[dim])).abs().sum().item()) <= 1e-7 * total
+        assert (ff - torch.flip(ff, dims=[dim])).abs().max().item() < 2e-3 * peak
+    # additivity of row shards: three blocks of launch rows into one set of planes
+    re2, im2, cnt2 = torch.zeros_like(re), torch.zeros_like(im), torch.zeros_like(cnt)
+    st2 = torch.zeros_like(st)
+    for r0, r1 in ((0, 10000), (10000, 10016), (10016, n_scan)):
+        rt.trace_bin_device(t, [[0, 0, 0]], spec, n, 420.0, row_begin=r0, row_end=r1,
+                            planes=(re2, im2, cnt2), stats=st2)
+    torch.cuda.synchronize()
+    assert torch.equal(cnt2, cnt)
+    assert (re2 - re).abs().max().item() <= 1e-4 * re.abs().max().item()   # fp32 atomics, order
+    s2 = st2.cpu().numpy()[0]
+    assert s2[_lib.STAT_N_VALID] == s[_lib.STAT_N_VALID] and s2[_lib.STAT_N_BINNED] == s[_lib.STAT_N_BINNED]
+    assert abs(s2[_lib.STAT_SUM_OPL] - s[_lib.STAT_SUM_OPL]) <= 1e-12 * abs(s[_lib.STAT_SUM_OPL])
+    # the bundle's statistics converge with the sampling: a 2000^2 bundle of the same cone
+    tc = _bundle(mods, 2000)
+    sc = rt.trace_stats(tc, [[0, 0, 0]])[0]
+    assert abs(s[_lib.STAT_N_VALID] / n_scan ** 2 - sc[_lib.STAT_N_VALID] / 2000 ** 2) < 2e-3
+    mean_full = s[_lib.STAT_SUM_OPL] / s[_lib.STAT_N_VALID]
+    mean_coarse = sc[_lib.STAT_SUM_OPL] / sc[_lib.STAT_N_VALID]
+    assert abs(mean_full - mean_coarse) < 2e-2                      # mm, of ~1.1e3 mm
