@@ -131,11 +131,13 @@ __device__ __forceinline__ double rsqrt_fast(double x) {
     double e = fma(-a, y, 1.0);
     return fma(0.5 * y, e, y);
 }
+// Full precision in ONE cubically convergent step from the seed (5 DP instead of the 8 of two
+// Newton-Raphson steps): with e = 1 - x y^2 (|e| ~ 2e-6), 1/sqrt(x) = y (1 + e/2 + 3 e^2/8 + O(e^3)),
+// remainder 5 e^3/16 ~ 3e-18.
 __device__ __forceinline__ double rsqrt_full(double x) {
-    double y = rsqrt_fast(x);
-    double a = x * y;
-    double e = fma(-a, y, 1.0);
-    return fma(0.5 * y, e, y);
+    const double y = rsqrt_seed(x);
+    const double e = fma(-(x * y), y, 1.0);
+    return fma(y, e * fma(0.375, e, 0.5), y);
 }
 // Where each precision is used (measured against the oracle on 2e6 rays):
 // the sag evaluation tolerates the one-step rsqrt (median |dOPL| 2e-12 mm), the normalisation
@@ -208,19 +210,16 @@ __device__ __forceinline__ void surf_eval(const SurfC &S, const bool refine, dou
     Z = fma(dz, t, Pz);
     u = fma(X, X, Z * Z);
     w = fma(-S.Kp, u, 1.0);
-    rs = SOSAT_RSQRT_EVAL(w);
+    // |cK| > 300 mm (refine folds to a constant in the unrolled surface loop): the (1 - s)
+    // cancellation needs the fully rounded rsqrt there
+    rs = (!GENERIC && refine) ? rsqrt_full(w) : SOSAT_RSQRT_EVAL(w);
     const double poly = fma(fma(S.a3p, u, S.a2p), u, S.a1p);
     const double base = fma(-u, poly, fma(-dy, t, y0PyK));
     if (GENERIC) {
         const double s = w * rs;
         f = fma(-u, S.cp * rcp_full(1.0 + s), base);
     } else {
-        const double B = S.cK * w;
-        if (refine) {  // |cK| > 300 mm (folds to a constant in the unrolled surface loop)
-            const double a = w * rs;
-            rs = fma(0.5 * rs, fma(-a, rs, 1.0), rs);
-        }
-        f = fma(B, rs, base);  // ... - cK (1 - s)
+        f = fma(S.cK * w, rs, base);  // ... - cK (1 - s)
     }
     h = fma(S.a3p6, u, S.a2p4);
     G = fma(S.cp, rs, fma(u, h, S.a1p2));  // c'/s + d(poly u)/du * 2
@@ -477,8 +476,7 @@ SOSAT_SCHED_TPL __device__ __forceinline__ void surface_hit(const GeomC &g, cons
         // 4 a2' + 12 a3' u = h + 6 a3' u with h = 4 a2' + 6 a3' u from the evaluation of G
         const double dGdu = fma(S.cKh, rs * rs * rs, fma(S.a3p6, u, h));
         G = fma(dGdu * xd, -2.0 * step, G);
-        X = fma(-step, R.dx, X);
-        Z = fma(-step, R.dz, Z);
+        // (X, Z at the new t are the advanced hit point below: R.Px, R.Pz)
         // largest |step| of the ray, tracked on the high word (2 ALU instructions per surface
         // instead of a DSETP on the fp64 pipe) and tested once after the last surface
         R.step_hi = max(R.step_hi, __double2hiint(step) & 0x7fffffff);
@@ -515,7 +513,10 @@ SOSAT_SCHED_TPL __device__ __forceinline__ void surface_hit(const GeomC &g, cons
     if (si == 0 && fma(R.Px, R.Px, R.Pz * R.Pz) >= g.clip_l3_sq) R.flags |= RAY_CLIPPED_L3;
     if (si == 3) R.r2a_sq = fma(R.Px, R.Px, R.Pz * R.Pz);
     R.opl = fma(t, S.n_in, R.opl);  // dist_* = |hit - previous| = t for unit d
-    refract(S, X, Z, G, R.dx, R.dy, R.dz, R.gx, R.gz, R.L2);
+    if (kLinear)
+        refract(S, R.Px, R.Pz, G, R.dx, R.dy, R.dz, R.gx, R.gz, R.L2);
+    else
+        refract(S, X, Z, G, R.dx, R.dy, R.dz, R.gx, R.gz, R.L2);
 }
 
 SOSAT_SCHED_TPL __device__ __forceinline__ void ray_finish(const GeomC &g, RayState &R,
