@@ -27,6 +27,9 @@
  *     workspaces is mutex-protected.  The geometry and the per-call frequency table are
  *     per-DEVICE __constant__ state written in stream order: trace calls that use different
  *     geometries or frequency lists must not overlap on different streams of the same device.
+ *     A DFT workspace (scratch of the transform in flight + the twiddles cached in it, written
+ *     by a kernel on the stream of the first call) belongs to ONE stream: give every stream its
+ *     own workspace (the Python wrappers key their workspace cache by device and stream).
  */
 #ifndef SOSAT_B200_H
 #define SOSAT_B200_H
@@ -165,6 +168,14 @@ int sosat_bins_to_field(const float *d_re, const float *d_im, const float *d_cnt
 int sosat_bins_to_field_stats(const float *d_re, const float *d_im, const float *d_cnt, int64_t n,
                               const double *d_stats, double k_over_2e3, double opl_ref,
                               float *d_b, void *stream);
+/* The whole stack of fields of a sweep in ONE launch (grid y = field): d_re / d_im / d_b
+ * [n_rx][n_freq][n], d_cnt [n_rx][n], d_stats [n_rx][SOSAT_NUM_STATS], h_k_over_2e3 [n_freq]
+ * (HOST array, copied into the launch parameters).  Replaces the n_rx x n_freq Python loop over
+ * sosat_bins_to_field_stats (a 32-receiver x 64-frequency sweep is 2 048 fields). */
+int sosat_bins_to_field_stats_batch(const float *d_re, const float *d_im, const float *d_cnt,
+                                    int64_t n, int n_rx, int n_freq, const double *d_stats,
+                                    const double *h_k_over_2e3, double opl_ref, float *d_b,
+                                    void *stream);
 
 /* ---- stage 2: far-field transform (opt_analyze.py:220-230 a2b) ----------------------- */
 /* B = W_r b W_c^T, W[k,n] = exp(-2 pi i (k - floor(N/2)) (n - ceil(N/2)) / N): identical to
@@ -254,6 +265,12 @@ int sosat_near_field_metrics(const double *d_out, int64_t n, int n_scan, int64_t
  * d_val[0] = peak |B|^2.  d_work: 8 bytes of scratch. */
 int sosat_ff_fwhm_indices(const float *d_B, int n, int *d_idx, float *d_val, void *d_work,
                           void *stream);
+/* The same for a stack d_B [n_fields][n][n] in one launch per search: d_idx [n_fields][6],
+ * d_val [n_fields], d_work 8 * n_fields bytes.  A field without a finite non-zero cell (e.g. a
+ * NaN in the near field, which the contraction spreads over the whole far field) reports all six
+ * indices as -1 and val = 0; the Python wrappers raise on it. */
+int sosat_ff_fwhm_indices_batch(const float *d_B, int n, int n_fields, int *d_idx, float *d_val,
+                                void *d_work, void *stream);
 
 /* ---- measurement helpers --------------------------------------------------------------- */
 /* ---- multi-GPU: reduce of the bin planes over NVLink peer memory -----------
@@ -285,6 +302,17 @@ int sosat_bins_reduce_field(const void *const *h_peer_base, int n_peers, int64_t
                             int64_t cell_begin, int64_t cell_end, double k_over_2e3,
                             double opl_ref, void *const *h_out_base, int n_out, int64_t out_off,
                             double *d_stats_sum, void *stream);
+/* The same for the whole stack of (receiver, frequency) fields of a sweep in one launch (grid
+ * y = field irx * n_freq + f): planes of n_cells cells each, re / im / field stacked
+ * [n_rx][n_freq], counts and statistics rows [n_rx]; offsets are those of field 0;
+ * h_k_over_2e3 [n_freq] HOST array; d_stats_sum [n_rx][SOSAT_NUM_STATS].  With more than one
+ * field n_cells must be a multiple of 4 (16-byte aligned planes). */
+int sosat_bins_reduce_fields(const void *const *h_peer_base, int n_peers, int64_t re_off,
+                             int64_t im_off, int64_t cnt_off, int64_t stats_off, int64_t n_cells,
+                             int n_rx, int n_freq, int64_t cell_begin, int64_t cell_end,
+                             const double *h_k_over_2e3, double opl_ref,
+                             void *const *h_out_base, int n_out, int64_t out_off,
+                             double *d_stats_sum, void *stream);
 
 /* Dependent-free FP64 FMA throughput microkernel: returns achieved FLOP/s (2 per FMA) in
  * *flops_per_s; used by bench.py as the roofline denominator of the ray tracer because

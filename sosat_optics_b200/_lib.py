@@ -60,6 +60,9 @@ SIGNATURES = {
                                     c_void_p]),
     "sosat_bins_to_field_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_double,
                                           c_double, c_void_p, c_void_p]),
+    "sosat_bins_to_field_stats_batch": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_int, c_int,
+                                                c_void_p, POINTER(c_double), c_double, c_void_p,
+                                                c_void_p]),
     "sosat_dft2_workspace_bytes": (c_size_t, [c_int]),
     "sosat_dft2_forget": (c_int, [c_void_p]),
     "sosat_dft2_gemm": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_size_t, c_void_p]),
@@ -85,6 +88,12 @@ SIGNATURES = {
     "sosat_near_field_metrics": (c_int, [c_void_p, c_int64, c_int, c_int64, c_double, POINTER(Freq),
                                          c_int, c_void_p, c_void_p, c_void_p]),
     "sosat_ff_fwhm_indices": (c_int, [c_void_p, c_int, c_void_p, c_void_p, c_void_p, c_void_p]),
+    "sosat_ff_fwhm_indices_batch": (c_int, [c_void_p, c_int, c_int, c_void_p, c_void_p, c_void_p,
+                                            c_void_p]),
+    "sosat_bins_reduce_fields": (c_int, [POINTER(c_void_p), c_int, c_int64, c_int64, c_int64, c_int64,
+                                         c_int64, c_int, c_int, c_int64, c_int64, POINTER(c_double),
+                                         c_double, POINTER(c_void_p), c_int, c_int64, c_void_p,
+                                         c_void_p]),
     "sosat_measure_fp64_peak": (c_int, [POINTER(c_double), POINTER(c_double)]),
     "sosat_peer_alloc": (c_int, [c_int64, POINTER(c_void_p)]),
     "sosat_peer_free": (c_int, [c_void_p]),

@@ -25,7 +25,12 @@ __global__ void __launch_bounds__(kNuThreads)
 nudft_kernel(const float4 *__restrict__ xyb, long long n_pts, const float2 *__restrict__ th,
              long long n_ang, float scale, long long pts_per_split, float2 *__restrict__ out) {
     __shared__ float4 s_pts[kNuPts];
-    float tx[kNuPerThread], ty[kNuPerThread], ar[kNuPerThread], ai[kNuPerThread];
+    // Two-level accumulation: fp32 within a shared-memory chunk (1024 points: coherent sums stay
+    // below 2^10 |b|, so every sample keeps >= 13 bits), chunk sums folded into fp64 -- a coherent
+    // beam peak over 1e7+ points per split would otherwise reach 2^23..2^24 |b| in fp32, where the
+    // ulp is the sample amplitude.  4 DADD + 4 F2F per thread and chunk: 0.2 % of the chunk's work.
+    float tx[kNuPerThread], ty[kNuPerThread];
+    double ar[kNuPerThread], ai[kNuPerThread];
     const long long j0 = ((long long)blockIdx.x * kNuThreads + threadIdx.x);
     const long long stride = (long long)gridDim.x * kNuThreads;
 #pragma unroll
@@ -34,8 +39,8 @@ nudft_kernel(const float4 *__restrict__ xyb, long long n_pts, const float2 *__re
         const float2 t = j < n_ang ? th[j] : make_float2(0.f, 0.f);
         tx[q] = t.x * scale;  // radians per unit x, sign of the numpy FFT (scale = -2 pi / lambda)
         ty[q] = t.y * scale;
-        ar[q] = 0.f;
-        ai[q] = 0.f;
+        ar[q] = 0.0;
+        ai[q] = 0.0;
     }
     const long long p_begin = (long long)blockIdx.y * pts_per_split;
     const long long p_end = min(n_pts, p_begin + pts_per_split);
@@ -44,6 +49,9 @@ nudft_kernel(const float4 *__restrict__ xyb, long long n_pts, const float2 *__re
         __syncthreads();
         for (int i = threadIdx.x; i < m; i += kNuThreads) s_pts[i] = xyb[p0 + i];
         __syncthreads();
+        float cr[kNuPerThread], ci[kNuPerThread];
+#pragma unroll
+        for (int q = 0; q < kNuPerThread; ++q) cr[q] = ci[q] = 0.f;
 #pragma unroll 4
         for (int i = 0; i < m; ++i) {
             const float4 pt = s_pts[i];
@@ -51,9 +59,14 @@ nudft_kernel(const float4 *__restrict__ xyb, long long n_pts, const float2 *__re
             for (int q = 0; q < kNuPerThread; ++q) {
                 const float ang = fmaf(pt.x, tx[q], pt.y * ty[q]);
                 const float sn = __sinf(ang), cs = __cosf(ang);
-                ar[q] = fmaf(pt.z, cs, fmaf(-pt.w, sn, ar[q]));
-                ai[q] = fmaf(pt.z, sn, fmaf(pt.w, cs, ai[q]));
+                cr[q] = fmaf(pt.z, cs, fmaf(-pt.w, sn, cr[q]));
+                ci[q] = fmaf(pt.z, sn, fmaf(pt.w, cs, ci[q]));
             }
+        }
+#pragma unroll
+        for (int q = 0; q < kNuPerThread; ++q) {
+            ar[q] += (double)cr[q];
+            ai[q] += (double)ci[q];
         }
     }
 #pragma unroll
@@ -61,10 +74,10 @@ nudft_kernel(const float4 *__restrict__ xyb, long long n_pts, const float2 *__re
         const long long j = j0 + q * stride;
         if (j < n_ang) {
             if (ATOMIC) {
-                atomicAdd(&out[j].x, ar[q]);
-                atomicAdd(&out[j].y, ai[q]);
+                atomicAdd(&out[j].x, (float)ar[q]);
+                atomicAdd(&out[j].y, (float)ai[q]);
             } else {
-                out[j] = make_float2(ar[q], ai[q]);
+                out[j] = make_float2((float)ar[q], (float)ai[q]);
             }
         }
     }

@@ -24,7 +24,11 @@ struct PeerArgs {
     const char *base[kMaxPeers];  // flat buffers of the peers (identical layout)
     char *out[kMaxPeers];         // buffers that receive the field slab
     int n_peers, n_out;
-    long long re_off, im_off, cnt_off, stats_off, out_off;  // byte offsets from a base
+    long long re_off, im_off, cnt_off, stats_off, out_off;  // byte offsets from a base (field 0)
+    // stack of (receiver, frequency) fields, blockIdx.y = irx * n_freq + f: plane `cells` long
+    int n_freq;
+    long long cells;
+    double k_over_2e3[SOSAT_MAX_FREQS];
 };
 
 __device__ __forceinline__ float4 add4(float4 a, float4 b) {
@@ -41,8 +45,13 @@ __device__ __forceinline__ float2 norm_cell(float r, float i, float c, float fcs
 }
 
 __global__ void __launch_bounds__(256)
-bins_reduce_field_kernel(PeerArgs P, long long begin, long long end, double k_over_2e3,
+bins_reduce_field_kernel(const __grid_constant__ PeerArgs P, long long begin, long long end,
                          double opl_ref, double *__restrict__ stats_sum) {
+    const int fld = blockIdx.y, irx = fld / P.n_freq, ifr = fld - irx * P.n_freq;
+    const long long re_off = P.re_off + 4 * fld * P.cells, im_off = P.im_off + 4 * fld * P.cells;
+    const long long cnt_off = P.cnt_off + 4 * irx * P.cells, out_off = P.out_off + 8 * fld * P.cells;
+    const long long stats_off = P.stats_off + 8 * SOSAT_NUM_STATS * irx;
+    const double k_over_2e3 = P.k_over_2e3[ifr];
     // statistics of the whole bundle: sum of the peers' rows (8 doubles each).  ONE thread per
     // statistic and block fetches them (every thread reading the same remote sectors would
     // serialise on the peers' L2: 1 ms at 8 GPUs, measured)
@@ -50,9 +59,9 @@ bins_reduce_field_kernel(PeerArgs P, long long begin, long long end, double k_ov
     if (threadIdx.x < SOSAT_NUM_STATS) {
         double v = 0.0;
         for (int p = 0; p < P.n_peers; ++p)
-            v += __ldcg((const double *)(P.base[p] + P.stats_off) + threadIdx.x);
+            v += __ldcg((const double *)(P.base[p] + stats_off) + threadIdx.x);
         s_st[threadIdx.x] = v;
-        if (stats_sum && blockIdx.x == 0) stats_sum[threadIdx.x] = v;
+        if (stats_sum && blockIdx.x == 0 && ifr == 0) stats_sum[SOSAT_NUM_STATS * irx + threadIdx.x] = v;
     }
     __syncthreads();
     double st[SOSAT_NUM_STATS];
@@ -72,15 +81,15 @@ bins_reduce_field_kernel(PeerArgs P, long long begin, long long end, double k_ov
         float4 r = make_float4(0.f, 0.f, 0.f, 0.f), m = r, c = r;
 #pragma unroll 4
         for (int p = 0; p < P.n_peers; ++p) {
-            r = add4(r, __ldcg((const float4 *)(P.base[p] + P.re_off) + (i >> 2)));
-            m = add4(m, __ldcg((const float4 *)(P.base[p] + P.im_off) + (i >> 2)));
-            c = add4(c, __ldcg((const float4 *)(P.base[p] + P.cnt_off) + (i >> 2)));
+            r = add4(r, __ldcg((const float4 *)(P.base[p] + re_off) + (i >> 2)));
+            m = add4(m, __ldcg((const float4 *)(P.base[p] + im_off) + (i >> 2)));
+            c = add4(c, __ldcg((const float4 *)(P.base[p] + cnt_off) + (i >> 2)));
         }
         const float2 v0 = norm_cell(r.x, m.x, c.x, fcs, fsn), v1 = norm_cell(r.y, m.y, c.y, fcs, fsn);
         const float2 v2 = norm_cell(r.z, m.z, c.z, fcs, fsn), v3 = norm_cell(r.w, m.w, c.w, fcs, fsn);
         const float4 lo = make_float4(v0.x, v0.y, v1.x, v1.y), hi = make_float4(v2.x, v2.y, v3.x, v3.y);
         for (int d = 0; d < P.n_out; ++d) {
-            float4 *o = (float4 *)(P.out[d] + P.out_off) + (i >> 1);
+            float4 *o = (float4 *)(P.out[d] + out_off) + (i >> 1);
             o[0] = lo;
             o[1] = hi;
         }
@@ -90,12 +99,12 @@ bins_reduce_field_kernel(PeerArgs P, long long begin, long long end, double k_ov
          i += (long long)gridDim.x * blockDim.x) {
         float r = 0.f, m = 0.f, c = 0.f;
         for (int p = 0; p < P.n_peers; ++p) {
-            r += __ldcg((const float *)(P.base[p] + P.re_off) + i);
-            m += __ldcg((const float *)(P.base[p] + P.im_off) + i);
-            c += __ldcg((const float *)(P.base[p] + P.cnt_off) + i);
+            r += __ldcg((const float *)(P.base[p] + re_off) + i);
+            m += __ldcg((const float *)(P.base[p] + im_off) + i);
+            c += __ldcg((const float *)(P.base[p] + cnt_off) + i);
         }
         const float2 v = norm_cell(r, m, c, fcs, fsn);
-        for (int d = 0; d < P.n_out; ++d) ((float2 *)(P.out[d] + P.out_off))[i] = v;
+        for (int d = 0; d < P.n_out; ++d) ((float2 *)(P.out[d] + out_off))[i] = v;
     }
 }
 
@@ -140,21 +149,28 @@ extern "C" int sosat_peer_close(void *d_peer) {
     return SOSAT_OK;
 }
 
-extern "C" int sosat_bins_reduce_field(const void *const *h_peer_base, int n_peers,
-                                       int64_t re_off, int64_t im_off, int64_t cnt_off,
-                                       int64_t stats_off, int64_t cell_begin, int64_t cell_end,
-                                       double k_over_2e3, double opl_ref,
-                                       void *const *h_out_base, int n_out, int64_t out_off,
-                                       double *d_stats_sum, void *stream) {
-    SOSAT_REQUIRE(h_peer_base && h_out_base, "sosat_bins_reduce_field: null pointer");
+extern "C" int sosat_bins_reduce_fields(const void *const *h_peer_base, int n_peers,
+                                        int64_t re_off, int64_t im_off, int64_t cnt_off,
+                                        int64_t stats_off, int64_t n_cells, int n_rx, int n_freq,
+                                        int64_t cell_begin, int64_t cell_end,
+                                        const double *h_k_over_2e3, double opl_ref,
+                                        void *const *h_out_base, int n_out, int64_t out_off,
+                                        double *d_stats_sum, void *stream) {
+    SOSAT_REQUIRE(h_peer_base && h_out_base && h_k_over_2e3, "sosat_bins_reduce_fields: null pointer");
     SOSAT_REQUIRE(n_peers >= 1 && n_peers <= kMaxPeers && n_out >= 1 && n_out <= kMaxPeers,
-                  "sosat_bins_reduce_field: between 1 and %d peers / destinations", kMaxPeers);
-    SOSAT_REQUIRE(cell_begin >= 0 && cell_end >= cell_begin, "bad cell range");
+                  "sosat_bins_reduce_fields: between 1 and %d peers / destinations", kMaxPeers);
+    SOSAT_REQUIRE(n_rx >= 1 && n_freq >= 1 && n_freq <= SOSAT_MAX_FREQS &&
+                      (long long)n_rx * n_freq <= 65535,
+                  "n_rx x n_freq = %d x %d out of range", n_rx, n_freq);
+    SOSAT_REQUIRE(cell_begin >= 0 && cell_end >= cell_begin && cell_end <= n_cells, "bad cell range");
     // (an empty slab -- more ranks than 4-cell units -- still launches: it sums the statistics)
     SOSAT_REQUIRE(cell_begin % 4 == 0 || cell_begin == cell_end, "cell_begin must be a multiple of 4");
     SOSAT_REQUIRE(re_off % 16 == 0 && im_off % 16 == 0 && cnt_off % 16 == 0 && out_off % 16 == 0 &&
                       stats_off % 8 == 0,
-                  "sosat_bins_reduce_field: misaligned plane offset");
+                  "sosat_bins_reduce_fields: misaligned plane offset");
+    SOSAT_REQUIRE(n_rx * n_freq == 1 || n_cells % 4 == 0,
+                  "a stack of fields needs a cell count per plane that is a multiple of 4 "
+                  "(16-byte aligned planes); got %lld", (long long)n_cells);
     PeerArgs P;
     memset(&P, 0, sizeof P);
     for (int p = 0; p < n_peers; ++p) {
@@ -169,13 +185,29 @@ extern "C" int sosat_bins_reduce_field(const void *const *h_peer_base, int n_pee
     P.n_out = n_out;
     P.re_off = re_off; P.im_off = im_off; P.cnt_off = cnt_off; P.stats_off = stats_off;
     P.out_off = out_off;
+    P.n_freq = n_freq;
+    P.cells = n_cells;
+    for (int f = 0; f < n_freq; ++f) P.k_over_2e3[f] = h_k_over_2e3[f];
+    const int fields = n_rx * n_freq;
     const long long n = cell_end - cell_begin;
     long long blocks = (n / 4 + 255) / 256;
     if (blocks < 1) blocks = 1;
-    const long long cap = (long long)num_sms() * 8;
+    long long cap = (long long)num_sms() * 8 / fields;
+    if (cap < 4) cap = 4;
     if (blocks > cap) blocks = cap;
-    bins_reduce_field_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
-        P, cell_begin, cell_end, k_over_2e3, opl_ref, d_stats_sum);
+    bins_reduce_field_kernel<<<dim3((unsigned)blocks, (unsigned)fields), 256, 0, (cudaStream_t)stream>>>(
+        P, cell_begin, cell_end, opl_ref, d_stats_sum);
     SOSAT_CUDA_OK(cudaGetLastError());
     return SOSAT_OK;
+}
+
+extern "C" int sosat_bins_reduce_field(const void *const *h_peer_base, int n_peers,
+                                       int64_t re_off, int64_t im_off, int64_t cnt_off,
+                                       int64_t stats_off, int64_t cell_begin, int64_t cell_end,
+                                       double k_over_2e3, double opl_ref,
+                                       void *const *h_out_base, int n_out, int64_t out_off,
+                                       double *d_stats_sum, void *stream) {
+    return sosat_bins_reduce_fields(h_peer_base, n_peers, re_off, im_off, cnt_off, stats_off,
+                                    cell_end, 1, 1, cell_begin, cell_end, &k_over_2e3, opl_ref,
+                                    h_out_base, n_out, out_off, d_stats_sum, stream);
 }

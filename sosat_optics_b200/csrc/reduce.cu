@@ -129,10 +129,22 @@ __global__ void nfm_fwhm_kernel(const double *__restrict__ out, NfmParams p, Met
 }
 
 // ---- far field: peak of |B|^2 and the half-power extent through the peak row and column ------
+// One launch covers a whole stack of fields (blockIdx.y = field): a receiver x frequency sweep
+// reads back ONE small array instead of synchronising once per field.
 // packed = float bits of |B|^2 << 32 | (0xffffffff - flat index): atomicMax picks the largest
 // value and, among equal values, the smallest index (np.where(...)[0][0], row-major).
-__global__ void ff_peak_kernel(const float2 *__restrict__ B, long long n2,
+__global__ void ff_init_kernel(int n, int n_fields, unsigned long long *packed, int *idx) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n_fields) {
+        packed[i] = 0ull;
+        int *d = idx + 6 * i;
+        d[0] = 0; d[1] = 0; d[2] = n; d[3] = -1; d[4] = n; d[5] = -1;
+    }
+}
+
+__global__ void ff_peak_kernel(const float2 *__restrict__ B_all, long long n2,
                                unsigned long long *packed) {
+    const float2 *B = B_all + (long long)blockIdx.y * n2;
     unsigned long long best = 0ull;
     for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n2;
          i += (long long)gridDim.x * blockDim.x) {
@@ -149,24 +161,34 @@ __global__ void ff_peak_kernel(const float2 *__restrict__ B, long long n2,
         const unsigned long long other = __shfl_xor_sync(0xffffffffu, best, o);
         best = other > best ? other : best;
     }
-    if ((threadIdx.x & 31) == 0 && best) atomicMax(packed, best);
+    if ((threadIdx.x & 31) == 0 && best) atomicMax(packed + blockIdx.y, best);
 }
 
-// idx: [0] peak row, [1] peak column, [2],[3] first/last column above half power in the peak
-// row, [4],[5] first/last row above half power in the peak column; val[0] = peak |B|^2
-__global__ void ff_extent_kernel(const float2 *__restrict__ B, int n,
-                                 const unsigned long long *__restrict__ packed, int *idx,
+// idx (per field): [0] peak row, [1] peak column, [2],[3] first/last column above half power in
+// the peak row, [4],[5] first/last row above half power in the peak column; val = peak |B|^2.
+// A field without a finite non-zero cell (one NaN in b spreads through the contraction to every
+// cell of B) reports all six indices as -1 and val = 0 -- the wrappers raise -- instead of
+// decoding the untouched 0 into a row index far outside the array.
+__global__ void ff_extent_kernel(const float2 *__restrict__ B_all, int n,
+                                 const unsigned long long *__restrict__ packed, int *idx_all,
                                  float *val) {
-    const unsigned long long pk = *packed;
+    const float2 *B = B_all + (size_t)blockIdx.y * n * n;
+    int *idx = idx_all + 6 * blockIdx.y;
+    const unsigned long long pk = packed[blockIdx.y];
     const unsigned flat = 0xffffffffu - (unsigned)(pk & 0xffffffffull);
     const float peak = __uint_as_float((unsigned)(pk >> 32));
     const int pr = (int)(flat / (unsigned)n), pc = (int)(flat % (unsigned)n);
-    if (threadIdx.x == 0 && blockIdx.x == 0) {
+    const bool along_row = blockIdx.x == 0;  // block 0: the peak row, block 1: the peak column
+    if (pk == 0ull || pr >= n || !(peak > 0.f)) {
+        if (threadIdx.x < 3) idx[3 * blockIdx.x + threadIdx.x] = -1;
+        if (threadIdx.x == 0 && along_row) val[blockIdx.y] = 0.f;
+        return;
+    }
+    if (threadIdx.x == 0 && along_row) {
         idx[0] = pr;
         idx[1] = pc;
-        val[0] = peak;
+        val[blockIdx.y] = peak;
     }
-    const bool along_row = blockIdx.x == 0;  // block 0: the peak row, block 1: the peak column
     int first = n, last = -1;
     for (int j = threadIdx.x; j < n; j += blockDim.x) {
         const float2 v = along_row ? B[(size_t)pr * n + j] : B[(size_t)j * n + pc];
@@ -223,22 +245,29 @@ extern "C" int sosat_near_field_metrics(const double *d_out, int64_t n, int n_sc
     return SOSAT_OK;
 }
 
-extern "C" int sosat_ff_fwhm_indices(const float *d_B, int n, int *d_idx, float *d_val,
-                                     void *d_work, void *stream) {
+extern "C" int sosat_ff_fwhm_indices_batch(const float *d_B, int n, int n_fields, int *d_idx,
+                                           float *d_val, void *d_work, void *stream) {
     SOSAT_REQUIRE(d_B && d_idx && d_val && d_work, "sosat_ff_fwhm_indices: null pointer");
     SOSAT_REQUIRE(n >= 1 && n <= 65535, "n=%d out of range [1, 65535]", n);
+    SOSAT_REQUIRE(n_fields >= 0 && n_fields <= 65535, "n_fields=%d out of range [0, 65535]", n_fields);
+    if (n_fields == 0) return SOSAT_OK;
     cudaStream_t st = (cudaStream_t)stream;
-    const int init[6] = {0, 0, n, -1, n, -1};
-    SOSAT_CUDA_OK(cudaMemsetAsync(d_work, 0, 8, st));
-    SOSAT_CUDA_OK(cudaMemcpyAsync(d_idx, init, sizeof init, cudaMemcpyHostToDevice, st));
+    ff_init_kernel<<<(n_fields + 255) / 256, 256, 0, st>>>(n, n_fields, (unsigned long long *)d_work,
+                                                          d_idx);
     const long long n2 = (long long)n * n;
     long long blocks = (n2 + 255) / 256;
-    const long long cap = (long long)num_sms() * 8;
+    long long cap = (long long)num_sms() * 8 / n_fields;
+    if (cap < 8) cap = 8;
     if (blocks > cap) blocks = cap;
-    ff_peak_kernel<<<(unsigned)blocks, 256, 0, st>>>((const float2 *)d_B, n2,
-                                                     (unsigned long long *)d_work);
-    ff_extent_kernel<<<2, 256, 0, st>>>((const float2 *)d_B, n, (const unsigned long long *)d_work,
-                                        d_idx, d_val);
+    ff_peak_kernel<<<dim3((unsigned)blocks, (unsigned)n_fields), 256, 0, st>>>(
+        (const float2 *)d_B, n2, (unsigned long long *)d_work);
+    ff_extent_kernel<<<dim3(2, (unsigned)n_fields), 256, 0, st>>>(
+        (const float2 *)d_B, n, (const unsigned long long *)d_work, d_idx, d_val);
     SOSAT_CUDA_OK(cudaGetLastError());
     return SOSAT_OK;
+}
+
+extern "C" int sosat_ff_fwhm_indices(const float *d_B, int n, int *d_idx, float *d_val,
+                                     void *d_work, void *stream) {
+    return sosat_ff_fwhm_indices_batch(d_B, n, 1, d_idx, d_val, d_work, stream);
 }

@@ -550,6 +550,39 @@ __global__ void bins_to_field_stats_kernel(const float *__restrict__ re, const f
     }
 }
 
+// The whole stack of (receiver, frequency) fields of a sweep in ONE launch: blockIdx.y = field
+// irx * n_freq + f; the statistics row is the receiver's, the phase scale the frequency's.
+struct FieldScales {
+    double k_over_2e3[SOSAT_MAX_FREQS];
+};
+__global__ void bins_to_field_stats_batch_kernel(const float *__restrict__ re, const float *__restrict__ im,
+                                                 const float *__restrict__ cnt, long long n, int n_freq,
+                                                 const double *__restrict__ stats, FieldScales ks,
+                                                 double opl_ref, float2 *__restrict__ b) {
+    const int fld = blockIdx.y, irx = fld / n_freq, f = fld - irx * n_freq;
+    const double *st = stats + (long long)irx * SOSAT_NUM_STATS;
+    const double nv = st[SOSAT_STAT_N_VALID];
+    const double mean_opl = nv > 0 ? st[SOSAT_STAT_SUM_OPL] / nv : 0.0;
+    double sn, cs;
+    sincos(ks.k_over_2e3[f] * (mean_opl - opl_ref), &sn, &cs);
+    const float fcs = (float)cs, fsn = (float)sn;
+    re += (long long)fld * n;
+    im += (long long)fld * n;
+    cnt += (long long)irx * n;
+    b += (long long)fld * n;
+    for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n;
+         i += (long long)gridDim.x * blockDim.x) {
+        const float c = cnt[i];
+        float2 v = make_float2(0.f, 0.f);
+        if (c > 0.f) {
+            const float inv = 1.0f / c, x = re[i] * inv, y = im[i] * inv;
+            v.x = x * fcs + y * fsn;  // (x + i y) * exp(-i phi0)
+            v.y = y * fcs - x * fsn;
+        }
+        b[i] = v;
+    }
+}
+
 // ---- FP64 FMA throughput microkernel (roofline denominator of K1) ---------------------------
 __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, double a, double b) {
     double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5,
@@ -892,6 +925,32 @@ extern "C" int sosat_bins_to_field_stats(const float *d_re, const float *d_im, c
     if (blocks > cap) blocks = cap;
     bins_to_field_stats_kernel<<<(unsigned)blocks, 256, 0, (cudaStream_t)stream>>>(
         d_re, d_im, d_cnt, n, d_stats, k_over_2e3, opl_ref, (float2 *)d_b);
+    SOSAT_CUDA_OK(cudaGetLastError());
+    return SOSAT_OK;
+}
+
+extern "C" int sosat_bins_to_field_stats_batch(const float *d_re, const float *d_im,
+                                               const float *d_cnt, int64_t n, int n_rx, int n_freq,
+                                               const double *d_stats, const double *h_k_over_2e3,
+                                               double opl_ref, float *d_b, void *stream) {
+    SOSAT_REQUIRE(d_re && d_im && d_cnt && d_stats && d_b && h_k_over_2e3,
+                  "sosat_bins_to_field_stats_batch: null pointer");
+    SOSAT_REQUIRE(n >= 0, "negative cell count");
+    SOSAT_REQUIRE(n_rx >= 0 && n_freq >= 1 && n_freq <= SOSAT_MAX_FREQS &&
+                      (long long)n_rx * n_freq <= 65535,
+                  "n_rx x n_freq = %d x %d out of range", n_rx, n_freq);
+    if (n == 0 || n_rx == 0) return SOSAT_OK;
+    FieldScales ks;
+    memset(&ks, 0, sizeof ks);
+    for (int f = 0; f < n_freq; ++f) ks.k_over_2e3[f] = h_k_over_2e3[f];
+    const int fields = n_rx * n_freq;
+    long long blocks = (n + 255) / 256;
+    long long cap = (long long)num_sms() * 8 / fields;
+    if (cap < 4) cap = 4;
+    if (blocks > cap) blocks = cap;
+    bins_to_field_stats_batch_kernel<<<dim3((unsigned)blocks, (unsigned)fields), 256, 0,
+                                       (cudaStream_t)stream>>>(d_re, d_im, d_cnt, n, n_freq, d_stats,
+                                                               ks, opl_ref, (float2 *)d_b);
     SOSAT_CUDA_OK(cudaGetLastError());
     return SOSAT_OK;
 }

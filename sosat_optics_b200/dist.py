@@ -132,6 +132,9 @@ class PeerPlanes:
         self.rank, self.world = world_info(group)
         if self.world > 16:
             raise ValueError("PeerPlanes supports at most 16 ranks (one node)")
+        if n_rx * n_freq > 1 and (grid_n * grid_n) % 4:
+            raise ValueError("PeerPlanes with more than one field needs grid_n**2 to be a multiple "
+                             f"of 4 (16-byte aligned planes for the P2P loads); got grid_n={grid_n}")
         self.shape = (n_rx, n_freq, grid_n)
         self.layout = L = peer_layout(n_rx, n_freq, grid_n)
         # Every step that can fail locally (allocation, export, mapping a peer) is followed by
@@ -216,29 +219,46 @@ class PeerPlanes:
         b0, b1 = slab_cells(n * n, self.world, self.rank)
         stream = ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
         self.barrier()  # every rank's trace has finished
-        for i in range(n_rx):
-            for f, (k, _, _) in enumerate(freq_specs):
-                fld = (i * n_freq + f) * n * n
-                _lib.check(self.lib.sosat_bins_reduce_field(
-                    self._c_peers, self.world, L["re"] + 4 * fld, L["im"] + 4 * fld,
-                    L["cnt"] + 4 * i * n * n, L["stats"] + 64 * i, b0, b1,
-                    geometry.scalar(k) / 1e3 / 2, float(opl_ref), c_out, len(dest),
-                    L["field"] + 8 * fld, ctypes.c_void_p(self.stats_sum[i].data_ptr()), stream))
+        ks = (ctypes.c_double * n_freq)(*[geometry.scalar(k) / 1e3 / 2 for k, _, _ in freq_specs])
+        # one launch for the whole stack of (receiver, frequency) fields (grid y = field)
+        _lib.check(self.lib.sosat_bins_reduce_fields(
+            self._c_peers, self.world, L["re"], L["im"], L["cnt"], L["stats"], n * n, n_rx, n_freq,
+            b0, b1, ks, float(opl_ref), c_out, len(dest), L["field"],
+            ctypes.c_void_p(self.stats_sum.data_ptr()), stream))
         self.barrier()  # every slab has landed; the planes may be overwritten
         return self.field
 
     def close(self):
+        """Collective: every rank of the group calls it.  The local buffer is freed only after
+        EVERY rank has unmapped it -- freeing exported memory that a peer still has open through
+        ``cudaIpcOpenMemHandle`` is undefined behaviour -- so the order is: drain this device,
+        close the mappings of the peers' buffers, exchange "closed" over the group (host-level
+        ``all_gather_object``, as in ``__init__``), then free."""
         import ctypes
+        import torch
         from . import _lib
+        if getattr(self, "_closed", False):
+            return
+        self._closed = True
+        if torch.cuda.is_available():
+            torch.cuda.synchronize()  # no reduce kernel of this rank still reads a peer
+        err = None
         for ptr in self._opened:
-            _lib.check(self.lib.sosat_peer_close(ctypes.c_void_p(ptr)))
+            try:
+                _lib.check(self.lib.sosat_peer_close(ctypes.c_void_p(ptr)))
+            except Exception as exc:  # noqa: BLE001 - still take part in the exchange below
+                err = exc
         self._opened = []
+        # every rank takes part, also one whose own allocation failed (base == 0)
+        self._exchange("closed")  # every peer has dropped its mapping of this rank's buffer
         if self.base:
             for name in ("re", "im", "cnt", "stats", "stats_sum", "field", "accum", "flat", "_raw"):
                 if hasattr(self, name):
                     setattr(self, name, None)
             _lib.check(self.lib.sosat_peer_free(ctypes.c_void_p(self.base)))
             self.base = 0
+        if err is not None:
+            raise err
 
 
 def near_field_binned_distributed(tele_geo, rx, grid_n: int, extent_cm: float,
@@ -293,3 +313,35 @@ def sweep_distributed(problems: Sequence, solve: Callable, group=None) -> list:
     for part in gathered:
         merged.update(part)
     return [merged[i] for i in range(len(problems))]
+
+
+def beam_sweep_distributed(tele_geo, rx_list, freqs, grid_n: int = 256,
+                           extent_cm: Optional[float] = None, pad: int = 0, group=None,
+                           sweep_fn: Optional[Callable] = None) -> dict:
+    """BASELINE configs[3] over the GPUs of a node: the receivers of a focal-plane sweep are
+    dealt round-robin to the ranks (:func:`partition_items`), every rank runs
+    :func:`ray_trace.beam_sweep` on its receivers (one fused trace+bin launch, one batched
+    far-field transform, one batched FWHM search) and the per-field scalars are gathered --
+    no data-path collective.  Every rank returns the dict of ``beam_sweep`` for ALL receivers,
+    in the order of ``rx_list``.  ``sweep_fn`` is injectable so that the dealing and the merge
+    can be exercised on CPU with ``gloo``; it defaults to the CUDA ``beam_sweep``."""
+    from . import ray_trace
+    dist = _dist()
+    rank, world = world_info(group)
+    sweep_fn = sweep_fn or ray_trace.beam_sweep
+    rx_arr = np.asarray(rx_list, dtype=np.float64).reshape(-1, 3)
+    mine = partition_items(len(rx_arr), world, rank)
+    part = sweep_fn(tele_geo, rx_arr[mine], freqs, grid_n, extent_cm, pad) if mine else None
+    if world == 1:
+        return part
+    gathered = [None] * world
+    dist.all_gather_object(gathered, (mine, part), group=group)
+    first = next(p for _, p in gathered if p is not None)
+    merged = {k: np.zeros((len(rx_arr),) + np.asarray(v).shape[1:], dtype=np.asarray(v).dtype)
+              for k, v in first.items()}
+    for idx, p in gathered:
+        if p is None:
+            continue
+        for k, v in p.items():
+            merged[k][idx] = v
+    return merged

@@ -101,13 +101,16 @@ def coords_ang_to_spat(theta_x, theta_y, freq):
     return x_spat, y_spat
 
 
-# --- DFT-GEMM workspaces: one per (device, n, transform kind), kept alive so the twiddles of
-# each kind are generated once ------------------------------------------------------------------
+# --- DFT-GEMM workspaces: one per (device, stream, n, transform kind), kept alive so the twiddles
+# of each kind are generated once.  The stream is part of the key because a workspace holds the
+# scratch of a transform in flight (b1 / d1 / c64) and its twiddles are written by a kernel on
+# the stream of the first call: two streams (or threads with their own streams) transforming the
+# same size must not share one. -----------------------------------------------------------------
 _workspaces = {}
 
 
 def _workspace(lib, torch, n: int, kind: int = _lib.DFT_FORWARD):
-    key = (torch.cuda.current_device(), int(n), int(kind))
+    key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream, int(n), int(kind))
     ws = _workspaces.get(key)
     if ws is None:
         nbytes = int(lib.sosat_dft2_workspace_bytes(int(n)))
@@ -285,10 +288,10 @@ def far_field_batch(b, *, device: bool = False):
     out = torch.empty((k, n, n), dtype=torch.complex64, device="cuda")
     if k == 0:
         return out if device else _lib.to_numpy(out)
-    key = (torch.cuda.current_device(), n, k)
+    key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream, n, k)
     ws = _batch_workspaces.get(key)
     if ws is None:
-        for old in [q for q in _batch_workspaces if q[:2] == key[:2]]:  # one stack size per n
+        for old in [q for q in _batch_workspaces if q[:3] == key[:3]]:  # one stack size per n
             del _batch_workspaces[old]
         nbytes = int(lib.sosat_dft2_batch_workspace_bytes(n, k))
         ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")

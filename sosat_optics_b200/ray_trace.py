@@ -35,7 +35,8 @@ from . import _lib, geometry
 
 __all__ = ["rx_to_lyot", "getNearField", "get_sim", "get_beam_cent", "get_fwhm",
            "get_angle_out", "ff_fwhm_est", "near_field_binned", "trace_stats",
-           "near_field_metrics", "near_field_samples", "ff_fwhm_device", "beam_sweep", "sim2d",
+           "near_field_metrics", "near_field_samples", "ff_fwhm_device", "ff_fwhm_indices_device",
+           "beam_sweep", "sim2d",
            "sim_data",
            "SimOutput", "BinnedField"]
 
@@ -245,25 +246,44 @@ def near_field_metrics(tele_geo, rx, freqs: Optional[Sequence] = None):
             "angle_out": np.array(get_angle_out(sb)), "fwhm": np.concatenate(res_all, axis=0)}
 
 
+def ff_fwhm_indices_device(B):
+    """The searches of ``ff_fwhm_est`` for a stack of far fields ``B`` [K, N, N] (CUDA complex64)
+    in one launch per search and ONE read-back: returns ``(idx int32 [K, 6], peak_abs2 float32
+    [K])`` as numpy arrays, ``idx`` = peak row, peak column, first / last column above half power
+    in the peak row, first / last row above half power in the peak column.  Raises ``ValueError``
+    if a field has no finite non-zero cell (NaN in the near field)."""
+    lib = _lib.require_gpu()
+    torch = _torch()
+    k, n = int(B.shape[0]), int(B.shape[-1])
+    res = torch.empty((k, 8), dtype=torch.int32, device="cuda")  # [idx x 6 | val bits | pad]
+    idx = torch.empty((k, 6), dtype=torch.int32, device="cuda")
+    val = torch.empty(k, dtype=torch.float32, device="cuda")
+    work = torch.empty(k, dtype=torch.int64, device="cuda")
+    _lib.check(lib.sosat_ff_fwhm_indices_batch(
+        ctypes.c_void_p(B.data_ptr()), n, k, ctypes.c_void_p(idx.data_ptr()),
+        ctypes.c_void_p(val.data_ptr()), ctypes.c_void_p(work.data_ptr()), _stream(torch)))
+    res[:, :6] = idx
+    res[:, 6] = val.view(torch.int32)
+    h = _lib.to_numpy(res)
+    h_idx, h_val = h[:, :6].copy(), h[:, 6].copy().view(np.float32)
+    bad = np.nonzero((h_idx < 0).any(axis=1))[0]
+    if bad.size:
+        raise ValueError(f"far field {bad.tolist()[:8]} has no finite non-zero cell (NaN or all-zero "
+                         "near field): no beam peak to measure")
+    return h_idx, h_val
+
+
 def ff_fwhm_device(beam_fft, x_ang, y_ang):
     """``ff_fwhm_est`` (ray_trace.py:1757-1779) for a far field that lives on the GPU
     (``far_field(..., device=True)``): the peak and half-power searches run on the device and
     only six indices come back.  ``x_ang`` / ``y_ang``: the label grids of
     ``coords_spat_to_ang`` (host arrays)."""
-    lib = _lib.require_gpu()
     torch = _torch()
     B = beam_fft if not isinstance(beam_fft, np.ndarray) else torch.from_numpy(
         np.ascontiguousarray(beam_fft.astype(np.complex64))).to("cuda")
     B = B.to(device="cuda", dtype=torch.complex64).contiguous()
-    n = B.shape[0]
-    idx = torch.empty(6, dtype=torch.int32, device="cuda")
-    val = torch.empty(1, dtype=torch.float32, device="cuda")
-    work = torch.empty(1, dtype=torch.int64, device="cuda")
-    _lib.check(lib.sosat_ff_fwhm_indices(ctypes.c_void_p(B.data_ptr()), n,
-                                         ctypes.c_void_p(idx.data_ptr()),
-                                         ctypes.c_void_p(val.data_ptr()),
-                                         ctypes.c_void_p(work.data_ptr()), _stream(torch)))
-    pr, pc, c0, c1, r0, r1 = (int(v) for v in _lib.to_numpy(idx))
+    idx, _ = ff_fwhm_indices_device(B.unsqueeze(0))
+    pr, pc, c0, c1, r0, r1 = (int(v) for v in idx[0])
     x_out, y_out = y_ang, x_ang  # the reference's swap, ray_trace.py:1759-1760
     scale = 60 * 180 / np.pi
     fwhm1 = abs(y_out[pr, c0] * scale - y_out[pr, c1] * scale)
@@ -400,13 +420,12 @@ def bins_to_field_device(re, im, cnt, stats, freq_specs, opl_ref=0.0, *, sync: b
     n_rx, n_freq, n, _ = re.shape
     b = torch.empty((n_rx, n_freq, n, n, 2), dtype=torch.float32, device="cuda")
     if not sync:
-        for i in range(n_rx):
-            for f, (k, _, _) in enumerate(freq_specs):
-                _lib.check(lib.sosat_bins_to_field_stats(
-                    ctypes.c_void_p(re[i, f].data_ptr()), ctypes.c_void_p(im[i, f].data_ptr()),
-                    ctypes.c_void_p(cnt[i].data_ptr()), n * n, ctypes.c_void_p(stats[i].data_ptr()),
-                    geometry.scalar(k) / 1e3 / 2, float(opl_ref),
-                    ctypes.c_void_p(b[i, f].data_ptr()), _stream(torch)))
+        # one launch for the whole stack of (receiver, frequency) fields
+        ks = (ctypes.c_double * n_freq)(*[geometry.scalar(k) / 1e3 / 2 for k, _, _ in freq_specs])
+        _lib.check(lib.sosat_bins_to_field_stats_batch(
+            ctypes.c_void_p(re.data_ptr()), ctypes.c_void_p(im.data_ptr()),
+            ctypes.c_void_p(cnt.data_ptr()), n * n, n_rx, n_freq, ctypes.c_void_p(stats.data_ptr()),
+            ks, float(opl_ref), ctypes.c_void_p(b.data_ptr()), _stream(torch)))
         return torch.view_as_complex(b), None
     h_stats = _lib.to_numpy(stats)
     for i in range(n_rx):
@@ -443,14 +462,15 @@ def near_field_binned(tele_geo, rx, grid_n: int = 256, extent_cm: Optional[float
     for f0 in range(0, len(specs), _lib.MAX_FREQS):
         chunk = specs[f0:f0 + _lib.MAX_FREQS]
         re, im, cnt, stats = trace_bin_device(tele_geo, rx_arr, chunk, grid_n, extent_cm * 10.0)
-        b, h_stats = bins_to_field_device(re, im, cnt, stats, chunk)
+        b, _ = bins_to_field_device(re, im, cnt, stats, chunk, sync=False)  # one launch, no sync
         out_b.append(b)
-        out_c, out_s = cnt, h_stats
+        out_c, out_s = cnt, stats
         if keep_sums:
             out_re.append(re)
             out_im.append(im)
     torch = _torch()
-    b = torch.cat(out_b, dim=1)
+    out_s = _lib.to_numpy(out_s)  # the only read-back of the statistics (identical for every chunk)
+    b = torch.cat(out_b, dim=1) if len(out_b) > 1 else out_b[0]
     re = torch.cat(out_re, dim=1) if keep_sums else None
     im = torch.cat(out_im, dim=1) if keep_sums else None
     if not device:
@@ -479,36 +499,43 @@ def beam_sweep(tele_geo, rx_list, freqs, grid_n: int = 256, extent_cm: Optional[
     specs = list(freqs)
     if len(specs) > _lib.MAX_FREQS:
         raise ValueError(f"at most {_lib.MAX_FREQS} frequencies per sweep call")
-    bf = near_field_binned(tele_geo, rx_list, grid_n, extent_cm, specs, device=True)
-    n_rx, n_freq = bf.b.shape[:2]
-    fields = bf.b.reshape(n_rx * n_freq, grid_n, grid_n)
-    if pad > 0:
-        fields = torch.nn.functional.pad(fields, (pad, pad, pad, pad))
-    n = fields.shape[-1]
-    B = opt_analyze.far_field_batch(fields, device=True)
-    dx_m = extent_cm / grid_n / 100.0
-    fwhm = np.zeros((n_rx, n_freq))
-    peak = np.zeros((n_rx, n_freq))
-    pidx = np.zeros((n_rx, n_freq, 2), dtype=np.int64)
-    lib = _lib.require_gpu()
-    idx = torch.empty(6, dtype=torch.int32, device="cuda")
-    val = torch.empty(1, dtype=torch.float32, device="cuda")
-    work = torch.empty(1, dtype=torch.int64, device="cuda")
-    for i in range(n_rx):
-        for f, (k, _, _) in enumerate(specs):
-            _lib.check(lib.sosat_ff_fwhm_indices(
-                ctypes.c_void_p(B[i * n_freq + f].data_ptr()), n, ctypes.c_void_p(idx.data_ptr()),
-                ctypes.c_void_p(val.data_ptr()), ctypes.c_void_p(work.data_ptr()), _stream(torch)))
-            pr, pc, c0, c1, r0, r1 = (int(v) for v in _lib.to_numpy(idx))
-            lam = 2 * np.pi / geometry.scalar(k)
-            dth = lam / (n * dx_m) * (180 * 60 / np.pi)  # arcmin per far-field cell
-            fwhm[i, f] = 0.5 * (abs(c1 - c0) + abs(r1 - r0)) * dth
-            peak[i, f] = float(np.sqrt(_lib.to_numpy(val)[0]))
-            pidx[i, f] = (pr, pc)
-    st = bf.stats
-    return {"fwhm_arcmin": fwhm, "peak": peak, "peak_index": pidx,
+    rx_arr = np.asarray(rx_list, dtype=np.float64).reshape(-1, 3)
+    n_freq, n_far = len(specs), grid_n + 2 * pad
+    # receivers per pass: the far-field stack and its workspace (~80 B per padded cell and field)
+    # stay below ~12 GB however long the receiver list is
+    per_pass = max(1, min(int(12e9 // (80 * n_far * n_far * n_freq)), 4096 // n_freq))
+    parts = []
+    for r0 in range(0, rx_arr.shape[0], per_pass):
+        rxs = rx_arr[r0:r0 + per_pass]
+        re, im, cnt, stats = trace_bin_device(tele_geo, rxs, specs, grid_n, extent_cm * 10.0)
+        b, _ = bins_to_field_device(re, im, cnt, stats, specs, sync=False)
+        del re, im, cnt
+        fields = b.reshape(len(rxs) * n_freq, grid_n, grid_n)
+        if pad > 0:
+            fields = torch.nn.functional.pad(fields, (pad, pad, pad, pad))
+        B = opt_analyze.far_field_batch(fields, device=True)
+        del fields, b
+        parts.append(_sweep_scalars(B, _lib.to_numpy(stats), specs, len(rxs),
+                                    extent_cm / grid_n / 100.0))
+        del B
+    if len(parts) == 1:
+        return parts[0]
+    return {k: np.concatenate([p[k] for p in parts], axis=0) for k in parts[0]}
+
+
+def _sweep_scalars(B, stats, specs, n_rx, dx_m):
+    """Far-field FWHM / peak of every field of a sweep: ONE batched search, ONE read-back."""
+    n_freq, n = len(specs), int(B.shape[-1])
+    idx, val = ff_fwhm_indices_device(B)
+    idx = idx.reshape(n_rx, n_freq, 6).astype(np.int64)
+    lam = np.array([2 * np.pi / geometry.scalar(k) for k, _, _ in specs])
+    dth = lam / (n * dx_m) * (180 * 60 / np.pi)  # arcmin per far-field cell
+    fwhm = 0.5 * (np.abs(idx[..., 3] - idx[..., 2]) + np.abs(idx[..., 5] - idx[..., 4])) * dth[None, :]
+    st = np.asarray(stats)
+    return {"fwhm_arcmin": fwhm, "peak": np.sqrt(val.astype(np.float64)).reshape(n_rx, n_freq),
+            "peak_index": idx[..., :2].copy(),
             "n_valid": st[:, _lib.STAT_N_VALID].copy(), "n_binned": st[:, _lib.STAT_N_BINNED].copy(),
-            "mean_opl": bf.mean_opl}
+            "mean_opl": st[:, _lib.STAT_SUM_OPL] / np.maximum(st[:, _lib.STAT_N_VALID], 1)}
 
 
 def trace_stats(tele_geo, rx):

@@ -128,6 +128,71 @@ def test_two_gpu_peer_memory_reduce_matches_single_gpu():
             assert np.allclose(stats[:, 1], one.stats[:, 1], rtol=1e-12)
 
 
+def _sweep_setup():
+    from sosat_optics_b200 import geometry, opt_analyze, ot_geo
+    t = ot_geo.SatGeo()
+    t.n_scan = 300
+    t.y_source = ot_geo.y_lyot + 300
+    t.lambda_ = opt_analyze.ghz_to_m(90)
+    t.k = 2 * np.pi / t.lambda_
+    table = np.load(os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden",
+                                 "feedhorn_fwhm.npz"))["table"]
+    specs = geometry.freq_specs_from_table([90.0, 150.0], table)
+    g = np.linspace(-120, 120, 3)
+    rxs = np.array([[x, 0.0, z] for x in g for z in g][:7])   # 7 receivers: an uneven deal
+    return t, rxs, specs
+
+
+def _sweep_worker(rank, world, port, q):
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank),
+                      WORLD_SIZE=str(world), LOCAL_RANK=str(rank))
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import torch
+    import torch.distributed as dist
+    torch.cuda.set_device(rank)
+    dist.init_process_group("nccl", rank=rank, world_size=world,
+                            device_id=torch.device("cuda", rank))
+    try:
+        from sosat_optics_b200 import dist as sdist
+        t, rxs, specs = _sweep_setup()
+        res = sdist.beam_sweep_distributed(t, rxs, specs, grid_n=128, extent_cm=42.0, pad=64)
+        q.put((rank, res))
+    finally:
+        dist.destroy_process_group()
+
+
+def test_two_gpu_receiver_sweep_matches_single_gpu():
+    """BASELINE configs[3] sharded over 2 GPUs (receivers round-robin, scalars gathered) gives,
+    on every rank, exactly what the single-GPU beam_sweep gives for the whole receiver list."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    import torch.multiprocessing as mp
+    from sosat_optics_b200 import ray_trace
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_sweep_worker, args=(r, 2, port, q)) for r in range(2)]
+    [p.start() for p in procs]
+    res = sorted([q.get(timeout=300) for _ in procs], key=lambda r: r[0])
+    [p.join(60) for p in procs]
+    assert all(p.exitcode == 0 for p in procs)
+    t, rxs, specs = _sweep_setup()
+    one = ray_trace.beam_sweep(t, rxs, specs, grid_n=128, extent_cm=42.0, pad=64)
+    assert one["fwhm_arcmin"].shape == (7, 2) and (one["fwhm_arcmin"] > 0).all()
+    for rank, got in res:
+        assert set(got) == set(one)
+        for k in ("n_valid", "n_binned", "peak_index"):
+            assert np.array_equal(got[k], one[k]), (rank, k)
+        assert np.allclose(got["mean_opl"], one["mean_opl"], rtol=1e-13)
+        # the binning's fp32 atomics are order dependent: far-field scalars agree to that level
+        assert np.allclose(got["peak"], one["peak"], rtol=1e-4)
+        lam = np.array([2 * np.pi / float(k) for k, _, _ in specs])
+        cell = lam / (256 * (42.0 / 128 / 100.0)) * (180 * 60 / np.pi)   # arcmin per far-field cell
+        assert (np.abs(got["fwhm_arcmin"] - one["fwhm_arcmin"]) <= 1.001 * cell[None, :]).all()
+        assert np.mean(got["fwhm_arcmin"] == one["fwhm_arcmin"]) >= 0.8
+
+
 def test_side_stream_and_second_device_in_one_process():
     """The library launches on the caller's current stream and keeps per-device state
     (geometry in __constant__ memory, DFT plans): the same calls on a side stream, and on

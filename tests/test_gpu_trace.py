@@ -322,7 +322,7 @@ def test_binned_row_blocks_add_up(mods):
     assert stats[0, 1].item() == pytest.approx(st[0, 1].item(), rel=1e-12)
 
 
-def test_full_size_bundle_properties(mods):
+def test_quarter_size_bundle_properties_16384(mods):
     """cfg 5 shape at reduced ray count (2.7e8 rays, 2048^2 grid): size-independent properties
     -- every valid in-grid ray is counted once, boresight counts are mirror symmetric, the
     statistics pass agrees with the binning pass, |sum| <= count."""
@@ -625,6 +625,21 @@ def test_peer_reduce_kernel_on_one_device(mods, feed_table):
         assert views[1]["field"].abs().max().item() == 0.0  # not a destination
         assert torch.equal(ssum[:, [0, 7]], st[:, [0, 7]])
         assert torch.allclose(ssum[:, 1], st[:, 1], rtol=1e-12)
+        # the same in ONE launch per "rank" for the whole stack of fields (grid y = field)
+        for d in (0, 2):
+            views[d]["field"].zero_()
+        ssum.zero_()
+        ks = (ctypes.c_double * n_freq)(*[geometry.scalar(k) / 1e3 / 2 for k, _, _ in specs])
+        for rank in range(3):
+            b0, b1 = sdist.slab_cells(n * n, 3, rank)
+            _lib.check(lib.sosat_bins_reduce_fields(
+                c_peers, 3, L["re"], L["im"], L["cnt"], L["stats"], n * n, n_rx, n_freq, b0, b1, ks,
+                0.0, c_out, 2, L["field"], ctypes.c_void_p(ssum.data_ptr()), stream))
+        torch.cuda.synchronize()
+        for d in (0, 2):
+            got = torch.view_as_complex(views[d]["field"])
+            assert (got - want).abs().max().item() < 3e-6 * want.abs().max().item()
+        assert torch.equal(ssum[:, [0, 7]], st[:, [0, 7]])
         rc = lib.sosat_bins_reduce_field(c_peers, 3, L["re"], L["im"], L["cnt"], L["stats"], 2, 8,
                                          1.0, 0.0, c_out, 2, L["field"], None, stream)
         assert rc != 0 and b"multiple of 4" in lib.sosat_last_error()
@@ -701,3 +716,79 @@ def test_full_size_bundle_properties(mods):
     mean_full = s[_lib.STAT_SUM_OPL] / s[_lib.STAT_N_VALID]
     mean_coarse = sc[_lib.STAT_SUM_OPL] / sc[_lib.STAT_N_VALID]
     assert abs(mean_full - mean_coarse) < 2e-2                      # mm, of ~1.1e3 mm
+
+
+@pytest.mark.parametrize("rx", [[0.0, 0.0, 0.0], [90.0, 0.0, -60.0]])
+@pytest.mark.parametrize("where", ["first", "middle", "last"])
+def test_full_size_row_blocks_against_the_oracle(mods, rx, where):
+    """configs[4] at its benchmarked n_scan = 31623: 16-row blocks of the launch grid (first rows
+    = edge of the cone, middle rows = through the axis, last rows incl. the ragged final tile)
+    traced + binned by the fused kernel and compared with the oracle's trace + binning of exactly
+    those rays -- statistics exact, planes to the fp32 accumulation bound."""
+    rt, oracle = mods["rt"], mods["oracle"]
+    n_scan = 31623
+    t = _bundle(mods, n_scan)
+    spec = [(t.k, t.th_fwhp_x, t.th_fwhp_y)]
+    r0 = {"first": 0, "middle": n_scan // 2 - 8, "last": n_scan - 16}[where]
+    re, im, cnt, st = rt.trace_bin_device(t, [rx], spec, 2048, 420.0, row_begin=r0, row_end=r0 + 16)
+    ref = oracle.rx_to_lyot(rx, t, ray_begin=r0 * n_scan, ray_end=(r0 + 16) * n_scan)
+    rre, rim, rcnt, sums = oracle.bin_near_field(ref, float(t.k), 2048, 420.0, 0.0)
+    st = st.cpu().numpy()[0]
+    assert int(st[0]) == sums["n_valid"] and int(st[7]) == sums["n_binned"]
+    if sums["n_valid"]:
+        assert st[1] == pytest.approx(sums["sum_opl"], rel=1e-12)
+    assert int(st[6]) == 0
+    c = cnt[0].cpu().numpy()
+    assert np.abs(c - rcnt).sum() <= max(4, 1e-5 * rcnt.sum())     # rays sitting on a cell edge
+    scale = max(np.abs(rre).max(), np.abs(rim).max(), 1e-30)
+    assert np.abs(re[0, 0].cpu().numpy() - rre).max() < 2e-3 * scale
+    assert np.abs(im[0, 0].cpu().numpy() - rim).max() < 2e-3 * scale
+
+
+def test_far_field_of_the_real_binned_2048_field_against_fp64_fft(mods):
+    """The far field of the REAL 2048^2 binned near field (n_scan = 8192: 6.7e7 rays, 16 per
+    cell) against numpy's FFT in complex128: < 1e-4 of the peak (north_star), and the binned
+    field itself is what the bench transforms."""
+    rt, oa, torch = mods["rt"], mods["oa"], mods["torch"]
+    t = _bundle(mods, 8192)
+    bf = rt.near_field_binned(t, [0, 0, 0], grid_n=2048, extent_cm=42.0, device=True)
+    b = bf.b[0, 0]
+    B = oa.far_field(b, device=True)
+    hb = b.cpu().numpy().astype(np.complex128)
+    ref = np.fft.fftshift(np.fft.fft2(np.fft.fftshift(hb)))
+    peak = np.abs(ref).max()
+    assert peak > 0 and np.count_nonzero(hb) > 0.5 * 2048 ** 2 * np.pi / 4 * (40 / 42) ** 2
+    err = np.abs(B.cpu().numpy() - ref).max()
+    assert err < 1e-4 * peak, err / peak
+
+
+def test_ff_fwhm_search_batch_and_nan_guard(mods):
+    """sosat_ff_fwhm_indices_batch: a stack of fields in one launch equals the single-field
+    searches; a field with a NaN (or all zeros) reports -1 indices and the wrapper raises instead
+    of indexing with garbage."""
+    rt, torch = mods["rt"], mods["torch"]
+    g = torch.Generator(device="cuda").manual_seed(5)
+    n = 97
+    yy, xx = torch.meshgrid(torch.arange(n, device="cuda"), torch.arange(n, device="cuda"), indexing="ij")
+    stack = []
+    for cy, cx, w in ((48, 48, 9.0), (30, 60, 5.0), (70, 20, 14.0)):
+        amp = torch.exp(-((yy - cy) ** 2 + (xx - cx) ** 2) / (2 * w * w))
+        stack.append((amp * torch.exp(1j * torch.rand((n, n), device="cuda", generator=g))).to(torch.complex64))
+    B = torch.stack(stack)
+    idx, val = rt.ff_fwhm_indices_device(B)
+    for i, (cy, cx, w) in enumerate(((48, 48, 9.0), (30, 60, 5.0), (70, 20, 14.0))):
+        one, v1 = rt.ff_fwhm_indices_device(B[i:i + 1].contiguous())
+        assert np.array_equal(one[0], idx[i]) and v1[0] == val[i]
+        a = (B[i].abs() ** 2).cpu().numpy()
+        pr, pc = np.unravel_index(np.argmax(a), a.shape)
+        assert (idx[i][0], idx[i][1]) == (pr, pc) == (cy, cx)
+        row = np.nonzero(a[pr] / a.max() > 0.5)[0]
+        col = np.nonzero(a[:, pc] / a.max() > 0.5)[0]
+        assert list(idx[i][2:]) == [row[0], row[-1], col[0], col[-1]]
+    bad = B.clone()
+    bad[1, 3, 4] = float("nan")
+    bad[1] = bad[1] * float("nan")      # what the contraction does to a NaN in the near field
+    with pytest.raises(ValueError, match="no finite"):
+        rt.ff_fwhm_indices_device(bad)
+    with pytest.raises(ValueError, match="no finite"):
+        rt.ff_fwhm_indices_device(torch.zeros((1, n, n), dtype=torch.complex64, device="cuda"))

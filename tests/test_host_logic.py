@@ -123,6 +123,24 @@ def _worker(rank, world, port, q):
         b, cnt, stats = sdist.near_field_binned_distributed(
             t, [[0, 0, 0], [60, 0, -90]], 16, 42.0, trace_fn=_oracle_trace_fn, field_fn=_field_fn)
         sweep = sdist.sweep_distributed(list(range(5)), lambda p: (p, rank))
+        # configs[3]: receivers dealt round-robin, per-field scalars merged in receiver order
+        rxs = np.array([[10.0 * i, 0.0, -5.0 * i] for i in range(5)])
+        calls = []
+
+        def fake_sweep(tele_geo, rx, freqs, grid_n, extent_cm, pad):
+            calls.append(rx.copy())
+            return {"fwhm_arcmin": rx[:, :1] * np.arange(1, len(freqs) + 1)[None, :],
+                    "peak_index": np.repeat(rx[:, None, None, 0], 2, axis=2).repeat(len(freqs), 1).astype(np.int64),
+                    "n_valid": rx[:, 2] - 1.0}
+        bs = sdist.beam_sweep_distributed(t, rxs, [1, 2, 3], 8, 42.0, 0, sweep_fn=fake_sweep)
+        assert len(calls) == 1 and np.array_equal(calls[0], rxs[rank::world])
+        assert np.array_equal(bs["fwhm_arcmin"], rxs[:, :1] * np.arange(1, 4)[None, :])
+        assert bs["peak_index"].shape == (5, 3, 2) and bs["peak_index"].dtype == np.int64
+        assert np.array_equal(bs["peak_index"][:, 0, 0], rxs[:, 0].astype(np.int64))
+        assert np.array_equal(bs["n_valid"], rxs[:, 2] - 1.0)
+        # more ranks than receivers: the idle rank still takes part in the gather
+        one = sdist.beam_sweep_distributed(t, rxs[:1], [1], 8, 42.0, 0, sweep_fn=fake_sweep)
+        assert one["fwhm_arcmin"].shape == (1, 1) and one["n_valid"][0] == -1.0
         # the single-buffer form bench.py uses: planes are views of one flat tensor, one collective
         re, im, c2, flat = sdist.alloc_planes(2, 1, 16, device="cpu")
         st = torch.zeros((2, 8), dtype=torch.float64)
