@@ -329,7 +329,7 @@ def other_configs(torch, ot_geo, opt_analyze, ray_trace, table):
 def cfg3_sweep(torch, dist, sdist, ot_geo, opt_analyze, ray_trace, table, world, rank):
     """BASELINE.json configs[3]: focal-plane receiver sweep, near + far field, receivers dealt
     round-robin to the ranks (no data-path collective; scalars gathered).  All ranks call it."""
-    g = np.linspace(-150, 150, 18)
+    g = np.linspace(-150, 150, 20)
     rxs = np.array([[x, 0.0, z] for x in g for z in g if np.hypot(x, z) <= 150.0])
     t = _tele_geo(ot_geo, opt_analyze, table, 1000)
     spec = [(t.k, t.th_fwhp_x, t.th_fwhp_y)]

@@ -154,26 +154,22 @@ constexpr int kTile = 16;  // rays per tile edge in theta
 // A CTA of kBinWarps warps traces a 16 (theta) x kTileH (phi) patch of the launch grid, one 8 x 4
 // sub-patch per warp.  Measured (1e9 rays): 8 warps 1.74e10 rays/s, 16 warps +0.3 %, 4 warps
 // -1.6 %, 2 warps -4 %, barrier-free per-warp patches -4 %: warps that run in step share
-// instruction-cache lines of the 21 KB straight-line hot path, which outweighs the barrier skew.
+// instruction-cache lines of the straight-line hot path, which outweighs the barrier skew.
 #ifndef SOSAT_BIN_WARPS
 #define SOSAT_BIN_WARPS 8
 #endif
 constexpr int kBinWarps = SOSAT_BIN_WARPS;
 constexpr int kBinThreads = 32 * kBinWarps;
 constexpr int kTileH = 2 * kBinWarps;
-// Rays per thread: with kNR = 2 a thread traces two rays 16 launch columns apart in the same
-// straight-line block (tile = 32 x kTileH), so that ptxas can interleave the two independent
-// dependency chains; costs twice the registers (2 CTAs/SM instead of 4).
-#ifndef SOSAT_BIN_NR
-#define SOSAT_BIN_NR 1
-#endif
-constexpr int kNR = SOSAT_BIN_NR;
 // (A shared-memory bin window per CTA -- north_star's "shuffle, then shared-memory atomics" --
 // was built and measured at -8 %: after the run-length aggregation a warp issues only 3-6
-// global reductions per 32 rays.  DESIGN.md section 3; the code is in the history, commit
-// 3515e61.)
-constexpr int kTileW = kTile * kNR;
+// global reductions per 32 rays.  Two rays per thread, skewed by half a surface so that the fp32
+// steps of one ray sit next to the fp64 step of the other: -0.8 %, 128 registers.  DESIGN.md
+// section 3; the code is in the history, commits 3515e61 and 95805ee.)
+constexpr int kTileW = kTile;
 constexpr int kTileMax = kTileH > kTileW ? kTileH : kTileW;
+// seed history of the predicted-seed tracer: 2 tiles x 6 surfaces x one double per thread
+constexpr int kHistBytes = 2 * SOSAT_NUM_SURFACES * kBinThreads * (int)sizeof(double);
 
 struct BinFreq {
     float neg_c_fx[SOSAT_MAX_FREQS];  // -4 ln2 / fwhp_x^2
@@ -188,29 +184,42 @@ struct BinParams {
     long long row_begin;
     int n_scan, n_rows, n_rx, n_freq, grid_n;
     int tiles_x, tiles_y;
-    long long n_tiles;
+    int strip_len, strips_x;  // a strip = strip_len adjacent tiles along theta (the last may be shorter)
+    int predict;              // seeds of a tile predicted from the lane's last two tiles
+    long long n_strips;
 };
 
-// Persistent CTAs loop over 16 x 16 patches of the launch grid; a warp owns an 8 (theta) x 4
-// (phi) sub-patch, so its 32 rays land in a handful of neighbouring bins.  Binning is a
-// run-length aggregation along the lane order: every maximal run of consecutive lanes with the
-// same bin is summed into its first lane by a segmented shuffle reduction (5 steps whatever the
-// ray density), and that lane issues one red.global.add.f32 per plane.  Because the optical
-// map (theta, phi) -> (x, z) is smooth, the runs are long: 1-2 per warp at 240 rays/bin
-// (configs[4]), one per row of 8 at 15 rays/bin.  Any key sequence is handled correctly --
-// equal bins that are not adjacent in lane order simply become separate atomics.
+// Persistent CTAs walk STRIPS of adjacent 16 x 16 patches of the launch grid (strips dealt
+// round-robin); a warp owns an 8 (theta) x 4 (phi) sub-patch, so its 32 rays land in a handful
+// of neighbouring bins.
+// * Seeds: from the third tile of a strip on, a warp whose 32 lanes all hold a finite two-tile
+//   history takes the predicted-seed tracer (trace_device.cuh: one fp64 Newton step from
+//   2 t(x-1) - t(x-2)); the first two tiles, ragged edge tiles, warps with a lane whose history
+//   is NaN (outside the conic domain of lens 1b) or was re-traced, and launch grids too coarse
+//   for the extrapolation (p.predict = 0) take the fp32 Newton + Halley pre-iterations.
+// * Tables: sin / cos of the 16 phi rows once per strip, of the 16 theta columns per tile, double
+//   buffered (the columns of tile x + 1 are filled while tile x is traced): ONE barrier per tile.
+// * Binning: run-length aggregation along the lane order: every maximal run of consecutive lanes
+//   with the same bin is summed into its first lane by a segmented shuffle reduction (5 steps
+//   whatever the ray density), and that lane issues one red.global.add.f32 per plane.  Because
+//   the optical map (theta, phi) -> (x, z) is smooth, the runs are long: 1-2 per warp at 240
+//   rays/bin (configs[4]), one per row of 8 at 15 rays/bin.  Any key sequence is handled
+//   correctly -- equal bins that are not adjacent in lane order simply become separate atomics.
 template <int N32, int N64, int MINB, int GEO>
-__global__ void __launch_bounds__(kBinThreads, MINB * 8 / kBinWarps / kNR)
+__global__ void __launch_bounds__(kBinThreads, MINB * 8 / kBinWarps)
 trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict__ re,
                  float *__restrict__ im, float *__restrict__ cnt, double *__restrict__ stats) {
-    __shared__ double s_sin[2][kTileMax], s_cos[2][kTileMax], s_rx[4];
+    constexpr bool kCanPredict = N32 == 2 && N64 == 1;
+    extern __shared__ double s_hist[];  // [2][surface][thread], only when p.predict
+    __shared__ double s_sin_t[2][kTile], s_cos_t[2][kTile], s_sin_p[kTileH], s_cos_p[kTileH], s_rx[4];
     // Launch-angle tables, filled once per CTA: sin/cos of  l step (l < 16),  16 j step (j < 64)
     // and  start + 1024 k step (k < 64).  The angle of grid index i = l + 16 j + 1024 k is
     // start + i step (numpy.linspace, ray_trace.py:1086-1087); its sine and cosine follow from
     // two angle additions (8 DFMA/DMUL, ~3e-16 relative) instead of an fp64 sincos per tile
     // edge on the critical path in front of the tile barrier.
     __shared__ double2 s_rot[16 + 64 + 64];
-    __shared__ float s_amp[SOSAT_MAX_FREQS][2][kTileMax];  // [freq][theta|phi][index in tile]
+    __shared__ float s_amp_t[2][SOSAT_MAX_FREQS][kTile];  // [buffer][freq][column in tile]
+    __shared__ float s_amp_p[SOSAT_MAX_FREQS][kTileH];    // [freq][row in tile]
     // Running statistics.  fp64 sums: one shared-memory slot per thread (no conflicts, no
     // registers held across the tracer).  Counters: warp ballots added by lane 0 to its warp's
     // shared slot (a 64-bit shared atomicAdd is a CAS loop: 25 instructions per warp and ray,
@@ -239,9 +248,6 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
         }
     }
     int acc_rx = -1;
-    // tile bookkeeping in 32 bits (the host checks n_tiles < 2^31): 64-bit divisions cost
-    // ~100 instructions per tile otherwise
-    const unsigned tiles_per_rx = (unsigned)p.tiles_x * (unsigned)p.tiles_y;
     const long long plane = (long long)p.grid_n * p.grid_n;
 
     auto flush_stats = [&](int irx_done) {
@@ -272,108 +278,112 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
         if (t0) s_rare[0] = s_rare[1] = 0u;
     };
 
-    // tile = (irx, ty, tx): divided out once per CTA and then advanced by the grid stride with
-    // carries (the three 32-bit divisions per tile were 45 instructions per ray, measured)
-    const unsigned n_tiles = (unsigned)p.n_tiles, ntx = (unsigned)p.tiles_x, nty = (unsigned)p.tiles_y;
-    unsigned u_rx = blockIdx.x / tiles_per_rx, u_ty, u_tx;
-    {
-        const unsigned trem = blockIdx.x - u_rx * tiles_per_rx;
-        u_ty = trem / ntx;
-        u_tx = trem - u_ty * ntx;
-    }
-    const unsigned step_rx = gridDim.x / tiles_per_rx;
-    const unsigned step_rem = gridDim.x - step_rx * tiles_per_rx;
-    const unsigned step_ty = step_rem / ntx, step_tx = step_rem - step_ty * ntx;
-    auto next_tile = [&]() {
-        u_tx += step_tx;
-        unsigned carry = u_tx >= ntx ? 1u : 0u;
-        u_tx -= carry ? ntx : 0u;
-        u_ty += step_ty + carry;
-        carry = u_ty >= nty ? 1u : 0u;
-        u_ty -= carry ? nty : 0u;
-        u_rx += step_rx + carry;
+    // sin / cos / Gaussian feed factors of launch-grid index idx (clamped to the grid edge: lanes
+    // past it trace the edge ray so that whole warps stay converged; their result is dropped)
+    auto fill_entry = [&](int idx, double &sn, double &cs, float &a2) {
+        const int ic = idx < p.n_scan ? idx : p.n_scan - 1;
+        const double a = linspace_at(p.lin_start, p.lin_stop, p.lin_step, p.n_scan, ic);
+        if (use_rot) {
+            const double2 ra = s_rot[ic & 15], rb = s_rot[16 + ((ic >> 4) & 63)],
+                          rc = s_rot[80 + (ic >> 10)];
+            const double s1 = fma(rc.x, rb.y, rc.y * rb.x), c1 = fma(rc.y, rb.y, -(rc.x * rb.x));
+            sn = fma(s1, ra.y, c1 * ra.x);
+            cs = fma(c1, ra.y, -(s1 * ra.x));
+        } else {
+            sincos(a, &sn, &cs);
+        }
+        const float af = (float)(a - kHalfPi);  // -de_ho (theta) / de_ve (phi), ray_trace.py:1529-1532
+        a2 = af * af;
     };
-    for (unsigned tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, next_tile()) {
-        const int irx = (int)u_rx, ty = (int)u_ty, tx = (int)u_tx;
+    // theta columns of tile tx into buffer b (threads 0..15)
+    auto fill_theta = [&](int tx, int b) {
+        double sn, cs;
+        float a2;
+        fill_entry(tx * kTileW + tid, sn, cs, a2);
+        s_sin_t[b][tid] = sn;
+        s_cos_t[b][tid] = cs;
+        // separable Gaussian feed taper a = A_theta[i] A_phi[j] (ray_trace.py:1573-1577)
+        for (int f = 0; f < p.n_freq; ++f) s_amp_t[b][f][tid] = expf(g_freq.neg_c_fx[f] * a2);
+    };
+
+    const unsigned strips_per_rx = (unsigned)p.strips_x * (unsigned)p.tiles_y;
+    double *const my_hist = s_hist + tid;
+    constexpr int kHistStride = kBinThreads;
+    for (long long strip = blockIdx.x; strip < p.n_strips; strip += gridDim.x) {
+        const int irx = (int)(strip / strips_per_rx);
+        const unsigned srem = (unsigned)(strip - (long long)irx * strips_per_rx);
+        const int ty = (int)(srem / (unsigned)p.strips_x), sx = (int)(srem - (unsigned)ty * p.strips_x);
+        const int tx_begin = sx * p.strip_len;
+        const int tx_end = min(tx_begin + p.strip_len, p.tiles_x);
         if (irx != acc_rx) {
             if (acc_rx >= 0) flush_stats(acc_rx);
             acc_rx = irx;
         }
-        __syncthreads();  // previous tile done with the tables (first pass: s_rot is complete)
-        constexpr int kEntries = kTileW + kTileH;
-        if (tid >= kEntries && tid < kEntries + 3) s_rx[tid - kEntries] = d_rx[3 * irx + tid - kEntries];
-        if (tid < kEntries) {
-            const int which = tid >= kTileW, l = which ? tid - kTileW : tid;  // 0: theta, 1: phi
-            const int idx = which == 0 ? tx * kTileW + l : (int)p.row_begin + ty * kTileH + l;
-            const int ic = idx < p.n_scan ? idx : p.n_scan - 1;
-            const double a = linspace_at(p.lin_start, p.lin_stop, p.lin_step, p.n_scan, ic);
+        __syncthreads();  // previous strip done with the tables (first pass: s_rot is complete)
+        if (tid < kTileW) {
+            fill_theta(tx_begin, 0);
+        } else if (tid < kTileW + kTileH) {
+            const int l = tid - kTileW;
             double sn, cs;
-            if (use_rot) {
-                const double2 ra = s_rot[ic & 15], rb = s_rot[16 + ((ic >> 4) & 63)],
-                              rc = s_rot[80 + (ic >> 10)];
-                const double s1 = fma(rc.x, rb.y, rc.y * rb.x), c1 = fma(rc.y, rb.y, -(rc.x * rb.x));
-                sn = fma(s1, ra.y, c1 * ra.x);
-                cs = fma(c1, ra.y, -(s1 * ra.x));
-            } else {
-                sincos(a, &sn, &cs);
-            }
-            s_sin[which][l] = sn;
-            s_cos[which][l] = cs;
-            const double ang = a - kHalfPi;  // -de_ho (theta) / de_ve (phi), ray_trace.py:1529-1532
-            // separable Gaussian feed taper a = A_theta[i] A_phi[j] (ray_trace.py:1573-1577)
-            const float af = (float)ang, a2 = af * af;
-            for (int f = 0; f < p.n_freq; ++f)
-                s_amp[f][which][l] = expf((which == 0 ? g_freq.neg_c_fx[f] : g_freq.neg_c_fy[f]) * a2);
+            float a2;
+            fill_entry((int)p.row_begin + ty * kTileH + l, sn, cs, a2);
+            s_sin_p[l] = sn;
+            s_cos_p[l] = cs;
+            for (int f = 0; f < p.n_freq; ++f) s_amp_p[f][l] = expf(g_freq.neg_c_fy[f] * a2);
+        } else if (tid < kTileW + kTileH + 3) {
+            s_rx[tid - kTileW - kTileH] = d_rx[3 * irx + tid - kTileW - kTileH];
         }
-        __syncthreads();
-
         const int iph = ty * kTileH + lph;  // relative to row_begin
-        const double *rx = s_rx;  // feed position [mm], staged with the tables
-        RayResult rr[kNR];
-        if (kNR == 2) {
-            // two rays 16 launch columns apart, skewed by half a surface (trace_ray_newton_pair)
-            const double sph = s_sin[1][lph], cph = s_cos[1][lph];
-            const double st0 = s_sin[0][lth], ct0 = s_cos[0][lth];
-            const double st1 = s_sin[0][lth + kTile], ct1 = s_cos[0][lth + kTile];
-            trace_ray_newton_pair<N32, N64, GeoBuild<GEO>::generic, GeoBuild<GEO>::mask,
-                                  GeoBuild<GEO>::edge, false>(
-                g_geom, rx[0], rx[1], rx[2], st0 * cph, st0 * sph, ct0, st1 * cph, st1 * sph, ct1,
-                rr[0], rr[kNR - 1]);
-        } else {
-#pragma unroll
-            for (int q = 0; q < kNR; ++q) {
-                // lanes past the edge of the launch grid trace the clamped (edge) ray so that
-                // whole warps stay converged; their result is dropped
-                const double sth = s_sin[0][lth + kTile * q], cth = s_cos[0][lth + kTile * q];
-                const double sph = s_sin[1][lph], cph = s_cos[1][lph];
+        unsigned okbits = 0u;               // bit 0 / 1: the lane's history of the last / last but one tile is finite
+        int cur = 0;                        // s_hist[cur]: t(x-1), s_hist[cur ^ 1]: t(x-2) -> receives t(x)
+        for (int tx = tx_begin, buf = 0; tx < tx_end; ++tx, buf ^= 1) {
+            __syncthreads();  // tables of this tile complete; everybody is done with buffer buf ^ 1
+            if (tid < kTileW && tx + 1 < tx_end) fill_theta(tx + 1, buf ^ 1);
+            const double *rx = s_rx;  // feed position [mm], staged with the tables
+            const double sth = s_sin_t[buf][lth], cth = s_cos_t[buf][lth];
+            const double sph = s_sin_p[lph], cph = s_cos_p[lph];
+            RayResult r;
+            bool predicted = false;
+            if (kCanPredict && p.predict) {
+                const bool whole = tx * kTileW + kTileW <= p.n_scan;
+                predicted = whole && __all_sync(0xffffffffu, okbits == 3u);
+                double *h1 = my_hist + cur * (SOSAT_NUM_SURFACES * kHistStride);
+                double *h2 = my_hist + (cur ^ 1) * (SOSAT_NUM_SURFACES * kHistStride);
+                if (predicted)
+                    trace_ray_predicted<GeoBuild<GEO>::generic, GeoBuild<GEO>::mask, GeoBuild<GEO>::edge>(
+                        g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph, cth, r, h1, h2, kHistStride);
+                else
+                    trace_ray_newton_hist<N32, N64, GeoBuild<GEO>::generic, GeoBuild<GEO>::mask,
+                                          GeoBuild<GEO>::edge, false>(
+                        g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph, cth, r, h2, kHistStride);
+                cur ^= 1;
+                // a lane re-traced below leaves no usable history: its warp falls back for two tiles
+                const bool fin = (r.opl - r.opl == 0.0) && !(r.flags & RAY_UNCONVERGED);
+                okbits = ((okbits << 1) | (fin ? 1u : 0u)) & 3u;
+            } else {
                 trace_ray_newton<N32, N64, GeoBuild<GEO>::generic, GeoBuild<GEO>::mask,
                                  GeoBuild<GEO>::edge, false>(g_geom, rx[0], rx[1], rx[2], sth * cph,
-                                                             sth * sph, cth, rr[q]);
+                                                             sth * sph, cth, r);
             }
-        }
-#pragma unroll
-        for (int q = 0; q < kNR; ++q) {
-            RayResult &r = rr[q];
-            const int lthq = lth + kTile * q;
-            const bool live = tx * kTileW + lthq < p.n_scan && iph < p.n_rows;
+            const bool live = tx * kTileW + lth < p.n_scan && iph < p.n_rows;
             if (r.flags & (RAY_UNCONVERGED | RAY_FLAGGED)) {
                 // rare: the launch direction is re-read here (volatile) instead of being kept live
                 // across the fast path, and results go through a local copy so that r itself
                 // stays in registers.
-                const double sth = *(volatile double *)&s_sin[0][lthq], cth = *(volatile double *)&s_cos[0][lthq];
-                const double sph = *(volatile double *)&s_sin[1][lph], cph = *(volatile double *)&s_cos[1][lph];
+                const double sth2 = *(volatile double *)&s_sin_t[buf][lth], cth2 = *(volatile double *)&s_cos_t[buf][lth];
+                const double sph2 = *(volatile double *)&s_sin_p[lph], cph2 = *(volatile double *)&s_cos_p[lph];
                 RayResult rs;
                 rs.valid = r.valid;
                 rs.flags = r.flags;
                 bool redone = false;
                 if (r.flags & RAY_UNCONVERGED) {  // adaptive Newton refinement, out of line
                     trace_ray_adaptive<GeoBuild<GEO>::generic, GeoBuild<GEO>::mask, GeoBuild<GEO>::edge>(
-                        g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph, cth, rs);
+                        g_geom, rx[0], rx[1], rx[2], sth2 * cph2, sth2 * sph2, cth2, rs);
                     redone = true;
                 }
                 if (rs.valid && (rs.flags & RAY_FLAGGED)) {
                     // < 0.15 % of rays: the reference's bracketed solve
-                    trace_ray_bracketed(g_geom, rx[0], rx[1], rx[2], sth * cph, sth * sph, cth, rs);
+                    trace_ray_bracketed(g_geom, rx[0], rx[1], rx[2], sth2 * cph2, sth2 * sph2, cth2, rs);
                     redone = true;
                     if (live) {
                         atomicAdd(&s_rare[0], 1u);
@@ -422,7 +432,7 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
             for (int f = 0; f < p.n_freq; ++f, re_f += plane, im_f += plane) {
                 float vre = 0.f, vim = 0.f;
                 if (bin >= 0) {
-                    const float a = s_amp[f][0][lthq] * s_amp[f][1][lph];
+                    const float a = s_amp_t[buf][f][lth] * s_amp_p[f][lph];
                     double cyc = dopl * g_freq.kk[f];
                     // phase reduced to [-1/2, 1/2] cycles in fp64: cyc - rint(cyc) with the
                     // 1.5 * 2^52 trick (two DADDs; an FRND.F64 would go through the XU pipe)
@@ -785,16 +795,42 @@ extern "C" int sosat_rx_to_lyot_host(const sosat_geom_t *h_geom, const double *h
     return rc;
 }
 
-// Launch the persistent binning kernel with grid = SMs x resident CTAs per SM.
+// Launch the persistent binning kernel with grid = SMs x resident CTAs per SM.  The strip length
+// is chosen here because it needs the grid size: strips are dealt round-robin, so there must be
+// many more strips than CTAs; a predicted-seed strip pays two fp32-seeded tiles at its start.
 template <int N32, int N64, int MINB, int GEO>
-static void launch_bin(const BinParams &p, const double *rx, float *re, float *im, float *cnt,
+static void launch_bin(BinParams p, const double *rx, float *re, float *im, float *cnt,
                        double *stats, cudaStream_t st) {
+    auto kern = trace_bin_kernel<N32, N64, MINB, GEO>;
+    const size_t smem = p.predict ? (size_t)kHistBytes : 0;
+    static bool carveout_set[64][2] = {};
+    int dev = 0;
+    cudaGetDevice(&dev);
+    if (dev >= 0 && dev < 64 && !carveout_set[dev][p.predict ? 1 : 0]) {
+        // MINB CTAs of ~45 KB each: ask for the shared-memory-heavy split of the L1 / shared array
+        cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
+                             cudaSharedmemCarveoutMaxShared);
+        // static tables (25 KB) + history (24 KB) exceed the 48 KB default limit
+        if (smem) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        carveout_set[dev][p.predict ? 1 : 0] = true;
+    }
     int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(
-        &occ, trace_bin_kernel<N32, N64, MINB, GEO>, kBinThreads, 0);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBinThreads, smem);
     const long long want = (long long)num_sms() * (occ > 0 ? occ : 1);
-    const int blocks = (int)(p.n_tiles < want ? p.n_tiles : want);
-    trace_bin_kernel<N32, N64, MINB, GEO><<<blocks, kBinThreads, 0, st>>>(p, rx, re, im, cnt, stats);
+    const long long n_tiles = (long long)p.tiles_x * p.tiles_y * p.n_rx;
+    long long sl = 64;
+    if (const char *e = getenv("SOSAT_STRIP_LEN")) {  // testing / tuning hook
+        sl = atoll(e);
+    } else {
+        if (sl > n_tiles / (8 * want)) sl = n_tiles / (8 * want);  // >= 8 strips per CTA
+        if (sl < 8) p.predict = 0;  // short strips: the two seeding tiles would dominate
+    }
+    if (sl < 1) sl = 1;
+    p.strip_len = (int)sl;
+    p.strips_x = (p.tiles_x + p.strip_len - 1) / p.strip_len;
+    p.n_strips = (long long)p.strips_x * p.tiles_y * p.n_rx;
+    const int blocks = (int)(p.n_strips < want ? p.n_strips : want);
+    kern<<<blocks, kBinThreads, smem, st>>>(p, rx, re, im, cnt, stats);
 }
 
 template <int N32, int N64>
@@ -850,6 +886,8 @@ extern "C" int sosat_trace_bin(const double *d_rx, int n_rx, const sosat_freq_t 
     cudaStream_t st = (cudaStream_t)stream;
     SOSAT_CUDA_OK(cudaMemcpyToSymbolAsync(g_freq, &bf, sizeof bf, 0, cudaMemcpyHostToDevice, st));
     BinParams p;
+    const int minb = trace_minb();
+    const int geo = g_geom_build[dev];
     fill_linspace(g_host_geom[dev].cone, n_scan, p.lin_start, p.lin_stop, p.lin_step);
     p.opl_ref = opl_ref;
     p.half_extent = binning ? 0.5 * extent_mm : 0.0;
@@ -862,11 +900,16 @@ extern "C" int sosat_trace_bin(const double *d_rx, int n_rx, const sosat_freq_t 
     p.grid_n = binning ? grid_n : 0;
     p.tiles_x = (n_scan + kTileW - 1) / kTileW;
     p.tiles_y = (p.n_rows + kTileH - 1) / kTileH;
-    p.n_tiles = (long long)p.tiles_x * p.tiles_y * n_rx;
-    SOSAT_REQUIRE(p.n_tiles < 2147483647LL, "too many ray tiles for one launch (%lld): split the "
-                  "receiver list or the row range", p.n_tiles);
-    const int minb = trace_minb();
-    const int geo = g_geom_build[dev];
+    SOSAT_REQUIRE((long long)p.tiles_x * p.tiles_y * n_rx < 2147483647LL,
+                  "too many ray tiles for one launch (%lld): split the receiver list or the row range",
+                  (long long)p.tiles_x * p.tiles_y * n_rx);
+    // Predicted seeds (trace_device.cuh: trace_ray_predicted): the extrapolation error over one
+    // tile step, (16 dtheta)^2 |t''| <= 2.4e3 mm/rad^2 x (16 step)^2, must stay inside the
+    // 2^-10 mm step bound of the one-step schedule with a margin of 2: 16 step <= 4.5e-4 rad,
+    // i.e. n_scan >= ~28 500 for the 0.8 rad cone.  SOSAT_TRACE_PREDICT=0/1 forces it.
+    p.predict = 16.0 * p.lin_step <= 4.5e-4 && p.lin_step > 0.0;
+    if (const char *e = getenv("SOSAT_TRACE_PREDICT")) p.predict = atoi(e) != 0;
+    if (trace_variant() != 7 || geo == 2) p.predict = 0;
     switch (trace_variant()) {
         case 0: launch_bin_minb<0, 5>(geo, minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
         case 2: launch_bin_minb<3, 2>(geo, minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;

@@ -658,7 +658,7 @@ def test_peer_reduce_kernel_on_one_device(mods, feed_table):
         peer.close()
 
 
-def test_full_size_bundle_properties(mods):
+def test_full_size_bundle_properties(mods, monkeypatch):
     """BASELINE.json configs[4] at its full size -- 1.000014e9 rays (n_scan = 31623) into 2048^2
     bins -- through size-independent properties, since no oracle finishes 10^9 rays:
     conservation (every valid ray inside the grid is counted once), mirror symmetry of the
@@ -709,6 +709,18 @@ def test_full_size_bundle_properties(mods):
     s2 = st2.cpu().numpy()[0]
     assert s2[_lib.STAT_N_VALID] == s[_lib.STAT_N_VALID] and s2[_lib.STAT_N_BINNED] == s[_lib.STAT_N_BINNED]
     assert abs(s2[_lib.STAT_SUM_OPL] - s[_lib.STAT_SUM_OPL]) <= 1e-12 * abs(s[_lib.STAT_SUM_OPL])
+    # the two seedings of the kernel (predicted from the lane's last two tiles: the default at
+    # this size; fp32 Newton + Halley) bin every one of the 1e9 rays into the same cell
+    monkeypatch.setenv("SOSAT_TRACE_PREDICT", "0")
+    re3, im3, cnt3, st3 = rt.trace_bin_device(t, [[0, 0, 0]], spec, n, 420.0)
+    torch.cuda.synchronize()
+    monkeypatch.delenv("SOSAT_TRACE_PREDICT")
+    s3 = st3.cpu().numpy()[0]
+    assert s3[_lib.STAT_N_VALID] == s[_lib.STAT_N_VALID] and s3[_lib.STAT_N_BINNED] == s[_lib.STAT_N_BINNED]
+    assert float((cnt3 - cnt).abs().sum().item()) <= 1e-7 * total     # rays within rounding of a cell edge
+    assert (re3 - re).abs().max().item() <= 1e-4 * re.abs().max().item()
+    assert abs(s3[_lib.STAT_SUM_OPL] - s[_lib.STAT_SUM_OPL]) <= 1e-9 * s[_lib.STAT_N_VALID]
+    del re3, im3, cnt3
     # the bundle's statistics converge with the sampling: a 2000^2 bundle of the same cone
     tc = _bundle(mods, 2000)
     sc = rt.trace_stats(tc, [[0, 0, 0]])[0]
@@ -718,14 +730,20 @@ def test_full_size_bundle_properties(mods):
     assert abs(mean_full - mean_coarse) < 2e-2                      # mm, of ~1.1e3 mm
 
 
+@pytest.mark.parametrize("seeds", ["predicted", "fp32"])
 @pytest.mark.parametrize("rx", [[0.0, 0.0, 0.0], [90.0, 0.0, -60.0]])
 @pytest.mark.parametrize("where", ["first", "middle", "last"])
-def test_full_size_row_blocks_against_the_oracle(mods, rx, where):
+def test_full_size_row_blocks_against_the_oracle(mods, monkeypatch, rx, where, seeds):
     """configs[4] at its benchmarked n_scan = 31623: 16-row blocks of the launch grid (first rows
     = edge of the cone, middle rows = through the axis, last rows incl. the ragged final tile)
     traced + binned by the fused kernel and compared with the oracle's trace + binning of exactly
-    those rays -- statistics exact, planes to the fp32 accumulation bound."""
+    those rays -- statistics exact, planes to the fp32 accumulation bound.  Both seedings of the
+    kernel: the predicted seeds the full-size launch uses (strips of 64 adjacent tiles, forced
+    here because a 16-row block alone has too few tiles for the launch heuristic) and the fp32
+    Newton + Halley pre-iterations."""
     rt, oracle = mods["rt"], mods["oracle"]
+    monkeypatch.setenv("SOSAT_TRACE_PREDICT", "1" if seeds == "predicted" else "0")
+    monkeypatch.setenv("SOSAT_STRIP_LEN", "64")
     n_scan = 31623
     t = _bundle(mods, n_scan)
     spec = [(t.k, t.th_fwhp_x, t.th_fwhp_y)]
@@ -735,8 +753,10 @@ def test_full_size_row_blocks_against_the_oracle(mods, rx, where):
     rre, rim, rcnt, sums = oracle.bin_near_field(ref, float(t.k), 2048, 420.0, 0.0)
     st = st.cpu().numpy()[0]
     assert int(st[0]) == sums["n_valid"] and int(st[7]) == sums["n_binned"]
-    if sums["n_valid"]:
-        assert st[1] == pytest.approx(sums["sum_opl"], rel=1e-12)
+    # sum of OPL over the block: the edge-of-cone rows are mostly "wild" marginal rays, held to
+    # 2e-5 mm each (OPL_WILD_MM); the blocks through the axis agree to 1e-7 mm per ray
+    per_ray = OPL_WILD_MM if where != "middle" else 1e-7
+    assert abs(st[1] - sums["sum_opl"]) <= per_ray * max(1, sums["n_valid"])
     assert int(st[6]) == 0
     c = cnt[0].cpu().numpy()
     assert np.abs(c - rcnt).sum() <= max(4, 1e-5 * rcnt.sum())     # rays sitting on a cell edge
