@@ -272,6 +272,37 @@ int sosat_ff_fwhm_indices(const float *d_B, int n, int *d_idx, float *d_val, voi
 int sosat_ff_fwhm_indices_batch(const float *d_B, int n, int n_fields, int *d_idx, float *d_val,
                                 void *d_work, void *stream);
 
+/* ---- scattered rays -> regular grid -> stage grid --------------------------
+ * ray_trace.py:1675-1717 sim2d: scipy.interpolate.griddata(method="cubic") (Clough-Tocher on the
+ * Delaunay triangulation, globally estimated gradients) of amplitude and phase of the rays within
+ * r_select of the beam centre; ray_trace.py:1720-1754 sim_data: interp2d(kind="cubic") resampling.
+ * SciPy is not vendored by the reference (unpinned); csrc/gridder.cu restates the published
+ * algorithms for rays that form a warped structured lattice (d_ray_index[i] = iphi * n_scan +
+ * itheta of point i), see the header of that file.
+ * sosat_sim2d_prepare: beam centre, selection, lattice triangulation, `sweeps` four-colour
+ *   Gauss-Seidel sweeps of the gradient estimate (scipy converges to 1e-6 in 10-13).  d_x, d_y,
+ *   d_a, d_p [n_pts] doubles (x_sim, y_sim [cm], a_sim, p_sim).  d_scalars[8] receives {cx, cy,
+ *   xmin, xmax, ymin, ymax of the selected points, their number, lattice index of the centre ray}.
+ * sosat_sim2d_eval: the interpolant at the m x m points (d_gx[i], d_gy[j]) -> d_out_a / d_out_p
+ *   [m][m] (x along axis 0, like np.mgrid); 0 outside the triangulation and for r >= r_zero. */
+size_t sosat_sim2d_workspace_bytes(int64_t n_pts, int n_scan);
+int sosat_sim2d_prepare(const double *d_x, const double *d_y, const double *d_a, const double *d_p,
+                        const int64_t *d_ray_index, int64_t n_pts, int n_scan, double r_select,
+                        int sweeps, void *d_workspace, size_t workspace_bytes, double *d_scalars,
+                        void *stream);
+int sosat_sim2d_eval(const double *d_x, const double *d_y, const double *d_a, const double *d_p,
+                     int64_t n_pts, int n_scan, const void *d_workspace, const double *d_gx,
+                     const double *d_gy, int m, double r_zero, double *d_out_a, double *d_out_p,
+                     void *stream);
+/* sim_data: z_amp = |a|^T / max|a|, z_ph = arg((a e^{ip})^T) of the n x n grid, resampled as
+ * My z Mx^T with the m x n spline operators of the two axes (built by the caller: FITPACK's
+ * not-a-knot interpolating cubic spline is linear in the data), a_data = resampled amplitude /
+ * its maximum, p_data = resampled phase.  d_work: sosat_sim_data_work_doubles(n, m) doubles. */
+size_t sosat_sim_data_work_doubles(int n, int m);
+int sosat_sim_data(const double *d_a, const double *d_p, int n, const double *d_Mx,
+                   const double *d_My, int m, double *d_a_data, double *d_p_data, double *d_work,
+                   void *stream);
+
 /* ---- measurement helpers --------------------------------------------------------------- */
 /* ---- multi-GPU: reduce of the bin planes over NVLink peer memory -----------
  * The reference has no multi-device path; north_star shards the rays of a bundle over the GPUs

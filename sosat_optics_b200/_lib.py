@@ -94,6 +94,14 @@ SIGNATURES = {
                                          c_int64, c_int, c_int, c_int64, c_int64, POINTER(c_double),
                                          c_double, POINTER(c_void_p), c_int, c_int64, c_void_p,
                                          c_void_p]),
+    "sosat_sim2d_workspace_bytes": (c_size_t, [c_int64, c_int]),
+    "sosat_sim2d_prepare": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int,
+                                    c_double, c_int, c_void_p, c_size_t, c_void_p, c_void_p]),
+    "sosat_sim2d_eval": (c_int, [c_void_p, c_void_p, c_void_p, c_void_p, c_int64, c_int, c_void_p,
+                                 c_void_p, c_void_p, c_int, c_double, c_void_p, c_void_p, c_void_p]),
+    "sosat_sim_data_work_doubles": (c_size_t, [c_int, c_int]),
+    "sosat_sim_data": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
+                               c_void_p, c_void_p, c_void_p]),
     "sosat_measure_fp64_peak": (c_int, [POINTER(c_double), POINTER(c_double)]),
     "sosat_peer_alloc": (c_int, [c_int64, POINTER(c_void_p)]),
     "sosat_peer_free": (c_int, [c_void_p]),

@@ -17,7 +17,7 @@ ROOT = os.path.dirname(PKG)
 CSRC = os.path.join(PKG, "csrc")
 INCLUDE = os.path.join(ROOT, "include")
 LIB_PATH = os.path.join(PKG, "libsosat_b200.so")
-SOURCES = ["capi.cu", "trace.cu", "dft_gemm.cu", "nudft.cu", "reduce.cu", "peer.cu"]
+SOURCES = ["capi.cu", "trace.cu", "dft_gemm.cu", "nudft.cu", "reduce.cu", "peer.cu", "gridder.cu"]
 HEADERS = ["common.cuh", "trace_device.cuh"]
 NVCC_FLAGS = [
     "-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-std=c++17",

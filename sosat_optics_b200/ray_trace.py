@@ -17,9 +17,11 @@ function                reference                   device code
 ``near_field_metrics``  same reductions, on device  ``sosat_near_field_metrics`` (reduce.cu): one
                         for a whole frequency sweep trace, scalars per frequency come back
 ``ff_fwhm_device``      ff_fwhm_est on a CUDA field ``sosat_ff_fwhm_indices`` (reduce.cu)
-``sim2d``, ``sim_data`` ray_trace.py:1675-1754      host glue (scipy), kept so the notebooks'
-                                                    scattered->grid route still runs end to end;
-                                                    the device route is near_field_binned
+``sim2d``               ray_trace.py:1675-1717      ``sosat_sim2d_prepare`` / ``sosat_sim2d_eval``
+                                                    (gridder.cu): scipy's cubic griddata restated
+                                                    on the ray lattice
+``sim_data``            ray_trace.py:1720-1754      ``sosat_sim_data``: the bicubic spline resampling
+                                                    as two fp64 contractions
 ======================  ==========================  ==========================================
 
 ``plot`` / ``col`` arguments are accepted and ignored (plotting is out of scope).
@@ -135,9 +137,15 @@ def getNearField(tele_geo, rx, plot=False):
         ctypes.c_void_p(out.data_ptr()), n, geometry.scalar(tele_geo.k),
         ctypes.c_void_p(xyap.data_ptr()), ctypes.c_void_p(mask.data_ptr()),
         ctypes.c_void_p(tan_og.data_ptr()), ctypes.c_void_p(work.data_ptr()), _stream(torch)))
-    sel = _lib.to_numpy(xyap[:, mask.bool()])  # xx = np.where(out[4] != 0): order-preserving
-    return SimOutput(sel[0].copy(), sel[1].copy(), sel[2].copy(), sel[3].copy(),
-                     _lib.to_numpy(tan_og))
+    keep = mask.bool()
+    sel = _lib.to_numpy(xyap[:, keep])  # xx = np.where(out[4] != 0): order-preserving
+    sb = SimOutput(sel[0].copy(), sel[1].copy(), sel[2].copy(), sel[3].copy(),
+                   _lib.to_numpy(tan_og))
+    # where each returned ray sits in the n_scan x n_scan launch lattice (ray ii = iphi * n_scan +
+    # itheta, ray_trace.py:1086-1091): what sim2d needs to triangulate the rays without Qhull
+    sb.ray_index = _lib.to_numpy(torch.nonzero(keep).reshape(-1))
+    sb.n_scan = int(tele_geo.n_scan)
+    return sb
 
 
 # --- host helpers over the returned arrays (ray_trace.py:1648-1672, 1757-1779) ------------
@@ -291,32 +299,59 @@ def ff_fwhm_device(beam_fft, x_ang, y_ang):
     return (fwhm1 + fwhm2) / 2
 
 
-# --- the notebooks' scattered -> grid glue, host side -----------------
+# --- the notebooks' scattered -> grid glue, on the device -------------
 class _Grid2d:
     def __init__(self, x_sim, y_sim, a_sim, p_sim):
         self.a_sim, self.p_sim, self.x_sim, self.y_sim = a_sim, p_sim, x_sim, y_sim
 
 
+SIM2D_GRID = 100          # np.mgrid[...:100j], ray_trace.py:1686-1689
+SIM2D_R_SELECT = 21.0     # cm, :1684
+SIM2D_R_ZERO = 20.0       # cm, :1693
+SIM2D_SWEEPS = 40         # four-colour Gauss-Seidel sweeps (scipy stops at a 1e-6 change: 10-13)
+
+
 def sim2d(sb):
     """Cubic ``griddata`` of amplitude and phase on a 100 x 100 grid spanning the valid rays within
-    21 cm of the beam centre, zero beyond 20 cm (ray_trace.py:1675-1717).  Host glue exactly as
-    in the reference (scipy); on the device the same role is played by ``near_field_binned``."""
-    from scipy.interpolate import griddata
-    x_sim, y_sim = sb.x_sim, sb.y_sim
-    beam_cent = get_beam_cent(sb)
-    indx_xy = np.where((np.isnan(x_sim) == False) & (np.isnan(y_sim) == False)  # noqa: E712
-                       & ((x_sim - beam_cent[0]) ** 2 + (y_sim - beam_cent[1]) ** 2 <= 21.0 ** 2))
-    grid_x, grid_y = np.mgrid[np.min(x_sim[indx_xy]):np.max(x_sim[indx_xy]):100j,
-                              np.min(y_sim[indx_xy]):np.max(y_sim[indx_xy]):100j]
-    points = np.array([x_sim[indx_xy], y_sim[indx_xy]]).T
-    outside = (grid_x - beam_cent[0]) ** 2 + (grid_y - beam_cent[1]) ** 2 >= 20 ** 2
+    21 cm of the beam centre, zero beyond 20 cm (ray_trace.py:1675-1717), on the GPU.
 
-    def grid(values):
-        g = griddata(points, np.array(values[indx_xy]).T, (grid_x, grid_y), method="cubic")
-        g = np.where(outside, 0, g)
-        return np.where(np.isnan(g), 0, g)
-
-    return _Grid2d(grid_x, grid_y, grid(sb.a_sim), grid(sb.p_sim))
+    ``scipy.interpolate.griddata(method="cubic")`` is Clough-Tocher interpolation on the Delaunay
+    triangulation of the points with globally estimated gradients; ``csrc/gridder.cu`` restates
+    that algorithm for ray positions that form a warped structured lattice, which is why ``sb``
+    must come from this package's :func:`getNearField` (it carries ``ray_index`` / ``n_scan``,
+    the place of every ray in the launch lattice).  Returns the reference's attribute bag
+    (``x_sim, y_sim`` = the ``np.mgrid`` coordinates, ``a_sim, p_sim`` [100, 100])."""
+    lib = _lib.require_gpu()
+    torch = _torch()
+    idx = getattr(sb, "ray_index", None)
+    n_scan = getattr(sb, "n_scan", None)
+    if idx is None or n_scan is None:
+        raise ValueError("sim2d needs the SimOutput of sosat_optics_b200.ray_trace.getNearField "
+                         "(its ray_index / n_scan attributes place the rays in the launch lattice)")
+    n = len(sb.a_sim)
+    if not (len(sb.x_sim) == len(sb.y_sim) == len(sb.p_sim) == len(idx) == n) or n == 0:
+        raise ValueError("sim2d: x_sim, y_sim, a_sim, p_sim and ray_index must have one entry per ray")
+    up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=dt))).to("cuda")  # noqa: E731
+    d_x, d_y, d_a, d_p = (up(v, np.float64) for v in (sb.x_sim, sb.y_sim, sb.a_sim, sb.p_sim))
+    d_idx = up(idx, np.int64)
+    nbytes = int(lib.sosat_sim2d_workspace_bytes(n, int(n_scan)))
+    ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+    scal = torch.empty(8, dtype=torch.float64, device="cuda")
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    _lib.check(lib.sosat_sim2d_prepare(ptr(d_x), ptr(d_y), ptr(d_a), ptr(d_p), ptr(d_idx), n,
+                                       int(n_scan), SIM2D_R_SELECT, SIM2D_SWEEPS, ptr(ws), nbytes,
+                                       ptr(scal), _stream(torch)))
+    h = _lib.to_numpy(scal)  # beam centre, bounding box of the selected rays, their number
+    if h[6] < 3:
+        raise ValueError("sim2d: fewer than 3 rays within 21 cm of the beam centre")
+    grid_x, grid_y = np.mgrid[h[2]:h[3]:complex(0, SIM2D_GRID), h[4]:h[5]:complex(0, SIM2D_GRID)]
+    d_gx, d_gy = up(grid_x[:, 0], np.float64), up(grid_y[0, :], np.float64)
+    out_a = torch.empty((SIM2D_GRID, SIM2D_GRID), dtype=torch.float64, device="cuda")
+    out_p = torch.empty_like(out_a)
+    _lib.check(lib.sosat_sim2d_eval(ptr(d_x), ptr(d_y), ptr(d_a), ptr(d_p), n, int(n_scan), ptr(ws),
+                                    ptr(d_gx), ptr(d_gy), SIM2D_GRID, SIM2D_R_ZERO, ptr(out_a),
+                                    ptr(out_p), _stream(torch)))
+    return _Grid2d(grid_x, grid_y, _lib.to_numpy(out_a), _lib.to_numpy(out_p))
 
 
 class _StageData:
@@ -324,27 +359,72 @@ class _StageData:
         self.a_data, self.p_data, self.x_data, self.y_data = a_data, p_data, x_data, y_data
 
 
+def _bspline_basis(t, xs, k=3):
+    """B-spline basis functions of degree ``k`` on the knot vector ``t`` at ``xs`` (Cox-de Boor):
+    ``[len(xs), len(t) - k - 1]``; the last interval is closed on the right."""
+    t = np.asarray(t, dtype=np.float64)
+    xs = np.asarray(xs, dtype=np.float64)
+    nb = len(t) - k - 1
+    span = np.clip(np.searchsorted(t, xs, side="right") - 1, k, nb - 1)  # t[span] <= x < t[span+1]
+    B = np.zeros((len(xs), len(t) - 1))
+    B[np.arange(len(xs)), span] = 1.0
+    for d in range(1, k + 1):
+        nxt = np.zeros((len(xs), len(t) - 1 - d))
+        for j in range(len(t) - 1 - d):
+            left = t[j + d] - t[j]
+            right = t[j + d + 1] - t[j + 1]
+            if left > 0:
+                nxt[:, j] += (xs - t[j]) / left * B[:, j]
+            if right > 0:
+                nxt[:, j] += (t[j + d + 1] - xs) / right * B[:, j + 1]
+        B = nxt
+    return B[:, :nb]
+
+
+def _cubic_spline_operator(x, x_new):
+    """``M`` with ``s(x_new) = M @ z`` for the interpolating cubic spline through ``(x, z)`` that
+    FITPACK builds for ``interp2d(kind="cubic")`` / ``RectBivariateSpline(kx=3, s=0)``: knots
+    ``[x0]*4 + x[2:-2] + [x_end]*4`` (not-a-knot), arguments outside ``[x0, x_end]`` clamped to
+    the ends (fpbisp).  Index bookkeeping on ~100 numbers, done on the host like the twiddles of
+    the far field; the field data are contracted with it on the device (``sosat_sim_data``)."""
+    x = np.asarray(x, dtype=np.float64)
+    if x.ndim != 1 or len(x) < 4 or not np.all(np.diff(x) > 0):
+        raise ValueError("sim_data needs at least 4 strictly increasing grid coordinates per axis")
+    t = np.concatenate([[x[0]] * 4, x[2:-2], [x[-1]] * 4])
+    A = _bspline_basis(t, x)
+    E = _bspline_basis(t, np.clip(np.asarray(x_new, dtype=np.float64), x[0], x[-1]))
+    return np.ascontiguousarray(np.linalg.solve(A.T, E.T).T)
+
+
 def sim_data(sb_in, STAGE_RANGE, STEP):
-    """Resample the ``sim2d`` grid onto the holography stage grid (ray_trace.py:1720-1754).
-    The reference calls ``scipy.interpolate.interp2d(kind='cubic')``, removed in SciPy 1.14;
-    ``RectBivariateSpline(kx=ky=3, s=0)`` is the same interpolating bicubic spline."""
-    from scipy.interpolate import RectBivariateSpline
-    beam_final = sb_in.a_sim.T * np.exp(complex(0, 1) * sb_in.p_sim.T)
-    x_interp = sb_in.x_sim[:, 0]
-    y_interp = sb_in.y_sim[0, :]
-
-    def interp2d(z):
-        spl = RectBivariateSpline(x_interp, y_interp, np.asarray(z).T, kx=3, ky=3, s=0)
-        return lambda xn, yn: spl(xn, yn).T
-
-    func_beam = interp2d(np.abs(beam_final) / np.max(np.abs(beam_final)))
-    func_phase = interp2d(np.arctan2(np.imag(beam_final), np.real(beam_final)))
+    """Resample the ``sim2d`` grid onto the holography stage grid (ray_trace.py:1720-1754) on the
+    GPU.  The reference calls ``scipy.interpolate.interp2d(kind='cubic')`` (removed in SciPy
+    1.14) on ``|b| / max|b|`` and ``arg b``; that is FITPACK's interpolating bicubic spline, a
+    separable linear map ``My z Mx^T`` of the grid values, contracted here in fp64 on the device."""
+    lib = _lib.require_gpu()
+    torch = _torch()
+    a = np.ascontiguousarray(np.asarray(sb_in.a_sim, dtype=np.float64))
+    p = np.ascontiguousarray(np.asarray(sb_in.p_sim, dtype=np.float64))
+    if a.ndim != 2 or a.shape[0] != a.shape[1] or a.shape != p.shape:
+        raise ValueError("sim_data expects square [n, n] a_sim / p_sim grids of equal shape")
+    n = a.shape[0]
+    x_interp = np.asarray(sb_in.x_sim)[:, 0]
+    y_interp = np.asarray(sb_in.y_sim)[0, :]
     x_data = np.arange(-STAGE_RANGE / 2, STAGE_RANGE / 2, STEP)
     y_data = np.arange(-STAGE_RANGE / 2, STAGE_RANGE / 2, STEP)
-    beam_data = func_beam(x_data, y_data)
-    phase_data = func_phase(x_data, y_data)
-    x_data, y_data = np.meshgrid(x_data, y_data)
-    return _StageData(x_data, y_data, beam_data / np.max(beam_data), phase_data)
+    m = len(x_data)
+    Mx = _cubic_spline_operator(x_interp, x_data)
+    My = _cubic_spline_operator(y_interp, y_data)
+    up = lambda v: torch.from_numpy(v).to("cuda")  # noqa: E731
+    d_a, d_p, d_Mx, d_My = up(a), up(p), up(Mx), up(My)
+    a_data = torch.empty((m, m), dtype=torch.float64, device="cuda")
+    p_data = torch.empty_like(a_data)
+    work = torch.empty(int(lib.sosat_sim_data_work_doubles(n, m)), dtype=torch.float64, device="cuda")
+    ptr = lambda t: ctypes.c_void_p(t.data_ptr())  # noqa: E731
+    _lib.check(lib.sosat_sim_data(ptr(d_a), ptr(d_p), n, ptr(d_Mx), ptr(d_My), m, ptr(a_data),
+                                  ptr(p_data), ptr(work), _stream(torch)))
+    x_grid, y_grid = np.meshgrid(x_data, y_data)
+    return _StageData(x_grid, y_grid, _lib.to_numpy(a_data), _lib.to_numpy(p_data))
 
 
 # --- fused trace + binning (north_star) -------------------------------------------------------

@@ -435,41 +435,125 @@ def test_near_field_metrics_one_trace_for_the_whole_sweep(mods, feed_table):
     assert np.allclose(m["tan_og"], sb.tan_og, atol=1e-12)
 
 
-def test_notebook_scattered_grid_route_end_to_end(mods):
-    """Row f1: sat_farfield.ipynb cells 1-6 with the GPU tracer and the GPU a2b around the
-    reference's host glue (sim2d / sim_data): the 100 x 100 grid the reference produced, its 240^2
-    far field, and 'Estimated FWHM: 21.50 arcmin'.
-
-    The glue itself is ill-conditioned: scipy's cubic griddata triangulates the nearly regular
-    ray positions, and perturbing them by 1e-9 cm (CPU experiment with the oracle's rays, four
-    seeds) moves the interpolated amplitude grid by 3e-5, the wrapped-phase grid by 5e-3 rad and
-    the far field by 0.6-1.1e-4 of peak, while the FWHM stays 21.5039.  The bounds below are that
-    conditioning, not the kernels' accuracy (rays: 1e-8 mm, a2b: 5e-6 of peak)."""
-    g = golden("farfield_cfg2_240.npz")
-    rt, oa, ot_geo = mods["rt"], mods["oa"], mods["ot_geo"]
+def _notebook_geo(mods, g, n_scan, sqrt2=False):
+    ot_geo = mods["ot_geo"]
     table = golden("feedhorn_fwhm.npz")["table"]
     t = ot_geo.SatGeo()
-    t.n_scan = 100
+    t.n_scan = n_scan
     t.y_source = ot_geo.y_lyot + 300
     t.lambda_ = float(g["lambda_"])
     t.k = 2 * np.pi / t.lambda_
     row = int(g["table_row"])
-    t.th_fwhp_x = np.deg2rad(table[np.where(table[:, 0] == row), 1])
-    t.th_fwhp_y = np.deg2rad(table[np.where(table[:, 0] == row), 2])
+    f = np.sqrt(2) if sqrt2 else 1.0
+    t.th_fwhp_x = np.deg2rad(table[np.where(table[:, 0] == row), 1]) * f
+    t.th_fwhp_y = np.deg2rad(table[np.where(table[:, 0] == row), 2]) * f
+    return t
+
+
+def test_notebook_scattered_grid_route_end_to_end(mods):
+    """Row f1 on the device: sat_farfield.ipynb cells 1-6 -- GPU tracer, GPU sim2d (scipy's cubic
+    griddata restated on the ray lattice, csrc/gridder.cu), GPU sim_data (the bicubic spline as
+    two fp64 contractions), GPU a2b -- against what the reference itself produced: its 100 x 100
+    grid, its stage grid, its 240^2 far field and 'Estimated FWHM: 21.50 arcmin'.
+
+    The reference's glue is ill-conditioned: its Delaunay triangulation of the nearly regular
+    ray positions has ~180 co-circular quads whose diagonal is decided by roundoff, and the
+    wrapped phase it interpolates jumps by 2 pi along a contour through the beam.  Perturbing the
+    rays by 1e-9 cm (CPU experiment with the oracle's rays, four seeds) moves ITS amplitude grid
+    by 3e-5, its phase grid by 5e-3 rad (more on the cells that straddle the jump) and its far
+    field by 0.6-1.1e-4 of peak, while the FWHM stays 21.5039.  The bounds below are that
+    conditioning (the device restatement measured: 3e-5, 8e-7 on the stage grid, 8e-5 of peak)."""
+    g = golden("farfield_cfg2_240.npz")
+    rt, oa = mods["rt"], mods["oa"]
+    t = _notebook_geo(mods, g, 100)
     sb = rt.getNearField(t, [0, 0, 0], plot=False)
+    assert sb.n_scan == 100 and len(sb.ray_index) == len(sb.a_sim)
     sb2 = rt.sim2d(sb)
-    assert np.abs(sb2.x_sim - g["sb2_x"]).max() < 1e-6 and np.abs(sb2.y_sim - g["sb2_y"]).max() < 1e-6
-    assert np.abs(sb2.a_sim - g["sb2_a"]).max() < 1e-3
+    assert np.abs(sb2.x_sim - g["sb2_x"]).max() < 1e-9 and np.abs(sb2.y_sim - g["sb2_y"]).max() < 1e-9
+    assert np.abs(sb2.a_sim - g["sb2_a"]).max() < 1e-4
+    dp = np.abs(sb2.p_sim - g["sb2_p"])
+    assert np.percentile(dp, 99) < 1e-2 and np.mean(dp > 1e-2) < 0.01   # the 2 pi contour cells
+    assert ((sb2.a_sim == 0) == (g["sb2_a"] == 0)).mean() > 0.999       # same support
     d = rt.sim_data(sb2, 80, 2)
-    assert np.abs(d.a_data - g["a_data"]).max() < 1e-4
+    assert np.array_equal(d.x_data, g["x_data"]) and np.array_equal(d.y_data, g["y_data"])
+    assert np.abs(d.a_data - g["a_data"]).max() < 1e-5
+    assert np.abs(d.p_data - g["p_data"]).max() < 2e-2
     x_new, y_new, beam_data = oa.zero_pad(d.x_data, d.y_data, d.a_data, 100)
     x_data, y_data, phase_data = oa.zero_pad(d.x_data, d.y_data, d.p_data, 100)
     beam_fft, phase_fft = oa.a2b(beam_data, np.rad2deg(phase_data))
-    assert np.abs(beam_fft - g["beam_fft"]).max() < 1e-3 * np.abs(g["beam_fft"]).max()
+    assert np.abs(beam_fft - g["beam_fft"]).max() < 3e-4 * np.abs(g["beam_fft"]).max()
     x_ang, y_ang = oa.coords_spat_to_ang(x_data / 1e2, y_data / 1e2, oa.m_to_ghz(t.lambda_))
     assert abs(rt.ff_fwhm_est(beam_fft, x_ang, y_ang) - float(g["fwhm"])) < 1e-3
     assert "%.2f" % rt.ff_fwhm_est(beam_fft, x_ang, y_ang) == "21.50"
     assert "%.2f" % rt.ff_fwhm_device(beam_fft, x_ang, y_ang) == "21.50"
+    with pytest.raises(ValueError, match="ray_index"):
+        rt.sim2d(rt.SimOutput(sb.x_sim, sb.y_sim, sb.a_sim, sb.p_sim, sb.tan_og))
+
+
+def test_sim_data_on_the_device_matches_reference_golden(mods):
+    """sim_data alone, on the 100 x 100 grids the reference's sim2d produced: the reference's
+    stage-grid arrays to fp64 rounding, for both notebook stage grids (40^2 and 800^2)."""
+    from types import SimpleNamespace
+    rt = mods["rt"]
+    g = golden("farfield_cfg2_240.npz")
+    sb2 = SimpleNamespace(a_sim=g["sb2_a"], p_sim=g["sb2_p"], x_sim=g["sb2_x"], y_sim=g["sb2_y"])
+    d = rt.sim_data(sb2, 80, 2)
+    assert d.a_data.shape == g["a_data"].shape
+    assert np.abs(d.a_data - g["a_data"]).max() < 1e-12
+    assert np.abs(d.p_data - g["p_data"]).max() < 1e-11
+    g = golden("farfield_cfg2loop_1000_90ghz.npz")
+    sb2 = SimpleNamespace(a_sim=g["sb2_a"], p_sim=g["sb2_p"], x_sim=g["sb2_x"], y_sim=g["sb2_y"])
+    d = rt.sim_data(sb2, float(g["stage_range"]), float(g["step"]))
+    assert d.a_data.shape == (800, 800)
+    assert np.abs(np.diag(d.a_data) - g["a_data_diag"]).max() < 1e-12
+    assert np.abs(np.diag(d.p_data) - g["p_data_diag"]).max() < 1e-11
+    assert np.sum(d.a_data) == pytest.approx(float(g["a_data_checksum"]), rel=1e-11)
+    assert np.sum(d.p_data) == pytest.approx(float(g["p_data_checksum"]), rel=1e-9, abs=1e-8)
+
+
+def test_notebook_1000_route_end_to_end_on_the_device(mods):
+    """sat_farfield.ipynb cell 8 at 90 GHz, every step on the GPU: n_scan = 150 trace, sim2d,
+    sim_data(200, .25) -> 800^2, zero_pad -> 1000^2, a2b; against the reference's grids, samples
+    of its far field and 'Estimated FWHM: 27.53 arcmin'."""
+    g = golden("farfield_cfg2loop_1000_90ghz.npz")
+    rt, oa = mods["rt"], mods["oa"]
+    t = _notebook_geo(mods, g, 150, sqrt2=True)
+    sb = rt.getNearField(t, [0, 0, 0], plot=False)
+    assert len(sb.a_sim) == 15312
+    sb2 = rt.sim2d(sb)
+    assert np.abs(sb2.x_sim - g["sb2_x"]).max() < 1e-9
+    assert np.abs(sb2.a_sim - g["sb2_a"]).max() < 1e-4
+    d = rt.sim_data(sb2, float(g["stage_range"]), float(g["step"]))
+    assert np.abs(np.diag(d.a_data) - g["a_data_diag"]).max() < 1e-4
+    x_new, y_new, beam_data = oa.zero_pad(d.x_data, d.y_data, d.a_data, 100)
+    x_data, y_data, phase_data = oa.zero_pad(d.x_data, d.y_data, d.p_data, 100)
+    beam_fft, phase_fft = oa.a2b(beam_data, np.rad2deg(phase_data))
+    assert beam_fft.shape == (1000, 1000)
+    peak = abs(g["peak_value"])
+    idx = g["sample_index"]
+    assert np.abs(beam_fft[idx[:, 0], idx[:, 1]] - g["sample_value"]).max() < 1e-3 * peak
+    assert tuple(np.unravel_index(np.argmax(abs(beam_fft)), beam_fft.shape)) == tuple(g["peak_index"])
+    x_ang, y_ang = oa.coords_spat_to_ang(x_data / 1e2, y_data / 1e2, oa.m_to_ghz(float(g["lambda_"])))
+    assert "%.2f" % rt.ff_fwhm_est(beam_fft, x_ang, y_ang) == "27.53"
+
+
+def test_sim2d_off_axis_feed_against_scipy_griddata(mods):
+    """The lattice triangulation is not tied to the boresight symmetry: an off-axis feed, against
+    scipy's own griddata on the same rays (test infrastructure only; amplitude, whose
+    interpolation is well conditioned)."""
+    from scipy.interpolate import griddata
+    rt = mods["rt"]
+    g = golden("farfield_cfg2_240.npz")
+    t = _notebook_geo(mods, g, 80)
+    sb = rt.getNearField(t, [70, 0, -40], plot=False)
+    sb2 = rt.sim2d(sb)
+    cx, cy = np.mean(sb.x_sim), np.mean(sb.y_sim)
+    sel = (sb.x_sim - cx) ** 2 + (sb.y_sim - cy) ** 2 <= 21.0 ** 2
+    pts = np.array([sb.x_sim[sel], sb.y_sim[sel]]).T
+    want = griddata(pts, sb.a_sim[sel], (sb2.x_sim, sb2.y_sim), method="cubic")
+    want = np.where((sb2.x_sim - cx) ** 2 + (sb2.y_sim - cy) ** 2 >= 400, 0, np.nan_to_num(want))
+    assert sb2.x_sim[0, 0] == pts[:, 0].min() and sb2.y_sim[-1, -1] == pytest.approx(pts[:, 1].max(), rel=1e-14)
+    assert np.abs(sb2.a_sim - want).max() < 1e-4
 
 
 @pytest.mark.parametrize("n_scan", [65536, 65537])

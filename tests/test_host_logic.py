@@ -180,17 +180,37 @@ def test_ray_sharded_near_field_world2_gloo():
         assert sweep == [(0, 0), (1, 1), (2, 0), (3, 1), (4, 0)]
 
 
-def test_sim_data_glue_matches_reference_golden():
-    """Row f1 host glue: sim_data on the 100 x 100 grid the reference's sim2d produced gives the
-    reference's stage-grid arrays (RectBivariateSpline stands in for the removed interp2d)."""
-    from types import SimpleNamespace
+def test_spline_operator_reproduces_the_reference_sim_data_golden():
+    """Row f1: ``sim_data``'s bicubic spline resampling is the separable linear map My z Mx^T of
+    the grid values; the operators ``ray_trace._cubic_spline_operator`` builds (FITPACK's
+    not-a-knot knots, clamped arguments) applied in numpy to the 100 x 100 grid the reference's
+    sim2d produced give the reference's stage-grid arrays -- the arithmetic the device runs."""
     g = golden("farfield_cfg2_240.npz")
-    sb2 = SimpleNamespace(a_sim=g["sb2_a"], p_sim=g["sb2_p"], x_sim=g["sb2_x"], y_sim=g["sb2_y"])
-    d = ray_trace.sim_data(sb2, 80, 2)
-    assert d.a_data.shape == g["a_data"].shape
-    assert np.abs(d.a_data - g["a_data"]).max() < 1e-12
-    assert np.abs(d.p_data - g["p_data"]).max() < 1e-12
-    assert np.array_equal(d.x_data, g["x_data"]) and np.array_equal(d.y_data, g["y_data"])
+    a, p = g["sb2_a"], g["sb2_p"]
+    x_data = np.arange(-40.0, 40.0, 2)
+    Mx = ray_trace._cubic_spline_operator(g["sb2_x"][:, 0], x_data)
+    My = ray_trace._cubic_spline_operator(g["sb2_y"][0, :], x_data)
+    beam = a.T * np.exp(1j * p.T)
+    amp = My @ (np.abs(beam) / np.abs(beam).max()) @ Mx.T
+    ph = My @ np.arctan2(beam.imag, beam.real) @ Mx.T
+    assert np.abs(amp / amp.max() - g["a_data"]).max() < 1e-12
+    assert np.abs(ph - g["p_data"]).max() < 1e-12
+
+
+def test_spline_operator_matches_fitpack_on_an_irregular_grid():
+    from scipy.interpolate import RectBivariateSpline
+    rng = np.random.default_rng(4)
+    x = np.sort(rng.uniform(-3, 5, 37))
+    y = np.sort(rng.uniform(0, 2, 11))
+    z = rng.standard_normal((len(y), len(x)))
+    xn = np.linspace(-4, 6, 53)     # beyond both ends: clamped like fpbisp
+    yn = np.linspace(-0.5, 2.5, 29)
+    want = RectBivariateSpline(x, y, z.T, kx=3, ky=3, s=0)(xn, yn).T
+    got = ray_trace._cubic_spline_operator(y, yn) @ z @ ray_trace._cubic_spline_operator(x, xn).T
+    assert np.abs(got - want).max() < 1e-11 * np.abs(want).max()
+    with pytest.raises(ValueError):
+        ray_trace._cubic_spline_operator([0.0, 1.0, 1.0, 2.0], [0.5])
+
 
 
 def test_peer_plane_layout_and_cell_slabs():
