@@ -231,7 +231,28 @@ def gen_convolve(mods, fw):
     np.savez_compressed(os.path.join(GOLD, "b2a_convolve_small.npz"), **store)
 
 
-GENS = dict(convolve=gen_convolve, feedhorn=gen_feedhorn, trace=gen_trace, a2b=gen_a2b, farfield=gen_farfield,
+def gen_ot_geo(mods, fw):
+    """The reference's Python-level surface functions (sag, slope, frame maps) at seeded points,
+    incl. radii beyond the conic domain of lens 1b (NaN) -- ot_geo.py:49-458."""
+    ot_geo, ray_trace, opt_analyze = mods
+    rng = np.random.default_rng(11)
+    x = rng.uniform(-320, 320, 257)
+    y = rng.uniform(-320, 320, 257)
+    z = rng.uniform(-50, 900, 257)
+    store = dict(x=x, y=y, z=z)
+    with np.errstate(invalid="ignore"):
+        for name in ("1a", "1b", "2a", "2b", "3a", "3b"):
+            store[f"z{name}"] = getattr(ot_geo, f"z{name}")(x, y)
+            gx, gy = getattr(ot_geo, f"d_z{name}")(x, y)
+            store[f"d_z{name}_x"], store[f"d_z{name}_y"] = gx, gy
+            store[f"m{name}_into_tele"] = np.array(getattr(ot_geo, f"m{name}_into_tele")(x, y, z))
+            # the reference shifts y in place: hand it copies
+            store[f"tele_into_m{name}"] = np.array(
+                getattr(ot_geo, f"tele_into_m{name}")(x.copy(), y.copy(), z.copy()))
+    np.savez_compressed(os.path.join(GOLD, "ot_geo_surfaces.npz"), **store)
+
+
+GENS = dict(ot_geo=gen_ot_geo, convolve=gen_convolve, feedhorn=gen_feedhorn, trace=gen_trace, a2b=gen_a2b, farfield=gen_farfield,
             reqs=gen_reqs)
 
 if __name__ == "__main__":

@@ -4,8 +4,12 @@ Mirrors the part of the reference's ``sosat_optics/ot_geo.py`` that the ray trac
 the mutable ``SatGeo`` parameter bag (ot_geo.py:8-29), the lens placement constants
 (ot_geo.py:32-46) and the asphere coefficients, which the reference keeps as literals inside
 each ``z??`` / ``d_z??`` function (e.g. ot_geo.py:57-61) and which are collected here into
-one table, :data:`SURFACES`, in trace order.  The surface evaluation itself (sag, slope, frame
-maps) runs inside the CUDA kernel (csrc/trace_device.cuh); plotting helpers
+one table, :data:`SURFACES`, in trace order.  The ray tracer evaluates the surfaces inside the
+CUDA kernel (csrc/trace_device.cuh); the reference's Python-level surface functions -- sag
+``z1a .. z3b`` (ot_geo.py:49-91, 182-227, 313-354), slope ``d_z1a .. d_z3b`` (:94-143, 230-276,
+364-414) and the frame maps ``tele_into_m??`` / ``m??_into_tele`` (:146-179, 279-310, 417-458)
+-- are generated below from the same table so that ``from ot_geo import *`` keeps providing
+them (numpy, same arithmetic order; they are not on the hot path).  Plotting helpers
 (``plot_lenses``, ``filt``) are out of scope.
 """
 from __future__ import annotations
@@ -91,3 +95,54 @@ SURFACES = (
     Surface("1a", 9.65674282e-3, -30.00122787, 1.45021174e-3, 2.84858123e-6,
             -5.02176737e-9, lens1_y + lens_t1, "si", "vac", 5.0, 220.0),  # :79-83, :174
 )
+
+
+# ---- the reference's Python-level surface functions, generated from SURFACES --------------------
+_TILT = {"1a": "th1_l1", "1b": "th1_l1", "2a": "th2_l2", "2b": "th1_l2", "3a": "th1_l3", "3b": "th2_l3"}
+
+
+def _make_surface_functions(surf: Surface):
+    c, k, a_1, a_2, a_3, y0 = surf.c, surf.k, surf.a1, surf.a2, surf.a3, surf.y0
+    th = globals()[_TILT[surf.name]]
+
+    def sag(x, y):
+        """Surface sag [mm] at local (x, y) [mm]: 10 [c r^2 / (1 + sqrt(1 - (1+k) c^2 r^2)) +
+        a1 r^2 + a2 r^4 + a3 r^6], r in cm (NaN outside the conic domain, as in the reference)."""
+        x_temp = x / 1e1
+        y_temp = y / 1e1
+        r = np.sqrt(x_temp ** 2 + y_temp ** 2)
+        amp = (c * r ** 2) / (1 + np.sqrt(1 - ((1 + k) * c ** 2 * r ** 2)))
+        amp += a_1 * r ** 2 + a_2 * r ** 4 + a_3 * r ** 6
+        return amp * 10
+
+    def slope(x, y):
+        """(d sag / dx, d sag / dy) at local (x, y) [mm], dimensionless."""
+        x_temp = x / 1e1
+        y_temp = y / 1e1
+        r = np.sqrt(x_temp ** 2 + y_temp ** 2)
+        root = np.sqrt(1 - ((1 + k) * c ** 2 * r ** 2))
+        coeff_1 = (a_1 * 2) + (a_2 * 4 * r ** 2) + (a_3 * 6 * r ** 4)
+        coeff_2 = (c * 2) / (1 + root)
+        coeff_3 = (c ** 3 * (k + 1) * r ** 2) / (root * (1 + root) ** 2)
+        return x_temp * (coeff_1 + coeff_2 + coeff_3), y_temp * (coeff_1 + coeff_2 + coeff_3)
+
+    def into_tele(x, y, z):
+        """Surface frame -> telescope frame: rotate by the tilt about x, shift to the vertex."""
+        return x, (y * np.cos(th) - z * np.sin(th)) + y0, y * np.sin(th) + z * np.cos(th)
+
+    def tele_into(x, y, z):
+        """Telescope frame -> surface frame.  (The reference shifts ``y`` in place, which mutates
+        an array argument; this version leaves its arguments alone.)"""
+        y = y - y0
+        return x, y * np.cos(-th) - z * np.sin(-th), y * np.sin(-th) + z * np.cos(-th)
+
+    return sag, slope, into_tele, tele_into
+
+
+for _s in SURFACES:
+    _sag, _slope, _into, _from = _make_surface_functions(_s)
+    for _name, _fn in ((f"z{_s.name}", _sag), (f"d_z{_s.name}", _slope),
+                       (f"m{_s.name}_into_tele", _into), (f"tele_into_m{_s.name}", _from)):
+        _fn.__name__ = _fn.__qualname__ = _name
+        globals()[_name] = _fn
+del _s, _sag, _slope, _into, _from, _name, _fn

@@ -896,3 +896,31 @@ def test_ff_fwhm_search_batch_and_nan_guard(mods):
         rt.ff_fwhm_indices_device(bad)
     with pytest.raises(ValueError, match="no finite"):
         rt.ff_fwhm_indices_device(torch.zeros((1, n, n), dtype=torch.complex64, device="cuda"))
+
+
+def test_ot_geo_python_surface_functions_agree_with_the_kernel(mods):
+    """The Python-level ot_geo functions (z1a, d_z1a, tele_into_m1a, m1a_into_tele) and the
+    kernel describe the same last surface: walking every valid ray of rx_to_lyot's table back
+    from the source plane along its exit direction (rows 0-2, 8-10) to the root of
+    z_l - z1a(x_l, y_l) reproduces the surface normal the kernel stored (rows 5-7)."""
+    rt, ot_geo = mods["rt"], mods["ot_geo"]
+    t = _bundle(mods, 64)
+    out = rt.rx_to_lyot([30, 0, -20], t)
+    m = out[4] != 0
+    P, d, nrm = out[0:3][:, m], out[8:11][:, m], out[5:8][:, m]
+
+    def f(s):
+        x_l, y_l, z_l = ot_geo.tele_into_m1a(P[0] - s * d[0], P[1] - s * d[1], P[2] - s * d[2])
+        return z_l - ot_geo.z1a(x_l, y_l)
+
+    s = (P[1] - (ot_geo.lens1_y + ot_geo.lens_t1)) / d[1]   # back to the vertex plane
+    for _ in range(8):                                       # Newton with a numerical slope
+        h = 1e-4
+        s = s - f(s) * (2 * h) / (f(s + h) - f(s - h))
+    assert np.abs(f(s)).max() < 1e-9
+    x_l, y_l, _ = ot_geo.tele_into_m1a(P[0] - s * d[0], P[1] - s * d[1], P[2] - s * d[2])
+    gx, gy = ot_geo.d_z1a(x_l, y_l)
+    norm = np.sqrt(gx ** 2 + gy ** 2 + 1)
+    o = np.array(ot_geo.m1a_into_tele(0.0, 0.0, 0.0))
+    n_tele = np.array(ot_geo.m1a_into_tele(-gx / norm, -gy / norm, 1 / norm)) - o[:, None]
+    assert np.abs(n_tele - nrm).max() < 1e-9

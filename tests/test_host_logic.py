@@ -236,3 +236,29 @@ def test_peer_plane_layout_and_cell_slabs():
             assert all((b % 4 == 0 and e > b) or e == b for b, e in slabs)  # empty slabs allowed
             sizes = [e - b for b, e in slabs if e > b]
             assert max(sizes) - min(sizes) < 8 or len(sizes) < world  # one 4-cell unit + ragged tail
+
+
+def test_ot_geo_surface_functions_match_the_reference():
+    """``from ot_geo import *`` still provides the reference's Python-level sag / slope / frame
+    functions (ot_geo.py:49-458); values of the reference itself at seeded points, incl. NaN
+    beyond the conic domain of lens 1b (golden: oracle/make_golden.py ot_geo)."""
+    from sosat_optics_b200 import ot_geo
+    g = golden("ot_geo_surfaces.npz")
+    x, y, z = g["x"], g["y"], g["z"]
+    with np.errstate(invalid="ignore"):
+        for name in ("1a", "1b", "2a", "2b", "3a", "3b"):
+            sag = getattr(ot_geo, f"z{name}")(x, y)
+            assert np.array_equal(np.isnan(sag), np.isnan(g[f"z{name}"]))
+            assert np.allclose(sag, g[f"z{name}"], rtol=1e-14, atol=0, equal_nan=True)
+            gx, gy = getattr(ot_geo, f"d_z{name}")(x, y)
+            assert np.allclose(gx, g[f"d_z{name}_x"], rtol=1e-13, atol=0, equal_nan=True)
+            assert np.allclose(gy, g[f"d_z{name}_y"], rtol=1e-13, atol=0, equal_nan=True)
+            y_keep = y.copy()
+            fwd = np.array(getattr(ot_geo, f"tele_into_m{name}")(x, y, z))
+            assert np.array_equal(y, y_keep)                     # arguments are left alone
+            assert np.allclose(fwd, g[f"tele_into_m{name}"], rtol=1e-14, atol=1e-12)
+            back = np.array(getattr(ot_geo, f"m{name}_into_tele")(x, y, z))
+            assert np.allclose(back, g[f"m{name}_into_tele"], rtol=1e-14, atol=1e-12)
+            rt = getattr(ot_geo, f"m{name}_into_tele")(*getattr(ot_geo, f"tele_into_m{name}")(x, y, z))
+            assert np.allclose(np.array(rt), np.array([x, y, z]), atol=1e-10)
+    assert "1.5 * 2" not in ot_geo.z1b.__doc__ and ot_geo.z1b.__name__ == "z1b"
