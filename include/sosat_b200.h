@@ -98,6 +98,12 @@ enum {
 
 /* ---- library / device ------------------------------------------------------------- */
 int sosat_abi_version(void);
+/* Bit 0 (SOSAT_BUILD_EXPERIMENTS): the library was compiled with -DSOSAT_EXPERIMENTS and also
+ * holds the kernels that lost their A/B runs (other Newton schedules, split-K / one-tile-per-CTA
+ * far-field kernels, DESIGN.md sections 3-4), selectable by SOSAT_TRACE_VARIANT / SOSAT_GEMM_*
+ * environment variables.  The product library is built without them. */
+#define SOSAT_BUILD_EXPERIMENTS 1
+int sosat_build_flags(void);
 const char *sosat_last_error(void);
 int sosat_device_count(void);
 int sosat_set_device(int device);

@@ -40,6 +40,7 @@ class Freq(Structure):
 # name -> (restype, argtypes); mirrors include/sosat_b200.h one to one
 SIGNATURES = {
     "sosat_abi_version": (c_int, []),
+    "sosat_build_flags": (c_int, []),
     "sosat_last_error": (c_char_p, []),
     "sosat_device_count": (c_int, []),
     "sosat_set_device": (c_int, [c_int]),
@@ -138,6 +139,11 @@ def load():
         raise ImportError(f"{LIB_PATH}: ABI version {lib.sosat_abi_version()} != 1")
     _lib = lib
     return lib
+
+
+def has_experiments() -> bool:
+    """True if the loaded library was built with -DSOSAT_EXPERIMENTS (scripts/ab_build.py)."""
+    return bool(load().sosat_build_flags() & 1)
 
 
 def check(rc: int) -> None:

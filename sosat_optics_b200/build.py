@@ -39,11 +39,21 @@ def _stale(target: str, deps) -> bool:
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force: bool = False, verbose: bool = False) -> str:
+def build(force: bool = False, verbose: bool = False, experiments: bool = False) -> str:
+    """Compile the product library; ``experiments=True`` builds ``libsosat_b200_exp.so`` instead,
+    with -DSOSAT_EXPERIMENTS (the kernels that lost their A/B runs, for scripts/ab_* and the
+    variant-agreement tests: point SOSAT_LIB at it)."""
+    if experiments:
+        return _build("libsosat_b200_exp.so", "_obj_exp", ["-DSOSAT_EXPERIMENTS"], force, verbose)
+    return _build("libsosat_b200.so", "_obj", [], force, verbose)
+
+
+def _build(lib_name: str, obj_name: str, extra, force: bool, verbose: bool) -> str:
+    LIB_PATH = os.path.join(PKG, lib_name)  # noqa: N806
     deps = [os.path.join(CSRC, h) for h in HEADERS] + [os.path.join(INCLUDE, "sosat_b200.h"),
                                                        os.path.abspath(__file__)]
     objs = []
-    obj_dir = os.path.join(CSRC, "_obj")
+    obj_dir = os.path.join(CSRC, obj_name)
     os.makedirs(obj_dir, exist_ok=True)
     procs = []
     for src in SOURCES:
@@ -51,7 +61,7 @@ def build(force: bool = False, verbose: bool = False) -> str:
         o = os.path.join(obj_dir, src.replace(".cu", ".o"))
         objs.append(o)
         if force or _stale(o, deps + [s]):
-            cmd = [_nvcc(), *NVCC_FLAGS, "-I", INCLUDE, "-I", CSRC, "-c", s, "-o", o]
+            cmd = [_nvcc(), *NVCC_FLAGS, *extra, "-I", INCLUDE, "-I", CSRC, "-c", s, "-o", o]
             if verbose:
                 cmd.insert(1, "-Xptxas")
                 cmd.insert(2, "-v")
@@ -70,4 +80,5 @@ def build(force: bool = False, verbose: bool = False) -> str:
 
 
 if __name__ == "__main__":
-    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv))
+    print(build(force="--force" in sys.argv, verbose="--verbose" in sys.argv,
+                experiments="--experiments" in sys.argv))

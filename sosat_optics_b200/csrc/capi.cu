@@ -24,6 +24,14 @@ using namespace sosat;
 
 extern "C" int sosat_abi_version(void) { return SOSAT_ABI_VERSION; }
 
+extern "C" int sosat_build_flags(void) {
+#ifdef SOSAT_EXPERIMENTS
+    return SOSAT_BUILD_EXPERIMENTS;
+#else
+    return 0;
+#endif
+}
+
 extern "C" const char *sosat_last_error(void) { return error_buffer(); }
 
 extern "C" int sosat_device_count(void) {

@@ -439,6 +439,7 @@ struct PairBatch {
     long long out_stride;  // floats between the outputs of consecutive items (2 n^2)
 };
 
+#ifdef SOSAT_EXPERIMENTS  // one-tile-per-CTA form of the pair kernel (A/B runs: SOSAT_GEMM_PERSIST=0, SOSAT_GEMM_PAIR)
 template <int EPI, int BN2>
 __global__ void __launch_bounds__(128, 1)
 gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
@@ -549,6 +550,7 @@ gemm2_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                      "r"(Cfg::kTmem) : "memory");
 }
 
+#endif  // SOSAT_EXPERIMENTS
 // ---- persistent CTA-pair kernel: one pair per TPC, two TMEM accumulator stages -----------------
 // The 256 x 256 pair-tile kernel above as a persistent loop: a pair walks the pair tiles
 // t = pair, pair + P, ... and the accumulator alternates between two 256-column TMEM stages, so
@@ -703,6 +705,7 @@ gemm2p_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                      "r"(512) : "memory");
 }
 
+#ifdef SOSAT_EXPERIMENTS  // cluster-of-four split-K kernel (measured slower, SOSAT_GEMM_QUAD=1)
 // ---- two CTA pairs per tile: split-K inside a cluster of four ---------------------------------
 // For sizes whose 256 x 256 pair tiles cannot fill the machine (1024^2: 32 tiles, 74 TPCs) a
 // cluster of FOUR CTAs takes one tile: ranks (0,1) and (2,3) are two cta_group::2 pairs, each
@@ -838,6 +841,7 @@ gemm2k_bf16x3_kernel(const __grid_constant__ CUtensorMap map_a_hi,
                      "r"(BN2) : "memory");
 }
 
+#endif  // SOSAT_EXPERIMENTS
 // ---- operand preparation (HBM-bound elementwise kernels) -----------------------------------
 __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bfloat16 &lo) {
     hi = __float2bfloat16_rn(x);
@@ -973,6 +977,7 @@ prep_b_a2b_kernel(const double *__restrict__ amp, const double *__restrict__ phi
         n, np, b_hi, b_lo);
 }
 
+#ifdef SOSAT_EXPERIMENTS  // split-K helper kernels (measured slower, SOSAT_GEMM_SPLITK=1)
 // Split-K pass 1 leaves fp32 sums in src [n]: split them into the bf16 hi/lo operand of pass 2,
 // zero src in place for the next transform and zero the output the second pass reduces into.
 __global__ void split_f32_kernel(float *__restrict__ src, long long n, __nv_bfloat16 *__restrict__ hi,
@@ -1009,6 +1014,7 @@ __global__ void zero_f32_kernel(float *__restrict__ dst, long long n) {
         ((float4 *)dst)[i] = make_float4(0.f, 0.f, 0.f, 0.f);
 }
 
+#endif  // SOSAT_EXPERIMENTS
 // a2b / b2a outputs from the complex64 transform: complex128 field and phase =
 // arctan2(imag, real), opt_analyze.py:215-216, 228-229
 __global__ void finish_a2b_kernel(const float2 *__restrict__ c64, long long n2,
@@ -1229,6 +1235,7 @@ static int launch_gemm(dim3 grid, cudaStream_t st, const CUtensorMap *m, int num
                       m[1], m[2], m[3], num_kb, c64, d_hi, d_lo, ldd, n_valid, scale);
 }
 
+#ifdef SOSAT_EXPERIMENTS  // launcher of the one-tile-per-CTA pair kernel
 // grid = (M tiles of 128, N tiles of BN2): the pair kernel indexes M tiles with blockIdx.x
 template <int EPI, int BN2>
 static int launch_gemm_pair(dim3 grid, cudaStream_t st, const CUtensorMap *m, int num_kb, float *c64,
@@ -1247,6 +1254,7 @@ static int launch_gemm_pair(dim3 grid, cudaStream_t st, const CUtensorMap *m, in
                       m[0], m[1], m[2], m[3], num_kb, c64, d_hi, d_lo, ldd, n_valid, scale, pb);
 }
 
+#endif  // SOSAT_EXPERIMENTS
 // persistent form of the 256 x 256 pair kernel: grid = one pair per TPC (or per tile if fewer)
 template <int EPI>
 static int launch_gemm_pair_persistent(int m_tiles, int n_tiles256, cudaStream_t st,
@@ -1273,14 +1281,19 @@ static int launch_gemm_pair_persistent(int m_tiles, int n_tiles256, cudaStream_t
 
 // SOSAT_GEMM_PERSIST=0 selects the one-tile-per-CTA pair kernel for A/B runs
 static bool use_persistent_pair() {
+#ifdef SOSAT_EXPERIMENTS
     static int v = -1;
     if (v < 0) {
         const char *e = getenv("SOSAT_GEMM_PERSIST");
         v = e ? (atoi(e) != 0) : 1;
     }
     return v != 0;
+#else
+    return true;
+#endif
 }
 
+#ifdef SOSAT_EXPERIMENTS  // launchers / switches of the split-K experiments
 template <int EPI>
 static int launch_gemm_quad(int m_tiles, int n_tiles256, cudaStream_t st, const CUtensorMap *m,
                             int num_kb, float4 *scratch, float *c64, __nv_bfloat16 *d_hi,
@@ -1329,14 +1342,17 @@ static bool use_split_k() {
 //   CTA pair, 256 x 256 pair tiles                              0.098 / 0.324
 // The 256 x 256 pair tile is the only shape that is not shared-memory-pipe bound, but it needs
 // enough tiles to fill the machine: it is used when a pass has >= 120 CTAs (np >= 1536).
+#endif  // SOSAT_EXPERIMENTS
 // SOSAT_GEMM_PAIR = 0 / 128 / 256 overrides the choice for A/B runs.
 static int pair_kernel_width(int np) {
+#ifdef SOSAT_EXPERIMENTS
     static int v = -2;
     if (v == -2) {
         const char *e = getenv("SOSAT_GEMM_PAIR");
         v = e ? atoi(e) : -1;
     }
     if (v >= 0) return v;
+#endif
     return (np % 256 == 0 && (2 * np / BM) * (np / 256) >= 120) ? 256 : 0;
 }
 
@@ -1350,6 +1366,7 @@ static int run_passes(const DftWorkspace &w, const PlanEntry &pl, float scale, f
     int rc;
     const int pw = BK == 64 ? pair_kernel_width(w.np) : 0;
     const unsigned mt1 = 2 * w.np / BM, mt2 = w.np / BM;  // M tiles of pass 1 / pass 2
+#ifdef SOSAT_EXPERIMENTS
     // Cluster-of-four split-K (two CTA pairs per pair tile, partial sums through an L2-resident
     // scratch tile) for sizes with at most one tile per four SMs: 512^2 ... 1024^2.  Scratch:
     // pass 1 uses the complex64 staging area, pass 2 the (by then consumed) X operand.
@@ -1398,6 +1415,7 @@ static int run_passes(const DftWorkspace &w, const PlanEntry &pl, float scale, f
                                                             PairBatch{0, 0, 0, 0}, ksplit);
         }
     }
+#endif  // SOSAT_EXPERIMENTS
     if (pw == 256 && pl.wide && use_persistent_pair()) {
         if ((rc = launch_gemm_pair_persistent<EPI_SPLIT_BF16>((int)mt1, w.np / 256, st, pl.pair256,
                                                               num_kb, nullptr, w.d1_hi, w.d1_lo,
@@ -1405,6 +1423,7 @@ static int run_passes(const DftWorkspace &w, const PlanEntry &pl, float scale, f
         return launch_gemm_pair_persistent<EPI_C64>((int)mt2, 2 * w.np / 256, st, pl.pair256 + 4,
                                                     num_kb, d_c64, nullptr, nullptr, 0, n_out, scale);
     }
+#ifdef SOSAT_EXPERIMENTS
     if (pw == 256 && pl.wide) {
         if ((rc = launch_gemm_pair<EPI_SPLIT_BF16, 256>(dim3(mt1, w.np / 256), st, pl.pair256, num_kb,
                                                         nullptr, w.d1_hi, w.d1_lo, w.np, 0, 1.f)))
@@ -1423,6 +1442,7 @@ static int run_passes(const DftWorkspace &w, const PlanEntry &pl, float scale, f
         return launch_gemm<EPI_C64, 2, 1>(g2, st, pl.maps + 4, num_kb, d_c64, nullptr, nullptr, 0,
                                           n_out, scale);
     }
+#endif  // SOSAT_EXPERIMENTS
     if (pl.wide) {
         if ((rc = launch_gemm<EPI_SPLIT_BF16, 2, 2>(g1, st, pl.maps, num_kb, nullptr, w.d1_hi,
                                                     w.d1_lo, w.np, 0, 1.f))) return rc;
@@ -1564,11 +1584,15 @@ extern "C" int sosat_dft2_gemm_batch(const float *d_b, int n, int batch, float *
         return launch_gemm_pair_persistent<EPI_C64>(w.np / BM * batch, 2 * w.np / 256, st, m2, num_kb,
                                                     d_B, nullptr, nullptr, 0, w.n, (float)scale, pb);
     }
+#ifdef SOSAT_EXPERIMENTS
     if ((rc = launch_gemm_pair<EPI_SPLIT_BF16, 256>(dim3(2 * w.np / BM, w.np * batch / 256), st, m1,
                                                     num_kb, nullptr, d1_hi, d1_lo, w.np * batch, 0,
                                                     1.f))) return rc;
     return launch_gemm_pair<EPI_C64, 256>(dim3(w.np / BM * batch, 2 * w.np / 256), st, m2, num_kb, d_B,
                                           nullptr, nullptr, 0, w.n, (float)scale, pb);
+#else
+    return set_error(SOSAT_ERR_UNSUPPORTED, "unreachable: the persistent pair kernel is the only batch path");
+#endif
 }
 
 extern "C" int sosat_dft2_gemm(const float *d_b, int n, float *d_B, void *d_workspace,

@@ -612,8 +612,12 @@ __global__ void __launch_bounds__(256) fp64_peak_kernel(double *out, int iters, 
 // SOSAT_TRACE_VARIANT = 0: 0+5, 2: 3+2, 6: 2+2 (the default until v3) select the other
 // compiled schedules for experiments and for the parity test of the schedules.
 static int trace_variant() {
+#ifdef SOSAT_EXPERIMENTS
     const char *e = getenv("SOSAT_TRACE_VARIANT");
     return e ? atoi(e) : 7;
+#else
+    return 7;  // the other schedules are compiled with -DSOSAT_EXPERIMENTS only
+#endif
 }
 
 static void fill_linspace(double cone, int n_scan, double &start, double &stop, double &step) {
@@ -736,9 +740,11 @@ static int trace_rows_common(const double *h_rx, const sosat_freq_t *h_freq, int
         launch_rows<2, 1, true>(geo, p, nullptr, d_samples, d_stats, st);
     } else {
         switch (trace_variant()) {
+#ifdef SOSAT_EXPERIMENTS
             case 0: launch_rows<0, 5, false>(geo, p, d_out, nullptr, d_stats, st); break;
             case 2: launch_rows<3, 2, false>(geo, p, d_out, nullptr, d_stats, st); break;
             case 6: launch_rows<2, 2, false>(geo, p, d_out, nullptr, d_stats, st); break;
+#endif
             default: launch_rows<2, 1, false>(geo, p, d_out, nullptr, d_stats, st); break;
         }
     }
@@ -839,9 +845,8 @@ static void launch_bin_minb(int geo, int minb, const BinParams &p, const double 
     if (geo == 2) return launch_bin<N32, N64, 4, 2>(p, rx, re, im, cnt, stats, st);
     if (geo == 1) return launch_bin<N32, N64, 4, 1>(p, rx, re, im, cnt, stats, st);
     switch (minb) {
+#ifdef SOSAT_EXPERIMENTS
         case 3: launch_bin<N32, N64, 3, 0>(p, rx, re, im, cnt, stats, st); break;
-#ifdef SOSAT_BIN_MINB5
-        case 5: launch_bin<N32, N64, 5, 0>(p, rx, re, im, cnt, stats, st); break;
 #endif
         default: launch_bin<N32, N64, 4, 0>(p, rx, re, im, cnt, stats, st); break;
     }
@@ -849,8 +854,12 @@ static void launch_bin_minb(int geo, int minb, const BinParams &p, const double 
 
 // resident CTAs per SM the binning kernel is compiled for (register budget 80 / 64)
 static int trace_minb() {
+#ifdef SOSAT_EXPERIMENTS
     const char *e = getenv("SOSAT_TRACE_MINB");
     return e ? atoi(e) : 4;
+#else
+    return 4;
+#endif
 }
 
 extern "C" int sosat_trace_bin(const double *d_rx, int n_rx, const sosat_freq_t *h_freq,
@@ -911,9 +920,11 @@ extern "C" int sosat_trace_bin(const double *d_rx, int n_rx, const sosat_freq_t 
     if (const char *e = getenv("SOSAT_TRACE_PREDICT")) p.predict = atoi(e) != 0;
     if (trace_variant() != 7 || geo == 2) p.predict = 0;
     switch (trace_variant()) {
+#ifdef SOSAT_EXPERIMENTS
         case 0: launch_bin_minb<0, 5>(geo, minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
         case 2: launch_bin_minb<3, 2>(geo, minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
         case 6: launch_bin_minb<2, 2>(geo, minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
+#endif
         default: launch_bin_minb<2, 1>(geo, minb, p, d_rx, d_re, d_im, d_cnt, d_stats, st); break;
     }
     SOSAT_CUDA_OK(cudaGetLastError());

@@ -310,6 +310,10 @@ def test_all_umma_kernels_agree(mods, monkeypatch, pair):
     cta_group::2 pair tiles 256 x 128 and 256 x 256) on a size where all of them are legal and on
     one that is not a multiple of 256 (the pair kernels then run pass 1 only / fall back)."""
     import subprocess, sys, os
+    import sosat_optics_b200
+    lib = os.path.join(os.path.dirname(sosat_optics_b200.__file__), "libsosat_b200_exp.so")
+    if pair != "0" and pair != "256" and not os.path.exists(lib):
+        pytest.skip("experiments library not built (python -m sosat_optics_b200.build --experiments)")
     code = (
         "import numpy as np, sys; sys.path.insert(0, %r)\n"
         "from sosat_optics_b200 import opt_analyze as oa\n"
@@ -321,6 +325,8 @@ def test_all_umma_kernels_agree(mods, monkeypatch, pair):
         "    assert err < 1e-4, (n, err)\n"
         "print('ok')\n") % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
     env = dict(os.environ)  # the switches are read once per process: run in a fresh one
+    if os.path.exists(lib):
+        env["SOSAT_LIB"] = lib  # only the experiments build honours the SOSAT_GEMM_* switches
     if pair == "splitk":   # split-K slices of the pair kernel meeting through red.global.add
         env.update(SOSAT_GEMM_SPLITK="1")
         env.pop("SOSAT_GEMM_PAIR", None)
