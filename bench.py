@@ -419,6 +419,9 @@ def run_ours(args):
         stats = torch.zeros((1, _lib.NUM_STATS), dtype=torch.float64, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")
     host_B = torch.empty((GRID_N, GRID_N), dtype=torch.complex64).pin_memory()
+    # N > 1, peer path: ONE host array shared by the ranks (POSIX shared memory, page-locked in
+    # every rank); each rank ships its slab of rank 0's far field over its own PCIe link
+    shared_B = sdist.SharedHostArray((1, 1, GRID_N, GRID_N), np.complex64) if use_peer else None
     ev = lambda: torch.cuda.Event(enable_timing=True)  # noqa: E731
 
     def step(e2e=False, kernel_events=None):
@@ -440,14 +443,19 @@ def run_ours(args):
         if kernel_events is not None:
             kernel_events[2].record()
         B = None
-        if rank == 0 or not use_peer:
+        if use_peer:
+            if rank == 0:
+                B = opt_analyze.far_field(b[0, 0], device=True, out=peer.out[0, 0])
+        else:
             B = opt_analyze.far_field(b[0, 0], device=True)
         if kernel_events is not None:
             kernel_events[3].record()
         if e2e:
-            if B is not None:
+            if use_peer:
+                peer.gather_to_host(shared_B)   # collective; returns when every slab has landed
+            else:
                 host_B.copy_(B, non_blocking=True)
-            torch.cuda.current_stream().synchronize()
+                torch.cuda.current_stream().synchronize()
         return B
 
     def barrier():
@@ -518,7 +526,7 @@ def run_ours(args):
     # its peak (fp32 accumulation order is the only difference).
     parity_n = None
     if world > 1:
-        step()                                    # leaves the reduced statistics / field behind
+        step(e2e=True)                            # leaves the reduced statistics / field behind
         torch.cuda.synchronize()
         if use_peer:
             b_multi = peer.field[0, 0].clone()
@@ -540,11 +548,15 @@ def run_ours(args):
             B1 = opt_analyze.far_field(b1, device=True)
             Bm = opt_analyze.far_field(b_multi, device=True)
             ff_err = (Bm - B1).abs().max().item() / B1.abs().max().item()
-            ok = ints_ok and opl_ok and cnt_ok and err < 1e-4 and ff_err < 1e-4
+            host_ok = None
+            if use_peer:   # the far field every rank shipped slab-wise to the shared host array
+                host_ok = bool(np.array_equal(shared_B.view()[0, 0], peer.out[0, 0].cpu().numpy()))
+            ok = ints_ok and opl_ok and cnt_ok and err < 1e-4 and ff_err < 1e-4 and host_ok is not False
             parity_n = {"status": "ok" if ok else "FAILED", "n_valid": float(hm[_lib.STAT_N_VALID]),
                         "n_binned": float(hm[_lib.STAT_N_BINNED]), "counts_equal_1gpu": bool(ints_ok and cnt_ok),
                         "sum_opl_rel_diff": float(abs(h1[_lib.STAT_SUM_OPL] - hm[_lib.STAT_SUM_OPL]) / abs(h1[_lib.STAT_SUM_OPL])),
                         "near_field_max_err_of_peak": err, "far_field_max_err_of_peak": ff_err,
+                        "shared_host_far_field_equals_device": host_ok,
                         "how": "rank 0 re-traced the whole 1.000014e9-ray bundle on one GPU after the timed region"}
             del re1, im1, cnt1, b1, B1, Bm
         dist.barrier()
@@ -556,6 +568,7 @@ def run_ours(args):
         if world > 1:
             dist.barrier()
             if use_peer:
+                shared_B.close()
                 peer.close()
             dist.destroy_process_group()
         return
@@ -764,6 +777,7 @@ def run_ours(args):
     if world > 1:
         dist.barrier()
         if use_peer:
+            shared_B.close()
             peer.close()
         dist.destroy_process_group()
     if parity_n is not None and parity_n["status"] != "ok":

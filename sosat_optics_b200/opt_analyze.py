@@ -217,7 +217,8 @@ def beam_convolve(x, y, beam, apert1, apert2, plots=0):
     return x, y, _lib.to_numpy(final).astype(np.complex128) * (scale * peak)
 
 
-def far_field(b, dx_cm=None, lam_m=None, theta_x=None, theta_y=None, *, device: bool = False):
+def far_field(b, dx_cm=None, lam_m=None, theta_x=None, theta_y=None, *, device: bool = False,
+              out=None):
     """Far field of a complex near field ``b`` [N, N] (numpy complex or CUDA complex64 tensor).
 
     Without angles: the centred 2-D DFT ``B = fftshift(fft2(fftshift(b)))``; if the cell size
@@ -228,7 +229,9 @@ def far_field(b, dx_cm=None, lam_m=None, theta_x=None, theta_y=None, *, device: 
     ``lam_m``): the zoomed matrix DFT ``B[j, k] = sum_mn b[m, n] exp(-2 pi i (y_m theta_y[j] +
     x_n theta_x[k]) / lam)`` on exactly those angles, cell centres ``x_n = (n - ceil(N/2)) dx``
     (the convention under which the FFT-bin angles reproduce the plain transform).  Returns the
-    ``[M, M]`` field.  ``device=True`` returns a CUDA complex64 tensor (no host copies)."""
+    ``[M, M]`` field.  ``device=True`` returns a CUDA complex64 tensor (no host copies); ``out``: a
+    contiguous CUDA complex64 ``[N, N]`` tensor that receives the plain transform (e.g. a view of
+    a buffer other ranks can read, ``dist.PeerPlanes.out``)."""
     lib = _lib.require_gpu()
     torch = _torch()
     if isinstance(b, np.ndarray):
@@ -256,7 +259,11 @@ def far_field(b, dx_cm=None, lam_m=None, theta_x=None, theta_y=None, *, device: 
                                        ws.numel(), _stream(torch)))
         torch.cuda.current_stream().synchronize()  # the host arrays above are read asynchronously
         return out if device else _lib.to_numpy(out)
-    out = torch.empty((n, n), dtype=torch.complex64, device="cuda")
+    if out is None:
+        out = torch.empty((n, n), dtype=torch.complex64, device="cuda")
+    elif (not out.is_cuda or out.dtype != torch.complex64 or tuple(out.shape) != (n, n)
+          or not out.is_contiguous()):
+        raise ValueError("out must be a contiguous CUDA complex64 [N, N] tensor")
     ws = _workspace(lib, torch, n)
     _lib.check(lib.sosat_dft2_gemm(ctypes.c_void_p(d_b.data_ptr()), n,
                                    ctypes.c_void_p(out.data_ptr()),

@@ -90,10 +90,22 @@ def _peer_worker(rank, world, port, q):
         for rx in RX_STEPS:  # the same buffers twice: a stale read of a peer's planes would show
             b, _, stats = sdist.near_field_binned_distributed(t, rx, 128, 42.0, peer=peer)
             out.append((b.cpu().numpy(), stats))
+        # far field of the first field on rank 0, written where the peers can read it, then shipped
+        # to ONE shared host array by both ranks (each its slab, over its own PCIe link)
+        from sosat_optics_b200 import opt_analyze as oa
+        host = sdist.SharedHostArray((2, 1, 128, 128), np.complex64)
+        if rank == 0:
+            peer.out.zero_()
+            oa.far_field(peer.field[0, 0], device=True, out=peer.out[0, 0])
+            oa.far_field(peer.field[1, 0], device=True, out=peer.out[1, 0])
+        peer.gather_to_host(host)
+        shipped = host.view().copy()
+        want = peer.out.cpu().numpy() if rank == 0 else None
         torch.cuda.synchronize()
         dist.barrier()
+        host.close()
         peer.close()
-        q.put((rank, out))
+        q.put((rank, out, shipped, want))
     finally:
         dist.destroy_process_group()
 
@@ -121,11 +133,16 @@ def test_two_gpu_peer_memory_reduce_matches_single_gpu():
     t.k = 2 * np.pi / t.lambda_
     for step, rx in enumerate(RX_STEPS):
         one = ray_trace.near_field_binned(t, rx, grid_n=128, extent_cm=42.0)
-        for rank, out in res:
+        for rank, out, _, _ in res:
             b, stats = out[step]
             assert np.abs(b - one.b).max() < 1e-4 * np.abs(one.b).max(), (step, rank)
             assert np.array_equal(stats[:, [0, 7]], one.stats[:, [0, 7]])
             assert np.allclose(stats[:, 1], one.stats[:, 1], rtol=1e-12)
+    # gather_to_host: both ranks see rank 0's far fields whole in the shared host array
+    want = res[0][3]
+    assert want is not None and np.abs(want).max() > 0
+    for rank, _, shipped, _ in res:
+        assert np.array_equal(shipped, want), rank
 
 
 def _sweep_setup():

@@ -955,3 +955,19 @@ def test_ot_geo_python_surface_functions_agree_with_the_kernel(mods):
     o = np.array(ot_geo.m1a_into_tele(0.0, 0.0, 0.0))
     n_tele = np.array(ot_geo.m1a_into_tele(-gx / norm, -gy / norm, 1 / norm)) - o[:, None]
     assert np.abs(n_tele - nrm).max() < 1e-9
+
+
+def test_large_results_come_back_through_the_staged_copy(mods, monkeypatch):
+    """_lib.to_numpy above PINNED_LIMIT_BYTES (rx_to_lyot's table at n_scan >= 2900) streams
+    through two pinned staging buffers; with the limits lowered the same table must come back
+    bit for bit, including a last chunk that is not a whole staging buffer."""
+    rt, lib, torch = mods["rt"], mods["lib"], mods["torch"]
+    t = _bundle(mods, 96)
+    want = rt.rx_to_lyot([10, 0, 5], t)
+    monkeypatch.setattr(lib, "PINNED_LIMIT_BYTES", 1 << 16)
+    monkeypatch.setattr(lib, "STAGE_BYTES", 100_000)
+    got = rt.rx_to_lyot([10, 0, 5], t)
+    assert got.shape == want.shape and got.dtype == want.dtype
+    assert np.array_equal(np.nan_to_num(got), np.nan_to_num(want))
+    x = torch.arange(300_001, dtype=torch.float64, device="cuda").reshape(1, -1)
+    assert np.array_equal(lib.to_numpy(x), np.arange(300_001, dtype=np.float64).reshape(1, -1))

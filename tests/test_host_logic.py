@@ -138,6 +138,13 @@ def _worker(rank, world, port, q):
         assert bs["peak_index"].shape == (5, 3, 2) and bs["peak_index"].dtype == np.int64
         assert np.array_equal(bs["peak_index"][:, 0, 0], rxs[:, 0].astype(np.int64))
         assert np.array_equal(bs["n_valid"], rxs[:, 2] - 1.0)
+        # one host array shared by the ranks (POSIX shared memory): every rank fills its slab
+        sh = sdist.SharedHostArray((6, 5), np.complex64)
+        c0, c1 = sdist.slab_cells(30, world, rank)
+        sh.array[c0:c1] = np.arange(c0, c1) * (1 + 1j)
+        dist.barrier()
+        assert np.array_equal(sh.view(), (np.arange(30) * (1 + 1j)).astype(np.complex64).reshape(6, 5))
+        sh.close()
         # more ranks than receivers: the idle rank still takes part in the gather
         one = sdist.beam_sweep_distributed(t, rxs[:1], [1], 8, 42.0, 0, sweep_fn=fake_sweep)
         assert one["fwhm_arcmin"].shape == (1, 1) and one["n_valid"][0] == -1.0
