@@ -163,6 +163,17 @@ int sosat_trace_bin(const double *d_rx, int n_rx, const sosat_freq_t *h_freq, in
                     double extent_mm, double opl_ref, float *d_re, float *d_im, float *d_cnt,
                     double *d_stats, void *stream);
 
+/* The same for an arbitrary set of TILE ROWS of the launch grid: tile row t = launch rows
+ * [SOSAT_TRACE_TILE_ROWS t, SOSAT_TRACE_TILE_ROWS (t + 1)) (the last one may be ragged);
+ * d_tile_rows: n_tile_rows DEVICE ints, each in [0, ceil(n_scan / SOSAT_TRACE_TILE_ROWS)), no
+ * duplicates (a duplicate is traced twice).  Multi-GPU ray sharding deals the tile rows cyclically
+ * to the ranks so that every rank traces the same mix of central and marginal rays. */
+#define SOSAT_TRACE_TILE_ROWS 16
+int sosat_trace_bin_tiles(const double *d_rx, int n_rx, const sosat_freq_t *h_freq, int n_freq,
+                          int n_scan, const int *d_tile_rows, int n_tile_rows, int grid_n,
+                          double extent_mm, double opl_ref, float *d_re, float *d_im, float *d_cnt,
+                          double *d_stats, void *stream);
+
 /* b = (re + i im)/cnt * exp(-i k_over_2e3 (mean_opl - opl_ref)) per cell (0 where cnt = 0);
  * d_b: [n][2] float32 interleaved complex.  In place over (re, im) is not supported. */
 int sosat_bins_to_field(const float *d_re, const float *d_im, const float *d_cnt, int64_t n,

@@ -21,10 +21,13 @@ im, cnt = torch.zeros_like(re), torch.zeros((1, 2048, 2048), device="cuda")
 st = torch.zeros((1, 8), dtype=torch.float64, device="cuda")
 
 VARIANTS = [{"SOSAT_TRACE_PREDICT": "0"}, {"SOSAT_TRACE_PREDICT": "1"},
+            {"SOSAT_TRACE_PREDICT": "1", "SOSAT_STRIP_LEN": "16"},
             {"SOSAT_TRACE_PREDICT": "1", "SOSAT_STRIP_LEN": "32"},
-            {"SOSAT_TRACE_PREDICT": "1", "SOSAT_STRIP_LEN": "128"},
-            {"SOSAT_TRACE_PREDICT": "1", "SOSAT_STRIP_LEN": "256"},
-            {"SOSAT_TRACE_PREDICT": "0", "SOSAT_STRIP_LEN": "1"}]
+            {"SOSAT_TRACE_PREDICT": "1", "SOSAT_STRIP_LEN": "128"}]
+ROWS = None
+if len(sys.argv) > 2:   # emulate rank 0 of a W-rank cyclic tile-row deal
+    from sosat_optics_b200 import dist as sdist
+    ROWS = torch.from_numpy(sdist.partition_tile_rows(n_scan, int(sys.argv[2]), 0)).to("cuda")
 base = None
 for env in VARIANTS:
     for k in ("SOSAT_TRACE_PREDICT", "SOSAT_STRIP_LEN"):
@@ -36,7 +39,8 @@ for env in VARIANTS:
             x.zero_()
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        ray_trace.trace_bin_device(t, [[0, 0, 0]], spec, 2048, 420.0, planes=(re, im, cnt), stats=st)
+        ray_trace.trace_bin_device(t, [[0, 0, 0]], spec, 2048, 420.0, planes=(re, im, cnt), stats=st,
+                                   tile_rows=ROWS)
         b.record()
         torch.cuda.synchronize()
         ts.append(a.elapsed_time(b))

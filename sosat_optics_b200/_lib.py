@@ -57,6 +57,9 @@ SIGNATURES = {
     "sosat_trace_bin": (c_int, [c_void_p, c_int, POINTER(Freq), c_int, c_int, c_int64, c_int64,
                                 c_int, c_double, c_double, c_void_p, c_void_p, c_void_p,
                                 c_void_p, c_void_p]),
+    "sosat_trace_bin_tiles": (c_int, [c_void_p, c_int, POINTER(Freq), c_int, c_int, c_void_p, c_int,
+                                      c_int, c_double, c_double, c_void_p, c_void_p, c_void_p,
+                                      c_void_p, c_void_p]),
     "sosat_bins_to_field": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_double, c_void_p,
                                     c_void_p]),
     "sosat_bins_to_field_stats": (c_int, [c_void_p, c_void_p, c_void_p, c_int64, c_void_p, c_double,

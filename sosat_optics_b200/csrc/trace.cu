@@ -161,6 +161,7 @@ constexpr int kTile = 16;  // rays per tile edge in theta
 constexpr int kBinWarps = SOSAT_BIN_WARPS;
 constexpr int kBinThreads = 32 * kBinWarps;
 constexpr int kTileH = 2 * kBinWarps;
+static_assert(kTileH == SOSAT_TRACE_TILE_ROWS, "sosat_trace_bin_tiles documents 16-row tiles");
 // (A shared-memory bin window per CTA -- north_star's "shuffle, then shared-memory atomics" --
 // was built and measured at -8 %: after the run-length aggregation a warp issues only 3-6
 // global reductions per 32 rays.  Two rays per thread, skewed by half a surface so that the fp32
@@ -177,6 +178,13 @@ struct BinFreq {
     double kk[SOSAT_MAX_FREQS];       // k / 2e3 / (2 pi): OPL [mm] -> phase in cycles
 };
 __constant__ BinFreq g_freq;
+// work queue of the persistent binning kernel: the next strip to hand out (zeroed in stream order
+// before every launch; like g_freq, per-device state of one stream at a time)
+__device__ unsigned long long g_next_strip;
+#ifdef SOSAT_STRIP_TIMING
+__device__ long long g_strip_t0[1 << 17], g_strip_t1[1 << 17];
+__device__ int g_strip_sm[1 << 17];
+#endif
 
 struct BinParams {
     double lin_start, lin_stop, lin_step;
@@ -187,6 +195,7 @@ struct BinParams {
     int strip_len, strips_x;  // a strip = strip_len adjacent tiles along theta (the last may be shorter)
     int predict;              // seeds of a tile predicted from the lane's last two tiles
     long long n_strips;
+    const int *tile_rows;     // optional: tile row ty of this launch is row tile_rows[ty] of the grid
 };
 
 // Persistent CTAs walk STRIPS of adjacent 16 x 16 patches of the launch grid (strips dealt
@@ -227,6 +236,7 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
     __shared__ double s_sum[4][kBinThreads];
     __shared__ unsigned s_nvalid[kBinWarps], s_nbinned[kBinWarps];  // one slot per warp: no atomics
     __shared__ unsigned s_rare[2];                 // n_slow, n_bracket_fail
+    __shared__ long long s_next;                   // the strip this CTA works on next
 
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
     const int lth = (lane & 7) + 8 * (warp & 1);
@@ -309,17 +319,34 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
     const unsigned strips_per_rx = (unsigned)p.strips_x * (unsigned)p.tiles_y;
     double *const my_hist = s_hist + tid;
     constexpr int kHistStride = kBinThreads;
-    for (long long strip = blockIdx.x; strip < p.n_strips; strip += gridDim.x) {
+    // Strips are handed out dynamically (first one = blockIdx.x, then an atomic counter): their
+    // cost varies with the position in the cone (binned / clipped / outside lens 1b's conic
+    // domain, where warps fall back to fp32 seeds), and with only 10-100 strips per CTA a static
+    // deal leaves SMs idle at the end (measured at 8 GPUs: 5.1 ms against 4.7 ms ideal).
+    for (long long strip = blockIdx.x; strip < p.n_strips;) {
+#ifdef SOSAT_STRIP_TIMING
+        long long t_begin = 0;
+        if (tid == 0) { asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_begin)); }
+#endif
         const int irx = (int)(strip / strips_per_rx);
         const unsigned srem = (unsigned)(strip - (long long)irx * strips_per_rx);
-        const int ty = (int)(srem / (unsigned)p.strips_x), sx = (int)(srem - (unsigned)ty * p.strips_x);
+        // strips are taken from the rim of the cone inwards (rows and, within a row, columns
+        // alternate between the two ends): the expensive, irregular strips -- clipped rays, fp32
+        // fallback outside lens 1b's conic domain, bracketed solves -- go first and the uniform
+        // central ones last, so the dynamic deal ends on short strips
+        const int ky = (int)(srem / (unsigned)p.strips_x), kx = (int)(srem - (unsigned)ky * p.strips_x);
+        const int ty_l = (ky & 1) ? p.tiles_y - 1 - (ky >> 1) : (ky >> 1);
+        const int sx = (kx & 1) ? p.strips_x - 1 - (kx >> 1) : (kx >> 1);
+        // a launch covers a block of consecutive launch rows or, with a row map, any set of tile
+        // rows (multi-GPU: tile rows dealt cyclically, so every rank gets the same mix of rays)
+        const int ty = p.tile_rows ? p.tile_rows[ty_l] : ty_l;
         const int tx_begin = sx * p.strip_len;
         const int tx_end = min(tx_begin + p.strip_len, p.tiles_x);
         if (irx != acc_rx) {
             if (acc_rx >= 0) flush_stats(acc_rx);
             acc_rx = irx;
         }
-        __syncthreads();  // previous strip done with the tables (first pass: s_rot is complete)
+        __syncthreads();  // first pass: s_rot is complete (later: s_next has been read by everyone)
         if (tid < kTileW) {
             fill_theta(tx_begin, 0);
         } else if (tid < kTileW + kTileH) {
@@ -366,10 +393,12 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
                                                              sth * sph, cth, r);
             }
             const bool live = tx * kTileW + lth < p.n_scan && iph < p.n_rows;
-            if (r.flags & (RAY_UNCONVERGED | RAY_FLAGGED)) {
+            if (live && (r.flags & (RAY_UNCONVERGED | RAY_FLAGGED))) {
                 // rare: the launch direction is re-read here (volatile) instead of being kept live
                 // across the fast path, and results go through a local copy so that r itself
-                // stays in registers.
+                // stays in registers.  (Queueing these rays for a second, densely packed pass was
+                // built and measured: the first pass did not get faster -- the rare rays cluster
+                // in few warps -- and the second pass cost 2.3 ms per 1e9 rays.)
                 const double sth2 = *(volatile double *)&s_sin_t[buf][lth], cth2 = *(volatile double *)&s_cos_t[buf][lth];
                 const double sph2 = *(volatile double *)&s_sin_p[lph], cph2 = *(volatile double *)&s_cos_p[lph];
                 RayResult rs;
@@ -385,10 +414,8 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
                     // < 0.15 % of rays: the reference's bracketed solve
                     trace_ray_bracketed(g_geom, rx[0], rx[1], rx[2], sth2 * cph2, sth2 * sph2, cth2, rs);
                     redone = true;
-                    if (live) {
-                        atomicAdd(&s_rare[0], 1u);
-                        if (rs.flags & RAY_BRACKET_FAIL) atomicAdd(&s_rare[1], 1u);
-                    }
+                    atomicAdd(&s_rare[0], 1u);
+                    if (rs.flags & RAY_BRACKET_FAIL) atomicAdd(&s_rare[1], 1u);
                 }
                 if (redone) {
                     r.ax = rs.ax; r.az = rs.az; r.opl = rs.opl;
@@ -457,6 +484,18 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
                 }
             }
         }
+#ifdef SOSAT_STRIP_TIMING
+        if (tid == 0 && strip < (1 << 17)) {
+            long long t_end;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t_end));
+            unsigned smid;
+            asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+            g_strip_t0[strip] = t_begin; g_strip_t1[strip] = t_end; g_strip_sm[strip] = (int)smid;
+        }
+#endif
+        if (tid == 0) s_next = (long long)gridDim.x + (long long)atomicAdd(&g_next_strip, 1ull);
+        __syncthreads();  // also: every warp is done with this strip's tables
+        strip = s_next;
     }
     if (acc_rx >= 0) flush_stats(acc_rx);
 }
@@ -828,7 +867,8 @@ static void launch_bin(BinParams p, const double *rx, float *re, float *im, floa
     if (const char *e = getenv("SOSAT_STRIP_LEN")) {  // testing / tuning hook
         sl = atoll(e);
     } else {
-        if (sl > n_tiles / (8 * want)) sl = n_tiles / (8 * want);  // >= 8 strips per CTA
+        // >= 32 strips per CTA, so that the dynamic deal ends within ~1.5 % of the ideal
+        if (sl > n_tiles / (32 * want)) sl = n_tiles / (32 * want);
         if (sl < 8) p.predict = 0;  // short strips: the two seeding tiles would dominate
     }
     if (sl < 1) sl = 1;
@@ -836,6 +876,9 @@ static void launch_bin(BinParams p, const double *rx, float *re, float *im, floa
     p.strips_x = (p.tiles_x + p.strip_len - 1) / p.strip_len;
     p.n_strips = (long long)p.strips_x * p.tiles_y * p.n_rx;
     const int blocks = (int)(p.n_strips < want ? p.n_strips : want);
+    void *counter = nullptr;
+    cudaGetSymbolAddress(&counter, g_next_strip);
+    cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
     kern<<<blocks, kBinThreads, smem, st>>>(p, rx, re, im, cnt, stats);
 }
 
@@ -862,10 +905,11 @@ static int trace_minb() {
 #endif
 }
 
-extern "C" int sosat_trace_bin(const double *d_rx, int n_rx, const sosat_freq_t *h_freq,
-                               int n_freq, int n_scan, int64_t row_begin, int64_t row_end,
-                               int grid_n, double extent_mm, double opl_ref, float *d_re,
-                               float *d_im, float *d_cnt, double *d_stats, void *stream) {
+static int trace_bin_common(const double *d_rx, int n_rx, const sosat_freq_t *h_freq,
+                            int n_freq, int n_scan, int64_t row_begin, int64_t row_end,
+                            const int *d_tile_rows, int n_tile_rows, int grid_n, double extent_mm,
+                            double opl_ref, float *d_re, float *d_im, float *d_cnt, double *d_stats,
+                            void *stream) {
     int dev;
     if (int rc = current_device(&dev)) return rc;
     if (!g_geom_set[dev]) return set_error(SOSAT_ERR_NO_GEOMETRY, "call sosat_set_geometry first");
@@ -908,7 +952,8 @@ extern "C" int sosat_trace_bin(const double *d_rx, int n_rx, const sosat_freq_t 
     p.n_freq = n_freq;
     p.grid_n = binning ? grid_n : 0;
     p.tiles_x = (n_scan + kTileW - 1) / kTileW;
-    p.tiles_y = (p.n_rows + kTileH - 1) / kTileH;
+    p.tiles_y = d_tile_rows ? n_tile_rows : (p.n_rows + kTileH - 1) / kTileH;
+    p.tile_rows = d_tile_rows;
     SOSAT_REQUIRE((long long)p.tiles_x * p.tiles_y * n_rx < 2147483647LL,
                   "too many ray tiles for one launch (%lld): split the receiver list or the row range",
                   (long long)p.tiles_x * p.tiles_y * n_rx);
@@ -932,6 +977,36 @@ extern "C" int sosat_trace_bin(const double *d_rx, int n_rx, const sosat_freq_t 
     // before the call returns, so no synchronisation is needed here.
     return SOSAT_OK;
 }
+
+extern "C" int sosat_trace_bin(const double *d_rx, int n_rx, const sosat_freq_t *h_freq,
+                               int n_freq, int n_scan, int64_t row_begin, int64_t row_end,
+                               int grid_n, double extent_mm, double opl_ref, float *d_re,
+                               float *d_im, float *d_cnt, double *d_stats, void *stream) {
+    return trace_bin_common(d_rx, n_rx, h_freq, n_freq, n_scan, row_begin, row_end, nullptr, 0, grid_n,
+                            extent_mm, opl_ref, d_re, d_im, d_cnt, d_stats, stream);
+}
+
+extern "C" int sosat_trace_bin_tiles(const double *d_rx, int n_rx, const sosat_freq_t *h_freq,
+                                     int n_freq, int n_scan, const int *d_tile_rows,
+                                     int n_tile_rows, int grid_n, double extent_mm, double opl_ref,
+                                     float *d_re, float *d_im, float *d_cnt, double *d_stats,
+                                     void *stream) {
+    SOSAT_REQUIRE(n_tile_rows >= 0, "n_tile_rows must be >= 0");
+    SOSAT_REQUIRE(n_tile_rows == 0 || d_tile_rows, "sosat_trace_bin_tiles: null tile row list");
+    if (n_tile_rows == 0) return SOSAT_OK;
+    return trace_bin_common(d_rx, n_rx, h_freq, n_freq, n_scan, 0, n_scan, d_tile_rows, n_tile_rows,
+                            grid_n, extent_mm, opl_ref, d_re, d_im, d_cnt, d_stats, stream);
+}
+
+#ifdef SOSAT_STRIP_TIMING
+extern "C" int sosat_debug_strip_times(long long *h_t0, long long *h_t1, int *h_sm, int n) {
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(h_t0, g_strip_t0, sizeof(long long) * n);
+    cudaMemcpyFromSymbol(h_t1, g_strip_t1, sizeof(long long) * n);
+    cudaMemcpyFromSymbol(h_sm, g_strip_sm, sizeof(int) * n);
+    return 0;
+}
+#endif
 
 extern "C" int sosat_near_field_arrays(const double *d_out, int64_t n, double k, double *d_xyap,
                                        uint8_t *d_mask, double *d_tan_og, double *d_work,

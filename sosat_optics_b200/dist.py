@@ -2,8 +2,9 @@
 
 The path shards naturally:
 
-* **rays** of one bundle: contiguous blocks of launch rows (iphi) per rank, each rank bins into
-  its own full-size private grid, then ONE reduce of the ``[re, im, count]`` planes plus the 8
+* **rays** of one bundle: 16-row tile rows of the launch grid dealt cyclically to the ranks (or
+  contiguous row blocks, :func:`partition_rows`), each rank bins into its own full-size private
+  grid, then ONE reduce of the ``[re, im, count]`` planes plus the 8
   fp64 statistics over NVLink -- the only exchange of the data path.  Two implementations:
   :func:`reduce_bins` (NCCL all-reduce, then the normalisation kernel) and
   :class:`PeerPlanes` (one kernel per rank over peer-mapped memory that reduces its slab of
@@ -32,6 +33,17 @@ def partition_rows(n_scan: int, world: int, rank: int, align: int = ROW_ALIGN) -
     u0 = rank * base + min(rank, extra)
     u1 = u0 + base + (1 if rank < extra else 0)
     return min(u0 * align, n_scan), min(u1 * align, n_scan)
+
+
+def partition_tile_rows(n_scan: int, world: int, rank: int, align: int = ROW_ALIGN) -> np.ndarray:
+    """Tile rows (``align`` launch rows each) of ``rank`` under a CYCLIC deal: rows rank,
+    rank + world, ...  Every rank then traces the same mix of central rays (all valid, all
+    binned, predicted seeds) and marginal rays (clipped, or outside lens 1b's conic domain: no
+    binning but fp32-seeded tiles), which contiguous blocks do not give: at 8 GPUs the slowest
+    block took 5.15 ms against 4.61 ms for the fastest."""
+    if not (0 <= rank < world):
+        raise ValueError("rank outside [0, world)")
+    return np.arange(rank, (n_scan + align - 1) // align, world, dtype=np.int32)
 
 
 def partition_items(n_items: int, world: int, rank: int) -> List[int]:
@@ -315,18 +327,18 @@ def near_field_binned_distributed(tele_geo, rx, grid_n: int, extent_cm: float,
     field_fn = field_fn or ray_trace.bins_to_field_device
     specs = list(freqs) if freqs is not None else [
         (tele_geo.k, tele_geo.th_fwhp_x, tele_geo.th_fwhp_y)]
-    r0, r1 = partition_rows(int(tele_geo.n_scan), world, rank)
+    rows = partition_tile_rows(int(tele_geo.n_scan), world, rank)  # cyclic deal of 16-row tiles
     rx_arr = np.asarray(rx, dtype=np.float64).reshape(-1, 3)
     if peer is not None:
         if peer.shape != (len(rx_arr), len(specs), grid_n):
             raise ValueError("PeerPlanes shape %r does not match the request" % (peer.shape,))
         peer.zero()
-        trace_fn(tele_geo, rx_arr, specs, grid_n, extent_cm * 10.0, row_begin=r0, row_end=r1,
+        trace_fn(tele_geo, rx_arr, specs, grid_n, extent_cm * 10.0, tile_rows=rows,
                  planes=(peer.re, peer.im, peer.cnt), stats=peer.stats)
         b = peer.reduce_field(specs).clone()
         return b, None, peer.stats_sum.cpu().numpy()
     re, im, cnt, stats = trace_fn(tele_geo, rx_arr, specs, grid_n, extent_cm * 10.0,
-                                  row_begin=r0, row_end=r1)
+                                  tile_rows=rows)
     re, im, cnt, stats = reduce_bins(re, im, cnt, stats, group)
     b, h_stats = field_fn(re, im, cnt, stats, specs)
     return b, cnt, h_stats

@@ -453,10 +453,12 @@ class BinnedField:
 
 
 def trace_bin_device(tele_geo, rx_list, freq_specs, grid_n, extent_mm, *, opl_ref=0.0,
-                     row_begin=0, row_end=None, planes=None, stats=None, bins=True):
+                     row_begin=0, row_end=None, planes=None, stats=None, bins=True, tile_rows=None):
     """Launch ``sosat_trace_bin`` on the current device/stream and return the raw accumulators
     ``(re, im, cnt, stats)`` as CUDA tensors (accumulated into ``planes`` / ``stats`` when
-    given, so several row blocks -- or several GPUs after an all-reduce -- add up)."""
+    given, so several row blocks -- or several GPUs after an all-reduce -- add up).
+    ``tile_rows``: instead of the row block, a list (or CUDA int32 tensor) of 16-row tile rows of
+    the launch grid to trace (``sosat_trace_bin_tiles``; ``dist.partition_tile_rows``)."""
     lib = _lib.require_gpu()
     torch = _torch()
     n_scan = int(tele_geo.n_scan)
@@ -481,6 +483,16 @@ def trace_bin_device(tele_geo, rx_list, freq_specs, grid_n, extent_mm, *, opl_re
     else:
         re = im = cnt = None
         ptrs = [ctypes.c_void_p(0)] * 3
+    if tile_rows is not None:
+        if not hasattr(tile_rows, "is_cuda"):
+            tile_rows = torch.from_numpy(np.ascontiguousarray(np.asarray(tile_rows, dtype=np.int32))).to("cuda")
+        if tile_rows.dtype != torch.int32 or not tile_rows.is_cuda or not tile_rows.is_contiguous():
+            raise ValueError("tile_rows must be a contiguous CUDA int32 tensor (or a host sequence)")
+        _lib.check(lib.sosat_trace_bin_tiles(
+            ctypes.c_void_p(d_rx.data_ptr()), n_rx, freqs, n_freq, n_scan,
+            ctypes.c_void_p(tile_rows.data_ptr()), int(tile_rows.numel()), int(grid_n),
+            float(extent_mm), float(opl_ref), *ptrs, ctypes.c_void_p(stats.data_ptr()), _stream(torch)))
+        return re, im, cnt, stats
     _lib.check(lib.sosat_trace_bin(
         ctypes.c_void_p(d_rx.data_ptr()), n_rx, freqs, n_freq, n_scan, row_begin, row_end,
         int(grid_n), float(extent_mm), float(opl_ref), *ptrs, ctypes.c_void_p(stats.data_ptr()),

@@ -971,3 +971,31 @@ def test_large_results_come_back_through_the_staged_copy(mods, monkeypatch):
     assert np.array_equal(np.nan_to_num(got), np.nan_to_num(want))
     x = torch.arange(300_001, dtype=torch.float64, device="cuda").reshape(1, -1)
     assert np.array_equal(lib.to_numpy(x), np.arange(300_001, dtype=np.float64).reshape(1, -1))
+
+
+def test_tile_row_lists_add_up_to_the_whole_bundle(mods, monkeypatch):
+    """sosat_trace_bin_tiles: three cyclic deals of the 16-row tile rows (what three ranks would
+    trace) add up to the one-shot planes -- counts exactly, sums to fp32 order -- incl. the ragged
+    last tile row, in both seedings of the kernel; a host list and a CUDA tensor are accepted."""
+    rt, torch = mods["rt"], mods["torch"]
+    from sosat_optics_b200 import dist as sdist
+    n_scan = 1000   # 63 tile rows, the last one 8 rows high
+    t = _bundle(mods, n_scan)
+    spec = [(t.k, t.th_fwhp_x, t.th_fwhp_y)]
+    rx = [[40, 0, -25]]
+    re, im, cnt, st = rt.trace_bin_device(t, rx, spec, 128, 420.0)
+    for predict in ("0", "1"):
+        monkeypatch.setenv("SOSAT_TRACE_PREDICT", predict)
+        monkeypatch.setenv("SOSAT_STRIP_LEN", "16")
+        re2, im2, cnt2 = torch.zeros_like(re), torch.zeros_like(im), torch.zeros_like(cnt)
+        st2 = torch.zeros_like(st)
+        for r in range(3):
+            rows = sdist.partition_tile_rows(n_scan, 3, r)
+            arg = rows if r == 0 else torch.from_numpy(rows).to("cuda")
+            rt.trace_bin_device(t, rx, spec, 128, 420.0, tile_rows=arg, planes=(re2, im2, cnt2), stats=st2)
+        assert torch.equal(cnt2, cnt), predict
+        assert (re2 - re).abs().max().item() <= 1e-4 * re.abs().max().item()
+        assert torch.equal(st2[:, [0, 7]], st[:, [0, 7]])
+        assert st2[0, 1].item() == pytest.approx(st[0, 1].item(), rel=1e-12)
+    with pytest.raises(ValueError):
+        rt.trace_bin_device(t, rx, spec, 128, 420.0, tile_rows=torch.zeros(3, dtype=torch.int64, device="cuda"))

@@ -64,6 +64,17 @@ def test_freq_specs_from_table(feed_table):
         geometry.make_freqs([(1, 1, 1)] * 65)
 
 
+def test_partition_tile_rows_is_a_cyclic_cover():
+    for n_scan, world in ((31623, 8), (150, 4), (16, 3), (17, 2), (1, 2)):
+        rows = [sdist.partition_tile_rows(n_scan, world, r) for r in range(world)]
+        allr = np.sort(np.concatenate(rows))
+        assert np.array_equal(allr, np.arange((n_scan + 15) // 16))
+        assert max(len(r) for r in rows) - min(len(r) for r in rows) <= 1
+        assert all(r.dtype == np.int32 for r in rows)
+        for r, rr in enumerate(rows):
+            assert np.all(rr % world == r)
+
+
 @pytest.mark.parametrize("n_scan,world", [(60, 1), (60, 2), (150, 8), (31623, 8), (7, 4), (16, 3)])
 def test_partition_rows_covers_exactly(n_scan, world):
     blocks = [sdist.partition_rows(n_scan, world, r) for r in range(world)]
@@ -91,21 +102,30 @@ def _free_port():
 
 
 def _oracle_trace_fn(tele_geo, rx_arr, specs, grid_n, extent_mm, *, opl_ref=0.0, row_begin=0,
-                     row_end=None, **_):
+                     row_end=None, tile_rows=None, **_):
     """CPU stand-in with the signature of ray_trace.trace_bin_device (test infrastructure)."""
     from oracle import oracle
     n_scan = int(tele_geo.n_scan)
+    if tile_rows is not None:   # 16-row tile rows of the launch grid (dist.partition_tile_rows)
+        blocks = [(16 * int(t), min(16 * int(t) + 16, n_scan)) for t in tile_rows]
+    else:
+        blocks = [(row_begin, n_scan if row_end is None else row_end)]
     re = torch.zeros((len(rx_arr), len(specs), grid_n, grid_n), dtype=torch.float32)
     im, cnt = torch.zeros_like(re), torch.zeros((len(rx_arr), grid_n, grid_n), dtype=torch.float32)
     stats = torch.zeros((len(rx_arr), 8), dtype=torch.float64)
     for i, rx in enumerate(rx_arr):
-        out = oracle.rx_to_lyot(rx, tele_geo, ray_begin=row_begin * n_scan,
-                                ray_end=row_end * n_scan, n_threads=1)
-        for f, (k, _, _) in enumerate(specs):
-            r, m, c, sums = oracle.bin_near_field(out, float(k), grid_n, extent_mm, opl_ref)
-            re[i, f], im[i, f], cnt[i] = (torch.from_numpy(r).float(), torch.from_numpy(m).float(),
-                                          torch.from_numpy(c).float())
-        stats[i, 0], stats[i, 1], stats[i, 7] = sums["n_valid"], sums["sum_opl"], sums["n_binned"]
+        for b0, b1 in blocks:
+            out = oracle.rx_to_lyot(rx, tele_geo, ray_begin=b0 * n_scan, ray_end=b1 * n_scan,
+                                    n_threads=1)
+            for f, (k, _, _) in enumerate(specs):
+                r, m, c, sums = oracle.bin_near_field(out, float(k), grid_n, extent_mm, opl_ref)
+                re[i, f] += torch.from_numpy(r).float()
+                im[i, f] += torch.from_numpy(m).float()
+                if f == 0:
+                    cnt[i] += torch.from_numpy(c).float()
+            stats[i, 0] += sums["n_valid"]
+            stats[i, 1] += sums["sum_opl"]
+            stats[i, 7] += sums["n_binned"]
     return re, im, cnt, stats
 
 
