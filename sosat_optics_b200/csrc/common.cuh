@@ -27,9 +27,12 @@ int set_error(int code, const char *fmt, ...);
     } while (0)
 
 inline int num_sms() {
+    static int cache[64] = {0};
     int dev = 0, n = 0;
     if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+    if (dev >= 0 && dev < 64 && cache[dev] > 0) return cache[dev];
     if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 148;
+    if (n > 0 && dev >= 0 && dev < 64) cache[dev] = n;
     return n > 0 ? n : 148;
 }
 

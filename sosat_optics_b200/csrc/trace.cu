@@ -848,19 +848,26 @@ static void launch_bin(BinParams p, const double *rx, float *re, float *im, floa
                        double *stats, cudaStream_t st) {
     auto kern = trace_bin_kernel<N32, N64, MINB, GEO>;
     const size_t smem = p.predict ? (size_t)kHistBytes : 0;
-    static bool carveout_set[64][2] = {};
+    // per device and per (kernel, smem) variant, queried once: attributes, occupancy, the address
+    // of the work-queue counter (host-side latency in front of small launches)
+    static bool ready[64][2] = {};
+    static int occ_cache[64][2] = {};
+    static void *counter_cache[64] = {};
     int dev = 0;
     cudaGetDevice(&dev);
-    if (dev >= 0 && dev < 64 && !carveout_set[dev][p.predict ? 1 : 0]) {
+    if (dev < 0 || dev >= 64) dev = 0;
+    const int v = p.predict ? 1 : 0;
+    if (!ready[dev][v]) {
         // MINB CTAs of ~45 KB each: ask for the shared-memory-heavy split of the L1 / shared array
         cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout,
                              cudaSharedmemCarveoutMaxShared);
         // static tables (25 KB) + history (24 KB) exceed the 48 KB default limit
         if (smem) cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        carveout_set[dev][p.predict ? 1 : 0] = true;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ_cache[dev][v], kern, kBinThreads, smem);
+        cudaGetSymbolAddress(&counter_cache[dev], g_next_strip);
+        ready[dev][v] = true;
     }
-    int occ = 0;
-    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, kern, kBinThreads, smem);
+    const int occ = occ_cache[dev][v];
     const long long want = (long long)num_sms() * (occ > 0 ? occ : 1);
     const long long n_tiles = (long long)p.tiles_x * p.tiles_y * p.n_rx;
     long long sl = 64;
@@ -876,9 +883,7 @@ static void launch_bin(BinParams p, const double *rx, float *re, float *im, floa
     p.strips_x = (p.tiles_x + p.strip_len - 1) / p.strip_len;
     p.n_strips = (long long)p.strips_x * p.tiles_y * p.n_rx;
     const int blocks = (int)(p.n_strips < want ? p.n_strips : want);
-    void *counter = nullptr;
-    cudaGetSymbolAddress(&counter, g_next_strip);
-    cudaMemsetAsync(counter, 0, sizeof(unsigned long long), st);
+    cudaMemsetAsync(counter_cache[dev], 0, sizeof(unsigned long long), st);
     kern<<<blocks, kBinThreads, smem, st>>>(p, rx, re, im, cnt, stats);
 }
 
