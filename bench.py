@@ -472,6 +472,30 @@ def run_ours(args):
     for _ in range(args.warmup):
         step()
     barrier()
+    # N > 1: rank 0 also computes the far field of every step.  Give it a smaller share of the
+    # rays, so that all ranks reach the reduce together and rank 0's far field of step k runs
+    # while the others already trace step k + 1 (weighted deal of the tile rows, calibrated on
+    # three untimed steps: shares f0 = f - ff/T, f = (1 + ff/T)/N, T = trace time of the bundle).
+    weights = None
+    if world > 1 and args.balance:
+        cal = []
+        for _ in range(3):
+            ke = [ev() for _ in range(4)]
+            step(kernel_events=ke)
+            torch.cuda.synchronize()
+            cal.append([ke[0].elapsed_time(ke[1]), ke[2].elapsed_time(ke[3]) if rank == 0 else 0.0])
+        c = torch.tensor(np.median(np.array(cal), axis=0), dtype=torch.float64, device="cuda")
+        dist.all_reduce(c)
+        t_all, t_ff = c.tolist()
+        if t_all > 0 and 0 < t_ff < t_all / world:
+            f = (1.0 + t_ff / t_all) / world
+            weights = [f - t_ff / t_all] + [f] * (world - 1)
+            my_rows = sdist.partition_tile_rows(n_scan, world, rank, weights=weights)
+            d_rows = torch.from_numpy(my_rows).to("cuda")
+            my_rays = int(sum(min(16 * int(tr) + 16, n_scan) - 16 * int(tr) for tr in my_rows)) * n_scan
+        for _ in range(2):
+            step()
+        barrier()
     sampler = ClockSampler(local)
     sampler.start()
     step_ms, trace_ms, ff_ms, red_ms = [], [], [], []
@@ -583,7 +607,7 @@ def run_ours(args):
     _lib.check(lib.sosat_measure_fp64_peak(__import__("ctypes").byref(fl),
                                            __import__("ctypes").byref(ms)))
     fp64_peak_tf = fl.value / 1e12
-    trace_ms_step = trace_ms_max / args.steps
+    trace_ms_step = sum(trace_ms) / args.steps     # this rank's launches (its own share of the rays)
     rays_per_s_kernel = my_rays / (trace_ms_step * 1e-3)
     ncu = {}
     try:
@@ -757,6 +781,7 @@ def run_ours(args):
                        "which computes the far field" if use_peer else
                        "one NCCL all-reduce of [re,im,count] planes (50 MB) + 8 fp64 sums" + (
                            f" ({peer_note})" if peer_note else "")),
+                "ray_shares": weights,
                 "l2": "256 MiB flush write between timed steps; the kernel reads no input arrays",
                 "newton_schedule": os.environ.get("SOSAT_TRACE_VARIANT", "default (fp32 Newton + Halley step, 1 fp64 Newton step, first-order slope update; long steps re-traced adaptively)")},
         "clocks": clocks,
@@ -802,6 +827,9 @@ def main():
     ap.add_argument("--impl", choices=["ours", "reference"], default="ours")
     ap.add_argument("--n-scan", type=int, default=N_SCAN, help="reduce only for debugging")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-balance", dest="balance", action="store_false",
+                    help="N > 1: equal shares of the rays for all ranks (default: rank 0, which also computes "
+                         "the far field, gets a smaller share, calibrated on untimed steps)")
     ap.add_argument("--reduce", choices=["peer", "nccl"], default="peer",
                     help="N > 1: fused peer-memory reduce (default) or NCCL all-reduce of the bin planes")
     args = ap.parse_args()

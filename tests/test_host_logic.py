@@ -75,6 +75,23 @@ def test_partition_tile_rows_is_a_cyclic_cover():
             assert np.all(rr % world == r)
 
 
+def test_weighted_tile_row_deal():
+    """Shares of the rays by weighted round-robin: an exact cover, sizes proportional to the
+    weights, rows of every rank spread over the whole grid; equal weights = the cyclic deal."""
+    n_scan, world = 31623, 8
+    w = [0.9] + [1.0] * 7
+    rows = [sdist.partition_tile_rows(n_scan, world, r, weights=w) for r in range(world)]
+    assert np.array_equal(np.sort(np.concatenate(rows)), np.arange(1977))
+    sizes = np.array([len(r) for r in rows])
+    assert abs(sizes[0] / sizes[1:].mean() - 0.9) < 0.01 and sizes[1:].max() - sizes[1:].min() <= 1
+    assert all(np.diff(r).max() <= 2 * world for r in rows)          # no rank owns a contiguous block
+    for r in range(world):
+        assert np.array_equal(sdist.partition_tile_rows(n_scan, world, r, weights=[2.0] * world),
+                              sdist.partition_tile_rows(n_scan, world, r))
+    with pytest.raises(ValueError):
+        sdist.partition_tile_rows(n_scan, 2, 0, weights=[1.0, 0.0])
+
+
 @pytest.mark.parametrize("n_scan,world", [(60, 1), (60, 2), (150, 8), (31623, 8), (7, 4), (16, 3)])
 def test_partition_rows_covers_exactly(n_scan, world):
     blocks = [sdist.partition_rows(n_scan, world, r) for r in range(world)]
