@@ -132,7 +132,14 @@ def a2b(apert, phi):
     ``apert``: real [N, N] amplitude (``abs`` is taken), ``phi``: phase in DEGREES.  Returns
     ``(beam_complex complex128 [N, N], phase float64 [N, N])`` with
     ``beam_complex = fftshift(fft2(fftshift(|A| exp(i phi pi/180))))`` computed as the dense
-    separable contraction W b W^T on tensor cores, and ``phase = arctan2(imag, real)``."""
+    separable contraction W b W^T on tensor cores, and ``phase = arctan2(imag, real)``.
+
+    Precision: the contraction runs as a 3-term split-bf16 product with fp32 accumulation, so the
+    complex128 array carries about fp32 information -- measured <= 1.5e-5 of the peak |B| on
+    worst-case random fields at N = 1024 and ~5e-6 on the reference's own fields, against the 1e-4
+    of peak that the hot path is held to.  ``phase`` is the arctan2 of those values: accurate
+    where |B| is well above that error floor (5e-3 rad at 1e-2 of peak), meaningless -- as in any
+    floating-point FFT -- where |B| is at the floor."""
     return _amp_phase_transform("a2b", apert, phi, _lib.DFT_FORWARD)
 
 
@@ -162,7 +169,8 @@ def b2a(beam, phase):
     ``beam``: [N, N] (``abs`` is taken), ``phase`` in DEGREES.  Returns ``(aper_field complex128,
     aper_phase float64)`` with ``aper_field = fftshift(ifft2(|beam| exp(i phase pi/180)))`` --
     the reference computes ``fftshift(beam_complex)`` on line 213 and then discards it on line
-    214, so the input is NOT shifted; kept."""
+    214, so the input is NOT shifted; kept.  Same precision as :func:`a2b` (fp32 information in a
+    complex128 array, <= 1.5e-5 of peak)."""
     return _amp_phase_transform("b2a", beam, phase, _lib.DFT_B2A)
 
 

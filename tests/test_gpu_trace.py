@@ -999,3 +999,32 @@ def test_tile_row_lists_add_up_to_the_whole_bundle(mods, monkeypatch):
         assert st2[0, 1].item() == pytest.approx(st[0, 1].item(), rel=1e-12)
     with pytest.raises(ValueError):
         rt.trace_bin_device(t, rx, spec, 128, 420.0, tile_rows=torch.zeros(3, dtype=torch.int64, device="cuda"))
+
+
+def test_predicted_seeds_with_two_receivers_and_two_frequencies(mods, monkeypatch, feed_table):
+    """The seed history is per strip: a launch over two receivers and two frequencies at the
+    benchmark density (a 32-row block, strips of 64 tiles, predicted seeds forced) must give, for
+    each receiver, the oracle's bins of exactly those rays."""
+    rt, oracle, geometry = mods["rt"], mods["oracle"], mods["geometry"]
+    monkeypatch.setenv("SOSAT_TRACE_PREDICT", "1")
+    monkeypatch.setenv("SOSAT_STRIP_LEN", "64")
+    n_scan = 31623
+    t = _bundle(mods, n_scan)
+    specs = geometry.freq_specs_from_table([90.0, 150.0], feed_table)
+    rxs = [[0.0, 0.0, 0.0], [-70.0, 0.0, 110.0]]
+    r0 = n_scan // 3
+    re, im, cnt, st = rt.trace_bin_device(t, rxs, specs, 512, 420.0, row_begin=r0, row_end=r0 + 32)
+    st = st.cpu().numpy()
+    for i, rx in enumerate(rxs):
+        t.th_fwhp_x, t.th_fwhp_y = specs[0][1], specs[0][2]
+        ref = oracle.rx_to_lyot(rx, t, ray_begin=r0 * n_scan, ray_end=(r0 + 32) * n_scan)
+        for f, (k, fx, fy) in enumerate(specs):
+            if f == 1:   # amplitude of the second frequency: re-taper the oracle's rays
+                t.th_fwhp_x, t.th_fwhp_y = fx, fy
+                ref = oracle.rx_to_lyot(rx, t, ray_begin=r0 * n_scan, ray_end=(r0 + 32) * n_scan)
+            rre, rim, rcnt, sums = oracle.bin_near_field(ref, float(k), 512, 420.0, 0.0)
+            assert int(st[i, 0]) == sums["n_valid"] and int(st[i, 7]) == sums["n_binned"]
+            assert np.abs(cnt[i].cpu().numpy() - rcnt).sum() <= 4
+            scale = max(np.abs(rre).max(), np.abs(rim).max())
+            assert np.abs(re[i, f].cpu().numpy() - rre).max() < 2e-3 * scale
+            assert np.abs(im[i, f].cpu().numpy() - rim).max() < 2e-3 * scale
