@@ -155,12 +155,18 @@ def check(rc: int) -> None:
         raise SosatError(f"libsosat_b200 error {rc}: {msg.decode() if msg else ''}")
 
 
+_gpu_ok = False
+
+
 def require_gpu():
     """The product path needs a B200; say so loudly instead of computing on the CPU."""
+    global _gpu_ok
     lib = load()
-    if lib.sosat_device_count() <= 0:
-        raise SosatError("no CUDA device visible: sosat_optics_b200 runs only on the GPU "
-                         "(there is deliberately no CPU fallback)")
+    if not _gpu_ok:   # checked until it succeeds once
+        if lib.sosat_device_count() <= 0:
+            raise SosatError("no CUDA device visible: sosat_optics_b200 runs only on the GPU "
+                             "(there is deliberately no CPU fallback)")
+        _gpu_ok = True
     return lib
 
 

@@ -43,11 +43,18 @@ __all__ = ["rx_to_lyot", "getNearField", "get_sim", "get_beam_cent", "get_fwhm",
            "SimOutput", "BinnedField"]
 
 
+_torch_ok = None
+
+
 def _torch():
+    global _torch_ok
+    if _torch_ok is not None:   # a device that was there stays there: check once per process
+        return _torch_ok
     import torch
     if not torch.cuda.is_available():
         raise _lib.SosatError("no CUDA device visible: sosat_optics_b200 runs only on the GPU "
                               "(there is deliberately no CPU fallback)")
+    _torch_ok = torch
     return torch
 
 
