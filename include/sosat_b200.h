@@ -24,9 +24,10 @@
  *   - there is no CPU fallback anywhere in this library.
  *   - threading: one host process per GPU is the intended use (torch.distributed for several).
  *     Calls on one device may come from several host threads; the plan registry of the DFT
- *     workspaces is mutex-protected.  The geometry and the per-call frequency table are
- *     per-DEVICE __constant__ state written in stream order: trace calls that use different
- *     geometries or frequency lists must not overlap on different streams of the same device.
+ *     workspaces is mutex-protected.  The geometry, the per-call frequency table and the strip
+ *     queue of the fused trace + bin kernel are per-DEVICE state written in stream order: trace
+ *     calls must not overlap on different streams of the same device (one after the other on
+ *     any stream is fine).
  *     A DFT workspace (scratch of the transform in flight + the twiddles cached in it, written
  *     by a kernel on the stream of the first call) belongs to ONE stream: give every stream its
  *     own workspace (the Python wrappers key their workspace cache by device and stream).

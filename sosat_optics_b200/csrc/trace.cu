@@ -198,9 +198,9 @@ struct BinParams {
     const int *tile_rows;     // optional: tile row ty of this launch is row tile_rows[ty] of the grid
 };
 
-// Persistent CTAs walk STRIPS of adjacent 16 x 16 patches of the launch grid (strips dealt
-// round-robin); a warp owns an 8 (theta) x 4 (phi) sub-patch, so its 32 rays land in a handful
-// of neighbouring bins.
+// Persistent CTAs walk STRIPS of adjacent 16 x 16 patches of the launch grid (strips handed out
+// dynamically, rim of the cone first); a warp owns an 8 (theta) x 4 (phi) sub-patch, so its 32
+// rays land in a handful of neighbouring bins.
 // * Seeds: from the third tile of a strip on, a warp whose 32 lanes all hold a finite two-tile
 //   history takes the predicted-seed tracer (trace_device.cuh: one fp64 Newton step from
 //   2 t(x-1) - t(x-2)); the first two tiles, ragged edge tiles, warps with a lane whose history
@@ -841,8 +841,8 @@ extern "C" int sosat_rx_to_lyot_host(const sosat_geom_t *h_geom, const double *h
 }
 
 // Launch the persistent binning kernel with grid = SMs x resident CTAs per SM.  The strip length
-// is chosen here because it needs the grid size: strips are dealt round-robin, so there must be
-// many more strips than CTAs; a predicted-seed strip pays two fp32-seeded tiles at its start.
+// is chosen here because it needs the grid size: strips are handed out dynamically, so there must
+// be many more strips than CTAs; a predicted-seed strip pays two fp32-seeded tiles at its start.
 template <int N32, int N64, int MINB, int GEO>
 static void launch_bin(BinParams p, const double *rx, float *re, float *im, float *cnt,
                        double *stats, cudaStream_t st) {

@@ -400,6 +400,8 @@ def beam_sweep_distributed(tele_geo, rx_list, freqs, grid_n: int = 256,
     part = sweep_fn(tele_geo, rx_arr[mine], freqs, grid_n, extent_cm, pad) if mine else None
     if world == 1:
         return part
+    if sweep_fn is ray_trace.beam_sweep and dist.get_backend(group) == "nccl":
+        return _gather_sweep_nccl(part, len(rx_arr), len(list(freqs)), world, rank, group)
     gathered = [None] * world
     dist.all_gather_object(gathered, (mine, part), group=group)
     first = next(p for _, p in gathered if p is not None)
@@ -410,6 +412,46 @@ def beam_sweep_distributed(tele_geo, rx_list, freqs, grid_n: int = 256,
             continue
         for k, v in p.items():
             merged[k][idx] = v
+    return merged
+
+
+# beam_sweep's result as one float64 row per receiver: [fwhm F | peak F | peak_index 2F | 3 scalars]
+_SWEEP_KEYS = ("fwhm_arcmin", "peak", "peak_index", "n_valid", "n_binned", "mean_opl")
+
+
+def _gather_sweep_nccl(part, n_rx: int, n_freq: int, world: int, rank: int, group) -> dict:
+    """Gather the per-receiver scalars of a sharded sweep with ONE NCCL all-gather of a packed
+    float64 tensor (an ``all_gather_object`` pickles through the host: ~1 ms at 8 ranks, a
+    quarter of the sharded configs[3] sweep)."""
+    import torch
+    dist = _dist()
+    per_rank = (n_rx + world - 1) // world
+    width = 4 * n_freq + 3
+    buf = np.zeros((per_rank, width))
+    if part is not None:
+        m = len(part["n_valid"])
+        buf[:m, 0:n_freq] = part["fwhm_arcmin"]
+        buf[:m, n_freq:2 * n_freq] = part["peak"]
+        buf[:m, 2 * n_freq:4 * n_freq] = part["peak_index"].reshape(m, 2 * n_freq)  # < 2^53: exact
+        buf[:m, 4 * n_freq] = part["n_valid"]
+        buf[:m, 4 * n_freq + 1] = part["n_binned"]
+        buf[:m, 4 * n_freq + 2] = part["mean_opl"]
+    mine = torch.from_numpy(buf).to("cuda")
+    out = torch.empty((world, per_rank, width), dtype=torch.float64, device="cuda")
+    dist.all_gather_into_tensor(out, mine, group=group)
+    h = out.cpu().numpy()
+    merged = {"fwhm_arcmin": np.zeros((n_rx, n_freq)), "peak": np.zeros((n_rx, n_freq)),
+              "peak_index": np.zeros((n_rx, n_freq, 2), dtype=np.int64), "n_valid": np.zeros(n_rx),
+              "n_binned": np.zeros(n_rx), "mean_opl": np.zeros(n_rx)}
+    for r in range(world):
+        idx = partition_items(n_rx, world, r)
+        rows = h[r, :len(idx)]
+        merged["fwhm_arcmin"][idx] = rows[:, 0:n_freq]
+        merged["peak"][idx] = rows[:, n_freq:2 * n_freq]
+        merged["peak_index"][idx] = np.rint(rows[:, 2 * n_freq:4 * n_freq]).astype(np.int64).reshape(-1, n_freq, 2)
+        merged["n_valid"][idx] = rows[:, 4 * n_freq]
+        merged["n_binned"][idx] = rows[:, 4 * n_freq + 1]
+        merged["mean_opl"][idx] = rows[:, 4 * n_freq + 2]
     return merged
 
 
