@@ -963,10 +963,14 @@ static int trace_bin_common(const double *d_rx, int n_rx, const sosat_freq_t *h_
                   "too many ray tiles for one launch (%lld): split the receiver list or the row range",
                   (long long)p.tiles_x * p.tiles_y * n_rx);
     // Predicted seeds (trace_device.cuh: trace_ray_predicted): the extrapolation error over one
-    // tile step, (16 dtheta)^2 |t''| <= 2.4e3 mm/rad^2 x (16 step)^2, must stay inside the
-    // 2^-10 mm step bound of the one-step schedule with a margin of 2: 16 step <= 4.5e-4 rad,
-    // i.e. n_scan >= ~28 500 for the 0.8 rad cone.  SOSAT_TRACE_PREDICT=0/1 forces it.
-    p.predict = 16.0 * p.lin_step <= 4.5e-4 && p.lin_step > 0.0;
+    // tile step is (16 dtheta)^2 |t''| <= 2.4e3 mm/rad^2 x (16 step)^2: 4e-4 mm at n_scan = 31 623,
+    // 1.5e-3 mm at 16 384.  A lane whose fp64 step exceeds 2^-10 mm is re-traced adaptively and its
+    // warp falls back to the fp32 seeds for two tiles, so a grid that is too coarse for the
+    // prediction costs nothing but the attempt.  Measured (scripts/ab_predict_threshold.py, time
+    // against the fp32 seeds, bin counts identical everywhere): 0.74 at n_scan >= 26 000, 0.78 at
+    // 16 384, 0.85 at 12 000, 0.91 at 10 000, 0.99-1.01 at <= 8 192.  Enabled for
+    // 16 step <= 1.3e-3 rad (n_scan >= ~9 850 for the 0.8 rad cone); SOSAT_TRACE_PREDICT=0/1 forces it.
+    p.predict = 16.0 * p.lin_step <= 1.3e-3 && p.lin_step > 0.0;
     if (const char *e = getenv("SOSAT_TRACE_PREDICT")) p.predict = atoi(e) != 0;
     if (trace_variant() != 7 || geo == 2) p.predict = 0;
     switch (trace_variant()) {

@@ -1028,3 +1028,26 @@ def test_predicted_seeds_with_two_receivers_and_two_frequencies(mods, monkeypatc
             scale = max(np.abs(rre).max(), np.abs(rim).max())
             assert np.abs(re[i, f].cpu().numpy() - rre).max() < 2e-3 * scale
             assert np.abs(im[i, f].cpu().numpy() - rim).max() < 2e-3 * scale
+
+
+@pytest.mark.parametrize("n_scan", [10500, 16384])
+def test_predicted_seeds_at_the_coarse_end_of_their_range(mods, monkeypatch, n_scan):
+    """The launch heuristic enables the predicted seeds from n_scan ~ 9 850 on, where the
+    extrapolation error (up to 3e-3 mm) exceeds the 2^-10 mm step bound for part of the lanes:
+    those are re-traced adaptively.  A 32-row block through the axis and one at the rim, off-axis
+    feed, against the oracle: statistics exact, sum of OPL to 1e-7 mm per ray on the axis block."""
+    rt, oracle = mods["rt"], mods["oracle"]
+    monkeypatch.setenv("SOSAT_STRIP_LEN", "32")     # a 32-row block alone is below the strip heuristic
+    t = _bundle(mods, n_scan)
+    spec = [(t.k, t.th_fwhp_x, t.th_fwhp_y)]
+    rx = [60.0, 0.0, 45.0]
+    for r0, per_ray in ((n_scan // 2 - 16, 1e-7), (n_scan // 9, OPL_WILD_MM)):
+        re, im, cnt, st = rt.trace_bin_device(t, [rx], spec, 1024, 420.0, row_begin=r0, row_end=r0 + 32)
+        ref = oracle.rx_to_lyot(rx, t, ray_begin=r0 * n_scan, ray_end=(r0 + 32) * n_scan)
+        rre, rim, rcnt, sums = oracle.bin_near_field(ref, float(t.k), 1024, 420.0, 0.0)
+        st = st.cpu().numpy()[0]
+        assert int(st[0]) == sums["n_valid"] and int(st[7]) == sums["n_binned"] and int(st[6]) == 0
+        assert abs(st[1] - sums["sum_opl"]) <= per_ray * max(1, sums["n_valid"])
+        assert np.abs(cnt[0].cpu().numpy() - rcnt).sum() <= 4
+        scale = max(np.abs(rre).max(), np.abs(rim).max(), 1e-30)
+        assert np.abs(re[0, 0].cpu().numpy() - rre).max() < 2e-3 * scale
