@@ -265,6 +265,28 @@ def other_configs(torch, ot_geo, opt_analyze, ray_trace, table):
     opt_analyze.a2b(amp, amp)
     out["cfg1_a2b_1000_host"] = {"wall_ms": (time.perf_counter() - t0) * 1e3,
                                  "reference": "81 ms (BASELINE.md, numpy 1 core)"}
+    # cfg 1, the notebook's own route (sat_farfield.ipynb cells 1-6): getNearField -> sim2d (cubic
+    # griddata restated on the device) -> sim_data (bicubic spline) -> zero_pad -> a2b, n_scan = 100
+    t = _tele_geo(ot_geo, opt_analyze, table, 100)
+    def notebook_route():
+        sb = ray_trace.getNearField(t, [0, 0, 0])
+        t1 = time.perf_counter()
+        sb2 = ray_trace.sim2d(sb)
+        t2 = time.perf_counter()
+        dd = ray_trace.sim_data(sb2, 80, 2)
+        t3 = time.perf_counter()
+        _, _, bd = opt_analyze.zero_pad(dd.x_data, dd.y_data, dd.a_data, 100)
+        xd, yd, pd = opt_analyze.zero_pad(dd.x_data, dd.y_data, dd.p_data, 100)
+        bf, _ = opt_analyze.a2b(bd, np.rad2deg(pd))
+        xa, ya = opt_analyze.coords_spat_to_ang(xd / 1e2, yd / 1e2, GHZ)
+        return t2 - t1, t3 - t2, ray_trace.ff_fwhm_est(bf, xa, ya)
+    notebook_route()
+    t0 = time.perf_counter()
+    w_sim2d, w_sim_data, fwhm = notebook_route()
+    out["cfg1_notebook_route_n100"] = {
+        "wall_ms": (time.perf_counter() - t0) * 1e3, "sim2d_ms": w_sim2d * 1e3, "sim_data_ms": w_sim_data * 1e3,
+        "fwhm_arcmin": float(fwhm),
+        "reference": "getNearField 15 s + sim2d 0.46 s + sim_data 0.05 s + a2b (BASELINE.md, 1 core)"}
     # cfg 2: 64-frequency sweep 77-106 GHz at n_scan=150, one fused launch
     t = _tele_geo(ot_geo, opt_analyze, table, 150)
     freqs = geometry.freq_specs_from_table(np.linspace(77, 106, 64), table)
