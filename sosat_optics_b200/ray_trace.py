@@ -338,6 +338,10 @@ def sim2d(sb):
     n = len(sb.a_sim)
     if not (len(sb.x_sim) == len(sb.y_sim) == len(sb.p_sim) == len(idx) == n) or n == 0:
         raise ValueError("sim2d: x_sim, y_sim, a_sim, p_sim and ray_index must have one entry per ray")
+    idx = np.asarray(idx, dtype=np.int64)
+    if int(n_scan) < 2 or idx.min() < 0 or idx.max() >= int(n_scan) ** 2 or np.any(np.diff(idx) <= 0):
+        raise ValueError("sim2d: ray_index must be strictly increasing indices into the "
+                         "n_scan x n_scan launch lattice")
     up = lambda a, dt: torch.from_numpy(np.ascontiguousarray(np.asarray(a, dtype=dt))).to("cuda")  # noqa: E731
     d_x, d_y, d_a, d_p = (up(v, np.float64) for v in (sb.x_sim, sb.y_sim, sb.a_sim, sb.p_sim))
     d_idx = up(idx, np.int64)
