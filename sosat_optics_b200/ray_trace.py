@@ -583,6 +583,9 @@ def near_field_binned(tele_geo, rx, grid_n: int = 256, extent_cm: Optional[float
     return BinnedField(b, out_c, out_s, extent_cm, grid_n, re, im)
 
 
+SWEEP_BYTES_PER_PASS = 12e9   # device memory budget of one pass of beam_sweep (fields + workspace)
+
+
 def beam_sweep(tele_geo, rx_list, freqs, grid_n: int = 256, extent_cm: Optional[float] = None,
                pad: int = 0):
     """BASELINE configs[3]: near + far field of every (receiver, frequency) pair of a focal-plane
@@ -606,7 +609,7 @@ def beam_sweep(tele_geo, rx_list, freqs, grid_n: int = 256, extent_cm: Optional[
     n_freq, n_far = len(specs), grid_n + 2 * pad
     # receivers per pass: the far-field stack and its workspace (~80 B per padded cell and field)
     # stay below ~12 GB however long the receiver list is
-    per_pass = max(1, min(int(12e9 // (80 * n_far * n_far * n_freq)), 4096 // n_freq))
+    per_pass = max(1, min(int(SWEEP_BYTES_PER_PASS // (80 * n_far * n_far * n_freq)), 4096 // n_freq))
     parts = []
     for r0 in range(0, rx_arr.shape[0], per_pass):
         rxs = rx_arr[r0:r0 + per_pass]
