@@ -848,12 +848,15 @@ __device__ __forceinline__ void split_bf16(float x, __nv_bfloat16 &hi, __nv_bflo
     lo = __float2bfloat16_rn(x - __bfloat162float(hi));
 }
 
-// Twiddle operands for both passes; np = padded size, rows/cols beyond n are zero.
-//   a1 (pass 1, K interleaved): a1[2l+c][2n+c'],   a2 (pass 2, K planar): a2[2k+c][c' np + m]
+// Twiddle operand of BOTH passes; np = padded size, rows/cols beyond n are zero.
+//   a[2k+c][c' np + m] = component (c, c') of W[k, m] folded as [Wr, -Wi; Wi, Wr]  (K planar)
 // W[k, m] = exp(sign 2 pi i ((k - so)(m - si) mod n) / n): the shifts express the fftshift /
-// ifftshift pairs of the reference (see dft_kind_params).
-__global__ void twiddle_kernel(int n, int np, int so, int si, int sign, __nv_bfloat16 *a1_hi,
-                               __nv_bfloat16 *a1_lo, __nv_bfloat16 *a2_hi, __nv_bfloat16 *a2_lo) {
+// ifftshift pairs of the reference (see dft_kind_params).  Pass 1 contracts it with the data
+// operand X[m][c' np + n] over (c', n), pass 2 with D1[l][c' np + m] over (c', m): the same
+// matrix in the same layout, so it is generated, stored and (second pass: mostly from L2) read
+// once -- round 1 kept a K-interleaved copy for pass 1, 16 np^2 bytes more traffic per transform.
+__global__ void twiddle_kernel(int n, int np, int so, int si, int sign, __nv_bfloat16 *a_hi,
+                               __nv_bfloat16 *a_lo) {
     const int col = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
     if (col >= np) return;
     float wr = 0.f, wi = 0.f;
@@ -873,10 +876,8 @@ __global__ void twiddle_kernel(int n, int np, int so, int si, int sign, __nv_bfl
         for (int cp = 0; cp < 2; ++cp) {
             __nv_bfloat16 h, l;
             split_bf16(vals[c][cp], h, l);
-            const size_t i1 = (size_t)(2 * row + c) * ld + 2 * col + cp;
-            const size_t i2 = (size_t)(2 * row + c) * ld + (size_t)cp * np + col;
-            a1_hi[i1] = h; a1_lo[i1] = l;
-            a2_hi[i2] = h; a2_lo[i2] = l;
+            const size_t i = (size_t)(2 * row + c) * ld + (size_t)cp * np + col;
+            a_hi[i] = h; a_lo[i] = l;
         }
 }
 
@@ -884,7 +885,8 @@ __global__ void twiddle_kernel(int n, int np, int so, int si, int sign, __nv_bfl
 //   W1[l][n] = exp(-2 pi i y_n thy_l / lambda)   (pass 1, rows of b = y axis)
 //   W2[k][m] = exp(-2 pi i x_m thx_k / lambda)   (pass 2, columns of b = x axis)
 // coords: y[n], x[n] (n values each), angles: thy[n_out], thx[n_out]; the phase in cycles is
-// reduced in fp64 before sincospi.  Same [c][c'] folding and layouts as twiddle_kernel.
+// reduced in fp64 before sincospi.  Same [c][c'] folding and K-planar layout as twiddle_kernel;
+// the two passes have different matrices here, so both operand planes are used.
 __global__ void twiddle_zoom_kernel(int n, int n_out, int np, const double *__restrict__ y,
                                     const double *__restrict__ thy, const double *__restrict__ x,
                                     const double *__restrict__ thx, double inv_lambda,
@@ -910,8 +912,8 @@ __global__ void twiddle_zoom_kernel(int n, int n_out, int np, const double *__re
 #pragma unroll
         for (int cp = 0; cp < 2; ++cp) {
             __nv_bfloat16 h, l;
-            const size_t i1 = (size_t)(2 * row + c) * ld + 2 * col + cp;
-            const size_t i2 = (size_t)(2 * row + c) * ld + (size_t)cp * np + col;
+            const size_t i1 = (size_t)(2 * row + c) * ld + (size_t)cp * np + col;
+            const size_t i2 = i1;
             split_bf16(v1[c][cp], h, l);
             a1_hi[i1] = h; a1_lo[i1] = l;
             split_bf16(v2[c][cp], h, l);
@@ -919,9 +921,9 @@ __global__ void twiddle_zoom_kernel(int n, int n_out, int np, const double *__re
         }
 }
 
-// Data operand of pass 1: X[m][2n+c'] = component c' of b[n][m] (the transpose, zero padded to
-// np), split into bf16 hi/lo.  32 x 32 tiles through shared memory: coalesced 8-byte reads along
-// the rows of b, coalesced 4-byte (bf16x2) writes along the rows of X.  LOAD(row, col) returns
+// Data operand of pass 1: X[m][c' np + n] = component c' of b[n][m] (the transpose, zero padded
+// to np, K planar like the twiddle operand), split into bf16 hi/lo.  32 x 32 tiles through shared
+// memory: coalesced 8-byte reads along the rows of b, coalesced 2-byte writes along the rows of X.  LOAD(row, col) returns
 // the complex sample b[row][col].
 template <class Load>
 __device__ __forceinline__ void prep_transposed(Load load, int n, int np, __nv_bfloat16 *b_hi,
@@ -942,9 +944,9 @@ __device__ __forceinline__ void prep_transposed(Load load, int n, int np, __nv_b
         __nv_bfloat16 h0, l0, h1, l1;
         split_bf16(v.x, h0, l0);
         split_bf16(v.y, h1, l1);
-        const size_t i = (size_t)m * 2 * np + 2 * nn;
-        *(__nv_bfloat162 *)(b_hi + i) = __nv_bfloat162(h0, h1);
-        *(__nv_bfloat162 *)(b_lo + i) = __nv_bfloat162(l0, l1);
+        const size_t i = (size_t)m * 2 * np + nn;
+        b_hi[i] = h0; b_hi[i + np] = h1;
+        b_lo[i] = l0; b_lo[i + np] = l1;
     }
 }
 
@@ -1151,10 +1153,14 @@ static int ensure_plan(const DftWorkspace &w, int kind, cudaStream_t st, PlanEnt
     const uint64_t np = w.np;
     const int half = 64, full = 128;
     int rc = 0;
-    // pass 1: A = twiddle a1 rows (l,c) (cluster y = M: always 2 -> B slices), B = X rows m
-    //   A is shared along cluster x (CX = wide ? 2 : 1), B along cluster y (CY = 2)
-    if ((rc = make_map(&e.maps[0], w.a1_hi, 2 * np, 2 * np, e.wide ? half : full))) return rc;
-    if ((rc = make_map(&e.maps[1], w.a1_lo, 2 * np, 2 * np, e.wide ? half : full))) return rc;
+    // pass 1: A = twiddle rows (l,c) (cluster y = M: always 2 -> B slices), B = X rows m
+    //   A is shared along cluster x (CX = wide ? 2 : 1), B along cluster y (CY = 2).
+    // The FFT kinds use ONE twiddle operand for both passes (the a2 planes); only the zoomed
+    // transform, whose two passes have different matrices, fills a1 as well.
+    const __nv_bfloat16 *t1_hi = kind == kKindZoom ? w.a1_hi : w.a2_hi;
+    const __nv_bfloat16 *t1_lo = kind == kKindZoom ? w.a1_lo : w.a2_lo;
+    if ((rc = make_map(&e.maps[0], t1_hi, 2 * np, 2 * np, e.wide ? half : full))) return rc;
+    if ((rc = make_map(&e.maps[1], t1_lo, 2 * np, 2 * np, e.wide ? half : full))) return rc;
     if ((rc = make_map(&e.maps[2], w.b1_hi, np, 2 * np, half))) return rc;
     if ((rc = make_map(&e.maps[3], w.b1_lo, np, 2 * np, half))) return rc;
     // pass 2: A = pass-1 output [2 np][np] viewed as [np][2 np] rows l, B = twiddle a2 rows (k,c)
@@ -1164,8 +1170,8 @@ static int ensure_plan(const DftWorkspace &w, int kind, cudaStream_t st, PlanEnt
     if ((rc = make_map(&e.maps[6], w.a2_hi, 2 * np, 2 * np, e.wide ? half : full))) return rc;
     if ((rc = make_map(&e.maps[7], w.a2_lo, 2 * np, 2 * np, e.wide ? half : full))) return rc;
     // CTA-pair kernel: whole 128-row A boxes, 64-row halves of the B tile
-    if ((rc = make_map(&e.pair[0], w.a1_hi, 2 * np, 2 * np, full))) return rc;
-    if ((rc = make_map(&e.pair[1], w.a1_lo, 2 * np, 2 * np, full))) return rc;
+    if ((rc = make_map(&e.pair[0], t1_hi, 2 * np, 2 * np, full))) return rc;
+    if ((rc = make_map(&e.pair[1], t1_lo, 2 * np, 2 * np, full))) return rc;
     if ((rc = make_map(&e.pair[2], w.b1_hi, np, 2 * np, half))) return rc;
     if ((rc = make_map(&e.pair[3], w.b1_lo, np, 2 * np, half))) return rc;
     if ((rc = make_map(&e.pair[4], w.d1_hi, np, 2 * np, full))) return rc;
@@ -1179,8 +1185,7 @@ static int ensure_plan(const DftWorkspace &w, int kind, cudaStream_t st, PlanEnt
     if ((rc = make_map(&e.pair256[7], w.a2_lo, 2 * np, 2 * np, full))) return rc;
     if (kind != kKindZoom) {
         dim3 grid((w.np + 127) / 128, w.np);
-        twiddle_kernel<<<grid, 128, 0, st>>>(w.n, w.np, so, si, sign, w.a1_hi, w.a1_lo, w.a2_hi,
-                                             w.a2_lo);
+        twiddle_kernel<<<grid, 128, 0, st>>>(w.n, w.np, so, si, sign, w.a2_hi, w.a2_lo);
         SOSAT_CUDA_OK(cudaGetLastError());
     }
     int slot = -1;
