@@ -80,6 +80,27 @@ def test_product_never_imports_the_oracle():
                 assert "import oracle" not in text and "from oracle" not in text
 
 
+def test_product_does_not_import_scipy():
+    """Round 1's sim2d / sim_data were host scipy; since round 2 they run on the device and the
+    product package must not import scipy anywhere (tests and the oracle may)."""
+    import re
+    pkg = os.path.join(ROOT, "sosat_optics_b200")
+    for f in os.listdir(pkg):
+        if f.endswith(".py"):
+            text = open(os.path.join(pkg, f)).read()
+            assert not re.search(r"^\s*(import|from)\s+scipy", text, flags=re.M), f
+    # and the no-GPU error comes before any work in the two glue functions
+    from types import SimpleNamespace
+    sb = SimpleNamespace(x_sim=np.zeros(4), y_sim=np.zeros(4), a_sim=np.zeros(4), p_sim=np.zeros(4),
+                         ray_index=np.arange(4), n_scan=2)
+    with pytest.raises(_lib.SosatError):
+        ray_trace.sim2d(sb)
+    grid = SimpleNamespace(a_sim=np.zeros((8, 8)), p_sim=np.zeros((8, 8)),
+                           x_sim=np.mgrid[0:1:8j, 0:1:8j][0], y_sim=np.mgrid[0:1:8j, 0:1:8j][1])
+    with pytest.raises(_lib.SosatError):
+        ray_trace.sim_data(grid, 2, 0.5)
+
+
 def test_geometry_marshalling():
     t = ot_geo.SatGeo()
     t.y_source = ot_geo.y_lyot + 300
