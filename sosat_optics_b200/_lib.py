@@ -106,6 +106,8 @@ SIGNATURES = {
     "sosat_sim_data_work_doubles": (c_size_t, [c_int, c_int]),
     "sosat_sim_data": (c_int, [c_void_p, c_void_p, c_int, c_void_p, c_void_p, c_int, c_void_p,
                                c_void_p, c_void_p, c_void_p]),
+    "sosat_peer_barrier": (c_int, [POINTER(c_void_p), c_int, c_int, c_int64, ctypes.c_uint64, c_double,
+                                   c_void_p]),
     "sosat_measure_fp64_peak": (c_int, [POINTER(c_double), POINTER(c_double)]),
     "sosat_peer_alloc": (c_int, [c_int64, POINTER(c_void_p)]),
     "sosat_peer_free": (c_int, [c_void_p]),

@@ -108,6 +108,41 @@ bins_reduce_field_kernel(const __grid_constant__ PeerArgs P, long long begin, lo
     }
 }
 
+// ---- barrier over the ranks of the node through flags in peer-mapped memory --------------------
+// Every rank owns an array of 64-bit slots in its exported buffer.  Rank r announces "epoch e
+// reached" by storing e into slot r of EVERY peer's array (st.release.sys after a system fence:
+// the kernels this rank launched before, in stream order, have completed, so their writes are
+// performed) and waits until all slots of its own array hold >= e (ld.acquire.sys).  One tiny
+// kernel per barrier, stream-ordered like the one-element NCCL all-reduce it replaces (8 us
+// against 40 us at 8 GPUs).  Epochs only grow, so a peer that is already one barrier ahead does no
+// harm.  A rank that waits longer than timeout_ns gives up, records it in slot 63 and returns --
+// wrong data later (the callers check the slot) instead of a hung GPU.
+constexpr int kBarrierErrSlot = 63;
+
+__global__ void peer_barrier_kernel(PeerArgs P, int rank, long long flags_off,
+                                    unsigned long long epoch, unsigned long long timeout_ns) {
+    const int t = threadIdx.x;
+    if (t >= P.n_peers) return;
+    __threadfence_system();
+    unsigned long long *remote = (unsigned long long *)(const_cast<char *>(P.base[t]) + flags_off) + rank;
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(remote), "l"(epoch) : "memory");
+    const unsigned long long *mine =
+        (const unsigned long long *)(P.base[rank] + flags_off) + t;
+    unsigned long long t0, now, seen = 0;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+    for (;;) {
+        asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(seen) : "l"(mine) : "memory");
+        if (seen >= epoch) break;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+        if (now - t0 > timeout_ns) {
+            unsigned long long *err = (unsigned long long *)(const_cast<char *>(P.base[rank]) + flags_off) + kBarrierErrSlot;
+            *err = epoch;
+            break;
+        }
+        __nanosleep(200);
+    }
+}
+
 }  // namespace sosat
 
 using namespace sosat;
@@ -210,4 +245,24 @@ extern "C" int sosat_bins_reduce_field(const void *const *h_peer_base, int n_pee
     return sosat_bins_reduce_fields(h_peer_base, n_peers, re_off, im_off, cnt_off, stats_off,
                                     cell_end, 1, 1, cell_begin, cell_end, &k_over_2e3, opl_ref,
                                     h_out_base, n_out, out_off, d_stats_sum, stream);
+}
+
+extern "C" int sosat_peer_barrier(const void *const *h_peer_base, int n_peers, int rank,
+                                  int64_t flags_off, uint64_t epoch, double timeout_s, void *stream) {
+    SOSAT_REQUIRE(h_peer_base, "sosat_peer_barrier: null pointer");
+    SOSAT_REQUIRE(n_peers >= 1 && n_peers <= kMaxPeers && rank >= 0 && rank < n_peers,
+                  "sosat_peer_barrier: rank %d of %d peers", rank, n_peers);
+    SOSAT_REQUIRE(flags_off >= 0 && flags_off % 8 == 0 && epoch > 0, "bad flag offset or epoch");
+    PeerArgs P;
+    memset(&P, 0, sizeof P);
+    for (int p = 0; p < n_peers; ++p) {
+        SOSAT_REQUIRE(h_peer_base[p], "peer base null");
+        P.base[p] = (const char *)h_peer_base[p];
+    }
+    P.n_peers = n_peers;
+    const unsigned long long ns = (unsigned long long)((timeout_s > 0 ? timeout_s : 10.0) * 1e9);
+    peer_barrier_kernel<<<1, 32, 0, (cudaStream_t)stream>>>(P, rank, flags_off,
+                                                            (unsigned long long)epoch, ns);
+    SOSAT_CUDA_OK(cudaGetLastError());
+    return SOSAT_OK;
 }

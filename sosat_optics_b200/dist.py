@@ -136,7 +136,7 @@ def peer_layout(n_rx: int, n_freq: int, grid_n: int) -> dict:
     off, out = 0, {}
     for name, nbytes in (("re", 4 * n_ri), ("im", 4 * n_ri), ("cnt", 4 * n_c),
                          ("stats", 8 * 8 * n_rx), ("stats_sum", 8 * 8 * n_rx), ("field", 8 * n_ri),
-                         ("out", 8 * n_ri)):
+                         ("out", 8 * n_ri), ("flags", 64 * 8)):
         out[name] = off
         off += (nbytes + 255) // 256 * 256
     out["bytes"] = off
@@ -217,6 +217,11 @@ class PeerPlanes:
             view("out", 8 * n_ri, torch.float32, (n_rx, n_freq, grid_n, grid_n, 2)))
         self.accum = self.flat[:L["accum_bytes"]]
         self._flag = torch.zeros(1, dtype=torch.float32, device="cuda")
+        self.flags = view("flags", 64 * 8, torch.int64, (64,))
+        self._epoch = 0
+        # barriers: flags in the peer-mapped buffers (default) or a one-element NCCL all-reduce
+        import os
+        self._flag_barrier = os.environ.get("SOSAT_PEER_BARRIER", "flags") != "nccl"
         self._c_peers = (ctypes.c_void_p * self.world)(*self.peer_base)
 
     def _exchange(self, obj):
@@ -238,9 +243,28 @@ class PeerPlanes:
         self.accum.zero_()
 
     def barrier(self):
-        """Stream-ordered barrier over the ranks (one-element NCCL all-reduce; no host sync)."""
-        if self.world > 1:
+        """Stream-ordered barrier over the ranks, no host sync: every rank writes an epoch into
+        a flag slot of every peer's buffer and waits for all of its own slots
+        (``sosat_peer_barrier``); ``SOSAT_PEER_BARRIER=nccl`` selects the one-element NCCL
+        all-reduce it replaced."""
+        if self.world == 1:
+            return
+        if not self._flag_barrier:
             _dist().all_reduce(self._flag, group=self.group)
+            return
+        import ctypes
+        import torch
+        from . import _lib
+        self._epoch += 1
+        _lib.check(self.lib.sosat_peer_barrier(
+            self._c_peers, self.world, self.rank, self.layout["flags"], self._epoch, 10.0,
+            ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)))
+
+    def check(self):
+        """Raise if a flag barrier of this rank ever timed out (host sync; call off the hot path)."""
+        if self.world > 1 and self.base and int(self.flags[63].item()) != 0:
+            raise RuntimeError(f"PeerPlanes: rank {self.rank} timed out in the peer barrier of epoch "
+                               f"{int(self.flags[63].item())}: a peer never arrived")
 
     def reduce_field(self, freq_specs, opl_ref: float = 0.0, dest: Optional[Sequence[int]] = None):
         """Sum every rank's planes and statistics, normalise to the complex field and store it
@@ -305,8 +329,13 @@ class PeerPlanes:
         if getattr(self, "_closed", False):
             return
         self._closed = True
+        timed_out = None
         if torch.cuda.is_available():
             torch.cuda.synchronize()  # no reduce kernel of this rank still reads a peer
+            try:
+                self.check()
+            except RuntimeError as exc:
+                timed_out = exc
         err = None
         for ptr in self._opened:
             try:
@@ -317,14 +346,16 @@ class PeerPlanes:
         # every rank takes part, also one whose own allocation failed (base == 0)
         self._exchange("closed")  # every peer has dropped its mapping of this rank's buffer
         if self.base:
-            for name in ("re", "im", "cnt", "stats", "stats_sum", "field", "out", "accum", "flat", "_raw",
-                         "_peer_out"):
+            for name in ("re", "im", "cnt", "stats", "stats_sum", "field", "out", "flags", "accum", "flat",
+                         "_raw", "_peer_out"):
                 if hasattr(self, name):
                     setattr(self, name, None)
             _lib.check(self.lib.sosat_peer_free(ctypes.c_void_p(self.base)))
             self.base = 0
         if err is not None:
             raise err
+        if timed_out is not None:
+            raise timed_out
 
 
 def near_field_binned_distributed(tele_geo, rx, grid_n: int, extent_cm: float,
