@@ -21,16 +21,16 @@ im, cnt = torch.zeros_like(re), torch.zeros((1, 2048, 2048), device="cuda")
 st = torch.zeros((1, 8), dtype=torch.float64, device="cuda")
 
 VARIANTS = [{"SOSAT_TRACE_PREDICT": "0"}, {"SOSAT_TRACE_PREDICT": "1"},
-            {"SOSAT_TRACE_PREDICT": "1", "SOSAT_STRIP_LEN": "16"},
+            {"SOSAT_TRACE_PREDICT": "1", "SOSAT_STRIP_ONE_PHASE": "1"},
             {"SOSAT_TRACE_PREDICT": "1", "SOSAT_STRIP_LEN": "32"},
-            {"SOSAT_TRACE_PREDICT": "1", "SOSAT_STRIP_LEN": "128"}]
+            {"SOSAT_TRACE_PREDICT": "1", "SOSAT_STRIP_LEN": "64"}]
 ROWS = None
 if len(sys.argv) > 2:   # emulate rank 0 of a W-rank cyclic tile-row deal
     from sosat_optics_b200 import dist as sdist
     ROWS = torch.from_numpy(sdist.partition_tile_rows(n_scan, int(sys.argv[2]), 0)).to("cuda")
 base = None
 for env in VARIANTS:
-    for k in ("SOSAT_TRACE_PREDICT", "SOSAT_STRIP_LEN"):
+    for k in ("SOSAT_TRACE_PREDICT", "SOSAT_STRIP_LEN", "SOSAT_STRIP_ONE_PHASE"):
         os.environ.pop(k, None)
     os.environ.update(env)
     ts = []
