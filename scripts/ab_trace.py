@@ -21,7 +21,6 @@ im, cnt = torch.zeros_like(re), torch.zeros((1, 2048, 2048), device="cuda")
 st = torch.zeros((1, 8), dtype=torch.float64, device="cuda")
 
 VARIANTS = [{"SOSAT_TRACE_PREDICT": "0"}, {"SOSAT_TRACE_PREDICT": "1"},
-            {"SOSAT_TRACE_PREDICT": "1", "SOSAT_STRIP_ONE_PHASE": "1"},
             {"SOSAT_TRACE_PREDICT": "1", "SOSAT_STRIP_LEN": "32"},
             {"SOSAT_TRACE_PREDICT": "1", "SOSAT_STRIP_LEN": "64"}]
 ROWS = None
@@ -30,7 +29,7 @@ if len(sys.argv) > 2:   # emulate rank 0 of a W-rank cyclic tile-row deal
     ROWS = torch.from_numpy(sdist.partition_tile_rows(n_scan, int(sys.argv[2]), 0)).to("cuda")
 base = None
 for env in VARIANTS:
-    for k in ("SOSAT_TRACE_PREDICT", "SOSAT_STRIP_LEN", "SOSAT_STRIP_ONE_PHASE"):
+    for k in ("SOSAT_TRACE_PREDICT", "SOSAT_STRIP_LEN"):
         os.environ.pop(k, None)
     os.environ.update(env)
     ts = []
