@@ -1073,3 +1073,32 @@ def test_beam_sweep_in_several_passes_equals_one_pass(mods, monkeypatch, feed_ta
     assert np.allclose(one["peak"], many["peak"], rtol=1e-4)
     assert np.allclose(one["mean_opl"], many["mean_opl"], rtol=1e-13)
     assert np.mean(one["fwhm_arcmin"] == many["fwhm_arcmin"]) >= 0.8
+
+
+@pytest.mark.parametrize("n_scan", [6, 12, 31])
+def test_sim2d_on_coarse_bundles(mods, n_scan):
+    """Edge cases of the device gridder: very few rays (a 6 x 6 lattice has ~20 valid rays), odd
+    lattice sizes.  The output is finite, zero beyond 20 cm, and agrees with scipy's griddata
+    wherever that is defined and the point is two lattice cells inside the selected region."""
+    from scipy.interpolate import griddata
+    rt = mods["rt"]
+    t = _bundle(mods, n_scan)
+    sb = rt.getNearField(t, [0, 0, 0], plot=False)
+    if len(sb.a_sim) < 3:
+        with pytest.raises(ValueError):
+            rt.sim2d(sb)
+        return
+    sb2 = rt.sim2d(sb)
+    assert sb2.a_sim.shape == (100, 100) and np.isfinite(sb2.a_sim).all() and np.isfinite(sb2.p_sim).all()
+    cx, cy = np.mean(sb.x_sim), np.mean(sb.y_sim)
+    r2 = (sb2.x_sim - cx) ** 2 + (sb2.y_sim - cy) ** 2
+    assert np.all(sb2.a_sim[r2 >= 400] == 0)
+    sel = (sb.x_sim - cx) ** 2 + (sb.y_sim - cy) ** 2 <= 21.0 ** 2
+    if sel.sum() >= 4:
+        pts = np.array([sb.x_sim[sel], sb.y_sim[sel]]).T
+        want = np.nan_to_num(griddata(pts, sb.a_sim[sel], (sb2.x_sim, sb2.y_sim), method="cubic"))
+        spacing = 42.0 / n_scan * 1.2
+        inner = (r2 < (max(20.0 - 2 * spacing, 0)) ** 2) & (sb2.a_sim != 0) & (want != 0)
+        if inner.any():
+            # coarse lattices: the gradient estimate sees a different boundary (no hull slivers)
+            assert np.abs(sb2.a_sim - want)[inner].max() < 2e-2
