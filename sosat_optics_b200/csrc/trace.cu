@@ -362,6 +362,7 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
         }
         const int iph = ty * kTileH + lph;  // relative to row_begin
         unsigned okbits = 0u;               // bit 0 / 1: the lane's history of the last / last but one tile is finite
+        unsigned strip_counts = 0u;         // valid (low 16 bits) and binned (high 16) rays of this warp in this strip
         int cur = 0;                        // s_hist[cur]: t(x-1), s_hist[cur ^ 1]: t(x-2) -> receives t(x)
         for (int tx = tx_begin, buf = 0; tx < tx_end; ++tx, buf ^= 1) {
             __syncthreads();  // tables of this tile complete; everybody is done with buffer buf ^ 1
@@ -437,10 +438,7 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
             }
             const unsigned vmask = __ballot_sync(0xffffffffu, valid);
             const unsigned bmask = __ballot_sync(0xffffffffu, bin >= 0);
-            if (lane == 0 && vmask) {
-                s_nvalid[warp] += __popc(vmask);
-                s_nbinned[warp] += __popc(bmask);
-            }
+            strip_counts += (unsigned)__popc(vmask) | ((unsigned)__popc(bmask) << 16);  // <= 64 x 32 per strip
             if (re == nullptr || bmask == 0u) continue;
 
             // ---- run-length aggregation along the lane order --------------------------------
@@ -456,7 +454,7 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
             const double dopl = r.opl - p.opl_ref;
             float *re_f = re + (long long)irx * p.n_freq * plane;
             float *im_f = im + (long long)irx * p.n_freq * plane;
-            for (int f = 0; f < p.n_freq; ++f, re_f += plane, im_f += plane) {
+            auto emit = [&](int f, float *re_p, float *im_p) {
                 float vre = 0.f, vim = 0.f;
                 if (bin >= 0) {
                     const float a = s_amp_t[buf][f][lth] * s_amp_p[f][lph];
@@ -479,9 +477,14 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
                     }
                 }
                 if (flush) {
-                    atomicAdd(re_f + bin, vre);
-                    atomicAdd(im_f + bin, vim);
+                    atomicAdd(re_p + bin, vre);
+                    atomicAdd(im_p + bin, vim);
                 }
+            };
+            if (p.n_freq == 1) {  // the common case without the loop's bookkeeping
+                emit(0, re_f, im_f);
+            } else {
+                for (int f = 0; f < p.n_freq; ++f, re_f += plane, im_f += plane) emit(f, re_f, im_f);
             }
         }
 #ifdef SOSAT_STRIP_TIMING
@@ -493,6 +496,10 @@ trace_bin_kernel(BinParams p, const double *__restrict__ d_rx, float *__restrict
             g_strip_t0[strip] = t_begin; g_strip_t1[strip] = t_end; g_strip_sm[strip] = (int)smid;
         }
 #endif
+        if (lane == 0) {
+            s_nvalid[warp] += strip_counts & 0xffffu;
+            s_nbinned[warp] += strip_counts >> 16;
+        }
         if (tid == 0) s_next = (long long)gridDim.x + (long long)atomicAdd(&g_next_strip, 1ull);
         __syncthreads();  // also: every warp is done with this strip's tables
         strip = s_next;
