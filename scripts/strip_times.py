@@ -20,7 +20,7 @@ lib = ctypes.CDLL(os.environ["SOSAT_LIB"])
 tiles_x = (n_scan + 15) // 16
 n_rows = len(rows) if rows is not None else tiles_x
 n_tiles = tiles_x * n_rows
-sl = min(64, n_tiles // (32 * 592))
+sl = max(1, min(64, n_tiles // (8 * 592)))
 strips_x = (tiles_x + sl - 1) // sl
 n = min(strips_x * n_rows, 1 << 17)
 t0 = np.zeros(n, np.int64); t1 = np.zeros(n, np.int64); sm = np.zeros(n, np.int32)

@@ -379,16 +379,15 @@ def _bspline_basis(t, xs, k=3):
     span = np.clip(np.searchsorted(t, xs, side="right") - 1, k, nb - 1)  # t[span] <= x < t[span+1]
     B = np.zeros((len(xs), len(t) - 1))
     B[np.arange(len(xs)), span] = 1.0
+    x = xs[:, None]
     for d in range(1, k + 1):
-        nxt = np.zeros((len(xs), len(t) - 1 - d))
-        for j in range(len(t) - 1 - d):
-            left = t[j + d] - t[j]
-            right = t[j + d + 1] - t[j + 1]
-            if left > 0:
-                nxt[:, j] += (xs - t[j]) / left * B[:, j]
-            if right > 0:
-                nxt[:, j] += (t[j + d + 1] - xs) / right * B[:, j + 1]
-        B = nxt
+        m = len(t) - 1 - d                      # basis functions of degree d
+        left = t[d:d + m] - t[:m]
+        right = t[d + 1:d + 1 + m] - t[1:1 + m]
+        with np.errstate(divide="ignore", invalid="ignore"):
+            wl = np.where(left > 0, (x - t[:m]) / left, 0.0)
+            wr = np.where(right > 0, (t[d + 1:d + 1 + m] - x) / right, 0.0)
+        B = wl * B[:, :m] + wr * B[:, 1:m + 1]
     return B[:, :nb]
 
 
