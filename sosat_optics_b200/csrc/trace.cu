@@ -168,7 +168,6 @@ static_assert(kTileH == SOSAT_TRACE_TILE_ROWS, "sosat_trace_bin_tiles documents 
 // steps of one ray sit next to the fp64 step of the other: -0.8 %, 128 registers.  DESIGN.md
 // section 3; the code is in the history, commits 3515e61 and 95805ee.)
 constexpr int kTileW = kTile;
-constexpr int kTileMax = kTileH > kTileW ? kTileH : kTileW;
 // seed history of the predicted-seed tracer: 2 tiles x 6 surfaces x one double per thread
 constexpr int kHistBytes = 2 * SOSAT_NUM_SURFACES * kBinThreads * (int)sizeof(double);
 
