@@ -226,6 +226,14 @@ int sosat_dft2_gemm_kind(const float *d_b, int n, float *d_B, int kind, void *d_
 size_t sosat_dft2_batch_workspace_bytes(int n, int batch);
 int sosat_dft2_gemm_batch(const float *d_b, int n, int batch, float *d_B, int kind,
                           void *d_workspace, size_t workspace_bytes, void *stream);
+/* The same for ZERO-PADDED fields (zero_pad, opt_analyze.py:20-32, before a2b; beam_sweep's pad):
+ * d_b [batch][n_in][n_in] is transformed as if it sat at rows / columns [pad, pad + n_in) of an
+ * n x n array of zeros, n = n_in + 2 pad; d_B [batch][n][n].  The zeros are not multiplied: both
+ * passes contract over the n_in columns of W that meet data (3/8 of the work at n = 2 n_in) and
+ * the padded input is never materialised.  Needs n padded to 128 to be a multiple of 256. */
+size_t sosat_dft2_batch_padded_workspace_bytes(int n_in, int pad, int batch);
+int sosat_dft2_gemm_batch_padded(const float *d_b, int n_in, int pad, int batch, float *d_B, int kind,
+                                 void *d_workspace, size_t workspace_bytes, void *stream);
 
 /* Zoomed far field on caller-chosen angles (the matrix-DFT form's advantage over
  * an FFT): for j, k < n_out

@@ -75,6 +75,9 @@ SIGNATURES = {
     "sosat_dft2_batch_workspace_bytes": (c_size_t, [c_int, c_int]),
     "sosat_dft2_gemm_batch": (c_int, [c_void_p, c_int, c_int, c_void_p, c_int, c_void_p, c_size_t,
                                       c_void_p]),
+    "sosat_dft2_batch_padded_workspace_bytes": (c_size_t, [c_int, c_int, c_int]),
+    "sosat_dft2_gemm_batch_padded": (c_int, [c_void_p, c_int, c_int, c_int, c_void_p, c_int, c_void_p,
+                                             c_size_t, c_void_p]),
     "sosat_dft2_zoom": (c_int, [c_void_p, c_int, c_void_p, c_int, POINTER(c_double),
                                 POINTER(c_double), POINTER(c_double), POINTER(c_double), c_double,
                                 c_void_p, c_size_t, c_void_p]),

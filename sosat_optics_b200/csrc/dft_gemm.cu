@@ -881,6 +881,36 @@ __global__ void twiddle_kernel(int n, int np, int so, int si, int sign, __nv_bfl
         }
 }
 
+// Twiddle operand of a ZERO-PADDED transform: the n_in x n_in field sits at rows / columns
+// [pad, pad + n_in) of the n x n input, everything else is zero, so only those columns of W take
+// part in either contraction:  a[2k+c][c' nip + j] = (c, c') component of W[k, pad + j], j < n_in
+// (nip = n_in padded to the tile size; rows k >= n and columns j >= n_in are zero).
+__global__ void twiddle_padded_kernel(int n, int np, int n_in, int nip, int pad, int so, int si,
+                                      int sign, __nv_bfloat16 *a_hi, __nv_bfloat16 *a_lo) {
+    const int col = blockIdx.x * blockDim.x + threadIdx.x, row = blockIdx.y;
+    if (col >= nip) return;
+    float wr = 0.f, wi = 0.f;
+    if (row < n && col < n_in) {
+        long long j = ((long long)(row - so) * (long long)(col + pad - si)) % n;
+        if (j < 0) j += n;
+        double s, c;
+        sincospi((double)sign * 2.0 * (double)j / (double)n, &s, &c);  // exact integer phase
+        wr = (float)c;
+        wi = (float)s;
+    }
+    const float vals[2][2] = {{wr, -wi}, {wi, wr}};  // [c][c']
+    const size_t ld = 2 * (size_t)nip;
+#pragma unroll
+    for (int c = 0; c < 2; ++c)
+#pragma unroll
+        for (int cp = 0; cp < 2; ++cp) {
+            __nv_bfloat16 h, l;
+            split_bf16(vals[c][cp], h, l);
+            const size_t i = (size_t)(2 * row + c) * ld + (size_t)cp * nip + col;
+            a_hi[i] = h; a_lo[i] = l;
+        }
+}
+
 // Twiddle operands of the zoomed ("matrix DFT") transform on caller-chosen angles:
 //   W1[l][n] = exp(-2 pi i y_n thy_l / lambda)   (pass 1, rows of b = y axis)
 //   W2[k][m] = exp(-2 pi i x_m thx_k / lambda)   (pass 2, columns of b = x axis)
@@ -1111,6 +1141,14 @@ struct PlanEntry {
     CUtensorMap pair[8];   // the same operands with the boxes of the CTA-pair kernel (256 x 128)
     CUtensorMap pair256[8];  // ... and of its 256 x 256 form (128-row halves of the B tile)
 };
+// the one cached plan of the zero-padded batch transform (sosat_dft2_gemm_batch_padded)
+struct PaddedPlan {
+    int device;
+    const void *ws;
+    int n_in, pad, batch, kind;
+    CUtensorMap m1[4], m2[4];
+};
+static PaddedPlan g_padded_plan = {-1, nullptr, 0, 0, 0, 0, {}, {}};
 static PlanEntry g_plans[64];
 static int g_num_plans = 0;
 static std::mutex g_plan_mutex;  // the registry is shared by all host threads of the process
@@ -1479,6 +1517,7 @@ extern "C" int sosat_dft2_forget(const void *d_workspace) {
     std::lock_guard<std::mutex> lock(g_plan_mutex);
     for (int i = 0; i < g_num_plans; ++i)
         if (g_plans[i].ws == d_workspace) g_plans[i] = g_plans[--g_num_plans], --i;
+    if (g_padded_plan.ws == d_workspace) g_padded_plan.ws = nullptr;
     return SOSAT_OK;
 }
 
@@ -1598,6 +1637,86 @@ extern "C" int sosat_dft2_gemm_batch(const float *d_b, int n, int batch, float *
 #else
     return set_error(SOSAT_ERR_UNSUPPORTED, "unreachable: the persistent pair kernel is the only batch path");
 #endif
+}
+
+// ---- batched transform of ZERO-PADDED fields -------------------------------------------------
+// A sweep zero-pads its near fields before the transform for a finer angle sampling (zero_pad,
+// opt_analyze.py:20-32; beam_sweep's `pad`).  The zeros need not be multiplied: with the field at
+// rows / columns [pad, pad + n_in) only n_in columns of W take part in either contraction, so both
+// passes run with K = 2 n_in instead of 2 n and pass 1 produces n_in instead of n columns -- the
+// same two UMMA launches on compact operands (twiddle_padded_kernel), 3/8 of the work at
+// n = 2 n_in, and the padded copy of the input is never materialised.
+static inline size_t pad256(size_t n) { return (n + 255) / 256 * 256; }
+
+static size_t padded_workspace_bytes(int n_in, int pad, int batch) {
+    const size_t np = pad128(n_in + 2 * pad), nip = pad256(n_in);
+    // twiddle [2 np][2 nip] hi/lo, X [batch nip][2 nip] hi/lo, D1 [2 np][batch nip] hi/lo
+    return 256 + 2 * (2 * np * 2 * nip * 2) + 2 * ((size_t)batch * nip * 2 * nip * 2) +
+           2 * (2 * np * (size_t)batch * nip * 2);
+}
+
+extern "C" size_t sosat_dft2_batch_padded_workspace_bytes(int n_in, int pad, int batch) {
+    return (n_in >= 1 && pad >= 0 && batch >= 1) ? padded_workspace_bytes(n_in, pad, batch) : 0;
+}
+
+extern "C" int sosat_dft2_gemm_batch_padded(const float *d_b, int n_in, int pad, int batch, float *d_B,
+                                            int kind, void *d_workspace, size_t workspace_bytes_,
+                                            void *stream) {
+    SOSAT_REQUIRE(d_b && d_B && d_workspace, "sosat_dft2_gemm_batch_padded: null pointer");
+    SOSAT_REQUIRE(n_in >= 1 && pad >= 0 && n_in + 2 * pad <= 16384, "n_in=%d pad=%d out of range", n_in, pad);
+    SOSAT_REQUIRE(batch >= 1 && batch <= 4096, "batch=%d out of range [1, 4096]", batch);
+    SOSAT_REQUIRE(((uintptr_t)d_workspace & 255) == 0, "workspace must be 256-byte aligned");
+    const int n = n_in + 2 * pad, np = pad128(n), nip = (int)pad256(n_in);
+    SOSAT_REQUIRE(np % 256 == 0 && BK == 64,
+                  "the padded batch transform needs a padded size that is a multiple of 256 (n = %d)", n);
+    SOSAT_REQUIRE(workspace_bytes_ >= padded_workspace_bytes(n_in, pad, batch),
+                  "workspace too small: %zu < %zu bytes", workspace_bytes_,
+                  padded_workspace_bytes(n_in, pad, batch));
+    int so, si, sign, dev = 0;
+    double scale;
+    if (int rc = dft_kind_params(kind, n, so, si, sign, scale)) return rc;
+    SOSAT_CUDA_OK(cudaGetDevice(&dev));
+    cudaStream_t st = (cudaStream_t)stream;
+    uint8_t *p = (uint8_t *)d_workspace + 256;
+    const size_t tw = (size_t)2 * np * 2 * nip, xs = (size_t)batch * nip * 2 * nip,
+                 ds = (size_t)2 * np * batch * nip;
+    __nv_bfloat16 *t_hi = (__nv_bfloat16 *)p, *t_lo = t_hi + tw, *x_hi = t_lo + tw, *x_lo = x_hi + xs,
+                  *d1_hi = x_lo + xs, *d1_lo = d1_hi + ds;
+    PaddedPlan pl;
+    {
+        std::lock_guard<std::mutex> lock(g_plan_mutex);
+        PaddedPlan &g = g_padded_plan;
+        if (!(g.device == dev && g.ws == d_workspace && g.n_in == n_in && g.pad == pad &&
+              g.batch == batch && g.kind == kind)) {
+            int rc = 0;
+            // pass 1: A = compact twiddle rows (l,c), B = X rows (item, m); pass 2: A = D1 viewed
+            // [np][2 nip batch] rows l, B = the same twiddle rows (k,c)
+            if ((rc = make_map(&g.m1[0], t_hi, 2 * (uint64_t)np, 2 * (uint64_t)nip, 128))) return rc;
+            if ((rc = make_map(&g.m1[1], t_lo, 2 * (uint64_t)np, 2 * (uint64_t)nip, 128))) return rc;
+            if ((rc = make_map(&g.m1[2], x_hi, (uint64_t)batch * nip, 2 * (uint64_t)nip, 128))) return rc;
+            if ((rc = make_map(&g.m1[3], x_lo, (uint64_t)batch * nip, 2 * (uint64_t)nip, 128))) return rc;
+            if ((rc = make_map(&g.m2[0], d1_hi, (uint64_t)np, 2 * (uint64_t)nip * batch, 128))) return rc;
+            if ((rc = make_map(&g.m2[1], d1_lo, (uint64_t)np, 2 * (uint64_t)nip * batch, 128))) return rc;
+            g.m2[2] = g.m1[0];
+            g.m2[3] = g.m1[1];
+            const dim3 grid((nip + 127) / 128, np);
+            twiddle_padded_kernel<<<grid, 128, 0, st>>>(n, np, n_in, nip, pad, so, si, sign, t_hi, t_lo);
+            SOSAT_CUDA_OK(cudaGetLastError());
+            g.device = dev; g.ws = d_workspace; g.n_in = n_in; g.pad = pad; g.batch = batch; g.kind = kind;
+        }
+        pl = g;
+    }
+    int rc = 0;
+    const dim3 pgrid(nip / 32, nip / 32, batch);
+    if ((rc = launch_pdl(prep_b_c64_kernel, pgrid, dim3(32, 8), 0, st, 1, 1, (const float2 *)d_b, n_in,
+                         nip, x_hi, x_lo))) return rc;
+    const int num_kb = 2 * nip / BK;
+    const PairBatch pb{nip / BK, nip * batch, np / BM, (long long)(2 * (size_t)n * n)};
+    if ((rc = launch_gemm_pair_persistent<EPI_SPLIT_BF16>(2 * np / BM, nip * batch / 256, st, pl.m1, num_kb,
+                                                          nullptr, d1_hi, d1_lo, nip * batch, 0, 1.f)))
+        return rc;
+    return launch_gemm_pair_persistent<EPI_C64>(np / BM * batch, 2 * np / 256, st, pl.m2, num_kb, d_B,
+                                                nullptr, nullptr, 0, n, (float)scale, pb);
 }
 
 extern "C" int sosat_dft2_gemm(const float *d_b, int n, float *d_B, void *d_workspace,

@@ -285,12 +285,17 @@ def far_field(b, dx_cm=None, lam_m=None, theta_x=None, theta_y=None, *, device: 
 _batch_workspaces = {}
 
 
-def far_field_batch(b, *, device: bool = False):
+def far_field_batch(b, *, device: bool = False, pad: int = 0):
     """Centred 2-D DFT of a stack of near fields ``b`` [K, N, N] (numpy complex or CUDA complex64
     tensor), e.g. all frequencies or receivers of a sweep (``near_field_binned(...).b``): one
     transpose/split kernel and one launch per UMMA pass for the whole stack, so that sizes too
     small to fill the GPU on their own (N = 1024) run on the ``cta_group::2`` pair kernel.
-    Returns ``[K, N, N]`` complex64 (numpy, or a CUDA tensor with ``device=True``)."""
+
+    ``pad``: transform every field as if ``zero_pad`` had put ``pad`` zero cells on each side
+    (finer angle sampling, output ``[K, N + 2 pad, N + 2 pad]``).  The zeros are neither stored
+    nor multiplied (``sosat_dft2_gemm_batch_padded``: both passes contract only over the N columns
+    of W that meet data -- 3/8 of the work at pad = N / 2).
+    Returns complex64 (numpy, or a CUDA tensor with ``device=True``)."""
     lib = _lib.require_gpu()
     torch = _torch()
     if isinstance(b, np.ndarray):
@@ -299,10 +304,31 @@ def far_field_batch(b, *, device: bool = False):
         d_b = b.to(device="cuda", dtype=torch.complex64).contiguous()
     if d_b.dim() != 3 or d_b.shape[1] != d_b.shape[2]:
         raise ValueError("far_field_batch expects a [K, N, N] stack of square fields")
-    k, n = int(d_b.shape[0]), int(d_b.shape[1])
+    pad = int(pad)
+    if pad < 0:
+        raise ValueError("pad must be >= 0")
+    k, n_in = int(d_b.shape[0]), int(d_b.shape[1])
+    n = n_in + 2 * pad
     out = torch.empty((k, n, n), dtype=torch.complex64, device="cuda")
     if k == 0:
         return out if device else _lib.to_numpy(out)
+    if pad > 0 and ((n + 127) // 128 * 128) % 256 == 0:
+        key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream, "pad", n_in, pad, k)
+        ws = _batch_workspaces.get(key)
+        if ws is None:
+            for old in [q for q in _batch_workspaces if q[:3] == key[:3]]:  # one padded stack per stream
+                del _batch_workspaces[old]
+            nbytes = int(lib.sosat_dft2_batch_padded_workspace_bytes(n_in, pad, k))
+            ws = torch.empty(nbytes, dtype=torch.uint8, device="cuda")
+            ptr = ws.data_ptr()
+            weakref.finalize(ws, lambda p=ptr: lib.sosat_dft2_forget(ctypes.c_void_p(p)))
+            _batch_workspaces[key] = ws
+        _lib.check(lib.sosat_dft2_gemm_batch_padded(
+            ctypes.c_void_p(d_b.data_ptr()), n_in, pad, k, ctypes.c_void_p(out.data_ptr()),
+            _lib.DFT_FORWARD, ctypes.c_void_p(ws.data_ptr()), ws.numel(), _stream(torch)))
+        return out if device else _lib.to_numpy(out)
+    if pad > 0:  # sizes the compact form does not take: materialise the zeros
+        d_b = torch.nn.functional.pad(d_b, (pad, pad, pad, pad))
     key = (torch.cuda.current_device(), torch.cuda.current_stream().cuda_stream, n, k)
     ws = _batch_workspaces.get(key)
     if ws is None:

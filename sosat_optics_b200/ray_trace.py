@@ -616,9 +616,7 @@ def beam_sweep(tele_geo, rx_list, freqs, grid_n: int = 256, extent_cm: Optional[
         b, _ = bins_to_field_device(re, im, cnt, stats, specs, sync=False)
         del re, im, cnt
         fields = b.reshape(len(rxs) * n_freq, grid_n, grid_n)
-        if pad > 0:
-            fields = torch.nn.functional.pad(fields, (pad, pad, pad, pad))
-        B = opt_analyze.far_field_batch(fields, device=True)
+        B = opt_analyze.far_field_batch(fields, device=True, pad=pad)  # the zeros are never stored
         del fields, b
         parts.append(_sweep_scalars(B, _lib.to_numpy(stats), specs, len(rxs),
                                     extent_cm / grid_n / 100.0))

@@ -412,3 +412,27 @@ def test_far_field_batch_equals_single_transforms(mods, n, k):
         ref = np.fft.fftshift(np.fft.fft2(np.fft.fftshift(b[i].astype(np.complex128))))
         assert _rel_peak(B[i], ref) < FF_TOL
     oa.release_workspaces()
+
+
+@pytest.mark.parametrize("n_in,pad", [(512, 256), (256, 128), (200, 28), (384, 64), (100, 14)])
+def test_zero_padded_batch_transform(mods, n_in, pad):
+    """far_field_batch(..., pad=p) = the plain transform of the explicitly zero-padded fields
+    (zero_pad + a2b of the reference, opt_analyze.py:20-32, 220-230) without storing or
+    multiplying the zeros: against numpy's FFT in complex128 and against the unpadded batch path;
+    sizes whose padded size is not a multiple of 256 take the explicit-padding fallback."""
+    oa, torch = mods["oa"], mods["torch"]
+    rng = np.random.default_rng(8)
+    k = 3
+    b = (rng.uniform(0, 1, (k, n_in, n_in)) * np.exp(2j * np.pi * rng.uniform(size=(k, n_in, n_in)))).astype(np.complex64)
+    out = oa.far_field_batch(b, pad=pad)
+    n = n_in + 2 * pad
+    assert out.shape == (k, n, n) and out.dtype == np.complex64
+    bp = np.pad(b.astype(np.complex128), ((0, 0), (pad, pad), (pad, pad)))
+    ref = np.fft.fftshift(np.fft.fft2(np.fft.fftshift(bp, axes=(1, 2)), axes=(1, 2)), axes=(1, 2))
+    for i in range(k):
+        assert _rel_peak(out[i], ref[i]) < FF_TOL
+    explicit = oa.far_field_batch(np.pad(b, ((0, 0), (pad, pad), (pad, pad))))
+    assert np.abs(out - explicit).max() <= 3e-5 * np.abs(explicit).max()
+    # a second stack size through the same cache slot, and a device tensor in / out
+    d = oa.far_field_batch(torch.from_numpy(b[:2]).to("cuda"), device=True, pad=pad)
+    assert d.is_cuda and np.abs(d.cpu().numpy() - out[:2]).max() <= 1e-6 * np.abs(out).max()
