@@ -501,7 +501,7 @@ def test_notebook_scattered_grid_route_end_to_end(mods):
     assert sb.n_scan == 100 and len(sb.ray_index) == len(sb.a_sim)
     sb2 = rt.sim2d(sb)
     assert np.abs(sb2.x_sim - g["sb2_x"]).max() < 1e-9 and np.abs(sb2.y_sim - g["sb2_y"]).max() < 1e-9
-    assert np.abs(sb2.a_sim - g["sb2_a"]).max() < 1e-4
+    assert np.abs(sb2.a_sim - g["sb2_a"]).max() < 6e-5      # measured 2.5e-5
     dp = np.abs(sb2.p_sim - g["sb2_p"])
     assert np.percentile(dp, 99) < 1e-2 and np.mean(dp > 1e-2) < 0.01   # the 2 pi contour cells
     assert ((sb2.a_sim == 0) == (g["sb2_a"] == 0)).mean() > 0.999       # same support
@@ -512,7 +512,8 @@ def test_notebook_scattered_grid_route_end_to_end(mods):
     x_new, y_new, beam_data = oa.zero_pad(d.x_data, d.y_data, d.a_data, 100)
     x_data, y_data, phase_data = oa.zero_pad(d.x_data, d.y_data, d.p_data, 100)
     beam_fft, phase_fft = oa.a2b(beam_data, np.rad2deg(phase_data))
-    assert np.abs(beam_fft - g["beam_fft"]).max() < 3e-4 * np.abs(g["beam_fft"]).max()
+    # measured 6.5e-5 of peak: inside the north_star's 1e-4 although the glue is ill-conditioned
+    assert np.abs(beam_fft - g["beam_fft"]).max() < 1.5e-4 * np.abs(g["beam_fft"]).max()
     x_ang, y_ang = oa.coords_spat_to_ang(x_data / 1e2, y_data / 1e2, oa.m_to_ghz(t.lambda_))
     assert abs(rt.ff_fwhm_est(beam_fft, x_ang, y_ang) - float(g["fwhm"])) < 1e-3
     assert "%.2f" % rt.ff_fwhm_est(beam_fft, x_ang, y_ang) == "21.50"
@@ -553,16 +554,19 @@ def test_notebook_1000_route_end_to_end_on_the_device(mods):
     assert len(sb.a_sim) == 15312
     sb2 = rt.sim2d(sb)
     assert np.abs(sb2.x_sim - g["sb2_x"]).max() < 1e-9
-    assert np.abs(sb2.a_sim - g["sb2_a"]).max() < 1e-4
+    assert np.abs(sb2.a_sim - g["sb2_a"]).max() < 2e-5      # measured 4e-6
+    assert np.percentile(np.abs(sb2.p_sim - g["sb2_p"]), 99) < 2e-5
     d = rt.sim_data(sb2, float(g["stage_range"]), float(g["step"]))
-    assert np.abs(np.diag(d.a_data) - g["a_data_diag"]).max() < 1e-4
+    assert np.abs(np.diag(d.a_data) - g["a_data_diag"]).max() < 1e-5
+    assert np.abs(np.diag(d.p_data) - g["p_data_diag"]).max() < 2e-5
     x_new, y_new, beam_data = oa.zero_pad(d.x_data, d.y_data, d.a_data, 100)
     x_data, y_data, phase_data = oa.zero_pad(d.x_data, d.y_data, d.p_data, 100)
     beam_fft, phase_fft = oa.a2b(beam_data, np.rad2deg(phase_data))
     assert beam_fft.shape == (1000, 1000)
     peak = abs(g["peak_value"])
     idx = g["sample_index"]
-    assert np.abs(beam_fft[idx[:, 0], idx[:, 1]] - g["sample_value"]).max() < 1e-3 * peak
+    # measured 8e-7 of peak (the reference's far field at this lattice size, reproduced end to end)
+    assert np.abs(beam_fft[idx[:, 0], idx[:, 1]] - g["sample_value"]).max() < 2e-5 * peak
     assert tuple(np.unravel_index(np.argmax(abs(beam_fft)), beam_fft.shape)) == tuple(g["peak_index"])
     x_ang, y_ang = oa.coords_spat_to_ang(x_data / 1e2, y_data / 1e2, oa.m_to_ghz(float(g["lambda_"])))
     assert "%.2f" % rt.ff_fwhm_est(beam_fft, x_ang, y_ang) == "27.53"
