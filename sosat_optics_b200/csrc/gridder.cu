@@ -24,9 +24,10 @@
 //   * the Gauss-Seidel sweeps run in a four-colour order (node (r, c) has colour (r&1, c&1); no
 //     two neighbours share one), i.e. exact Gauss-Seidel in another vertex order, converged
 //     further than scipy's 1e-6 stopping rule.
-// Agreement with the reference's own output (tests/golden/farfield_cfg2_240.npz): amplitude grid
-// 3e-5, stage-grid amplitude 8e-7, far field 8e-5 of peak, FWHM 21.5039 arcmin -- the
-// conditioning of the reference's glue under a 1e-9 cm perturbation of the rays.
+// Agreement with the reference's own output: tests/golden/farfield_cfg2_240.npz (n_scan = 100)
+// amplitude grid 2.5e-5, stage-grid amplitude 1e-6, far field 6.5e-5 of peak, FWHM 21.5039 arcmin
+// -- the conditioning of the reference's glue under a 1e-9 cm perturbation of the rays (DESIGN.md
+// 9); tests/golden/farfield_cfg2loop_1000_90ghz.npz (n_scan = 150, 1000^2 far field) 8e-7 of peak.
 #include <cmath>
 #include <cstdint>
 
